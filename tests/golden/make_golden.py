@@ -1,0 +1,166 @@
+"""Generate golden fixtures by running the UNMODIFIED reference in this container.
+
+    python tests/golden/make_golden.py        # needs /root/reference (build container only)
+
+The reference modules are imported with importlib under unique names; harness-side
+shims only (never edits the reference): ``builtins.xrange = range``, ``np.int = int``,
+a stub ``datasets`` module providing ``N_ATTRS = 18`` for celeba.  Parameters come
+from ``oracle.mvae_oracle.make_params`` (numpy RandomState stream), loaded into the
+reference ``MVAE`` with ``load_state_dict`` so the fixture does not need to carry 10 MB
+of weights.  Output: ``tests/golden/mnist_golden.npz`` and ``elementwise_golden.npz``.
+"""
+import builtins
+import importlib.util
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import mvae_oracle as O  # noqa: E402
+
+REF = os.environ.get("MVAE_REFERENCE", "/root/reference")
+warnings.filterwarnings("ignore")
+
+
+def load_ref(subdir, fname, modname, extra_modules=None):
+    """import /root/reference/<subdir>/<fname>.py as <modname>, with `model`/`datasets`
+    resolved to that directory's own files."""
+    builtins.xrange = range
+    if not hasattr(np, "int"):
+        np.int = int
+    saved = {k: sys.modules.get(k) for k in ("model", "datasets")}
+    try:
+        for k, v in (extra_modules or {}).items():
+            sys.modules[k] = v
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(REF, subdir, fname + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = mod
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def tensor_digest(t):
+    a = t.detach().double().reshape(-1)
+    return np.array([a.sum().item(), a.abs().sum().item(), a.pow(2).sum().sqrt().item()], np.float64)
+
+
+def main():
+    out = {}
+    # ---------------------------------------------------------------- mnist
+    ref_model = load_ref("mnist", "model", "ref_mnist_model")
+    ref_train = load_ref("mnist", "train", "ref_mnist_train", {"model": ref_model})
+    L, B = 64, 8
+    params = O.make_params(O.mnist_param_shapes(L), seed=0)
+    model = ref_model.MVAE(L)
+    assert [k for k, _ in model.state_dict().items()] == [k for k, _ in O.mnist_param_shapes(L)]
+    model.load_state_dict(params)
+    rs = np.random.RandomState(1234)
+    image = torch.from_numpy(rs.uniform(0, 1, size=(B, 1, 28, 28)).astype(np.float32))
+    text = torch.from_numpy(rs.randint(0, 10, size=(B,)).astype(np.int64))
+    lam_i, lam_t, beta = 1.0, 10.0, 0.5
+
+    def step(train_mode, seed=77):
+        model.train(train_mode)
+        model.zero_grad()
+        torch.manual_seed(seed)
+        r1 = model(image, text); r2 = model(image); r3 = model(text=text)
+        j = ref_train.elbo_loss(r1[0], image, r1[1], text, r1[2], r1[3], lambda_image=lam_i, lambda_text=lam_t, annealing_factor=beta)
+        i = ref_train.elbo_loss(r2[0], image, None, None, r2[2], r2[3], lambda_image=lam_i, lambda_text=lam_t, annealing_factor=beta)
+        t = ref_train.elbo_loss(None, None, r3[1], text, r3[2], r3[3], lambda_image=lam_i, lambda_text=lam_t, annealing_factor=beta)
+        loss = j + i + t
+        loss.backward()
+        return loss, (j, i, t), (r1, r2, r3)
+
+    # the three noise draws the reference makes, replayed (mnist/model.py:32: one [B,L] normal_ per forward)
+    torch.manual_seed(77)
+    noises = [torch.empty(B, L).normal_() for _ in range(3)]
+    for mode, tag in ((True, "train"), (False, "eval")):
+        loss, terms, rr = step(mode)
+        out[f"mnist_{tag}_loss"] = np.float64(loss.item())
+        out[f"mnist_{tag}_terms"] = np.array([t.item() for t in terms], np.float64)
+        for pi, r in enumerate(rr):
+            out[f"mnist_{tag}_mu{pi}"] = r[2].detach().numpy()
+            out[f"mnist_{tag}_logvar{pi}"] = r[3].detach().numpy()
+            out[f"mnist_{tag}_recon_text{pi}"] = r[1].detach().numpy()
+            out[f"mnist_{tag}_recon_image{pi}_digest"] = tensor_digest(r[0])
+            out[f"mnist_{tag}_recon_image{pi}_row0"] = r[0][0].detach().numpy()
+        for k, v in model.named_parameters():
+            out[f"mnist_{tag}_grad_digest/{k}"] = tensor_digest(v.grad)
+            out[f"mnist_{tag}_grad_head/{k}"] = v.grad.detach().reshape(-1)[:32].numpy().copy()
+            if v.grad.numel() <= 1024:
+                out[f"mnist_{tag}_grad_full/{k}"] = v.grad.detach().numpy().copy()
+    out["mnist_image"] = image.numpy(); out["mnist_text"] = text.numpy()
+    out["mnist_noises"] = torch.stack(noises).numpy()
+    out["mnist_hyper"] = np.array([lam_i, lam_t, beta], np.float64)
+    # one Adam step from the train-mode gradients (mnist/train.py:168,219)
+    step(True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt.step()
+    for k, v in model.named_parameters():
+        out[f"mnist_adam1_digest/{k}"] = tensor_digest(v)
+        out[f"mnist_adam1_head/{k}"] = v.detach().reshape(-1)[:32].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "mnist_golden.npz"), **out)
+
+    # ------------------------------------------------------- element-wise KATs
+    ew = {}
+    poeA = ref_model.ProductOfExperts()
+    celeba_ds = types.ModuleType("datasets"); celeba_ds.N_ATTRS = 18; celeba_ds.CelebAttributes = object
+    ref_celeba_model = load_ref("celeba", "model", "ref_celeba_model", {"datasets": celeba_ds})
+    tq = types.ModuleType("tqdm"); tq.tqdm = lambda x, **k: x
+    ref_celeba_train = load_ref("celeba", "train", "ref_celeba_train",
+                                {"datasets": celeba_ds, "model": ref_celeba_model, "tqdm": sys.modules.get("tqdm", tq)})
+    poeB = ref_celeba_model.ProductOfExperts()
+    rs = np.random.RandomState(99)
+    mu = torch.from_numpy(rs.standard_normal((4, 6, 16)).astype(np.float32)); mu[0] = 0
+    lv = torch.from_numpy((0.7 * rs.standard_normal((4, 6, 16))).astype(np.float32)); lv[0] = 0
+    for tag, poe in (("A", poeA), ("B", poeB)):
+        m, l = poe(mu, lv)
+        ew[f"poe{tag}_mu"] = m.numpy(); ew[f"poe{tag}_logvar"] = l.numpy()
+        m2, l2 = poe(mu[:2], lv[:2])
+        ew[f"poe{tag}_mu_2"] = m2.numpy(); ew[f"poe{tag}_logvar_2"] = l2.numpy()
+    ew["poe_in_mu"] = mu.numpy(); ew["poe_in_logvar"] = lv.numpy()
+    # SURVEY G1/G2/G3
+    g_mu = torch.tensor([0., 2., -1.]).view(3, 1, 1); g_lv = torch.tensor([0., -2., 1.]).view(3, 1, 1)
+    ew["G2"] = np.array([v.item() for v in poeA(g_mu, g_lv)]); ew["G3"] = np.array([v.item() for v in poeB(g_mu, g_lv)])
+    ew["G1"] = np.array([v.item() for v in poeA(torch.tensor([0., 1.]).view(2, 1, 1), torch.zeros(2, 1, 1))])
+    x = torch.tensor([-30., -2., 0., 0.5, 3., 30., 100.]); t = torch.tensor([0., 1., 0.5, 0.25, 1., 0., 1.])
+    ew["G4_x"] = x.numpy(); ew["G4_t"] = t.numpy()
+    ew["G4"] = ref_train.binary_cross_entropy_with_logits(x, t).numpy()
+    lg = torch.zeros(2, 10); lg[0, :3] = torch.tensor([1., 2., 3.])
+    ew["G5"] = ref_train.cross_entropy(lg, torch.tensor([2, 7])).sum(1).numpy()
+    xr = torch.from_numpy((3 * rs.standard_normal((5, 10))).astype(np.float32)); tr = torch.from_numpy(rs.randint(0, 10, 5))
+    ew["ce_x"] = xr.numpy(); ew["ce_t"] = tr.numpy(); ew["ce_out"] = ref_train.cross_entropy(xr, tr).numpy()
+    # celeba elbo (attrs column loop) on random tensors
+    Bc = 4
+    ri = torch.from_numpy(rs.standard_normal((Bc, 3, 64, 64)).astype(np.float32)); im = torch.from_numpy(rs.uniform(0, 1, (Bc, 3, 64, 64)).astype(np.float32))
+    ra = torch.from_numpy(rs.standard_normal((Bc, 18)).astype(np.float32)); at = torch.from_numpy(rs.randint(0, 2, (Bc, 18)).astype(np.float32))
+    mu_c = torch.from_numpy(rs.standard_normal((Bc, 100)).astype(np.float32)); lv_c = torch.from_numpy((0.5 * rs.standard_normal((Bc, 100))).astype(np.float32))
+    ew["celeba_recon_attrs"] = ra.numpy(); ew["celeba_attrs"] = at.numpy(); ew["celeba_mu"] = mu_c.numpy(); ew["celeba_logvar"] = lv_c.numpy()
+    ew["celeba_recon_image_seed"] = np.int64(99)
+    ew["celeba_elbo_attrs_only"] = np.float64(ref_celeba_train.elbo_loss(None, None, ra, at, mu_c, lv_c, lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.25).item())
+    ew["celeba_elbo_joint"] = np.float64(ref_celeba_train.elbo_loss(ri, im, ra, at, mu_c, lv_c, lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.25).item())
+    ew["celeba_recon_image"] = ri.numpy().astype(np.float16)  # compact; test upcasts the same way
+    ew["celeba_image"] = im.numpy().astype(np.float16)
+    ew["celeba_elbo_joint_f16in"] = np.float64(ref_celeba_train.elbo_loss(
+        torch.from_numpy(ew["celeba_recon_image"].astype(np.float32)), torch.from_numpy(ew["celeba_image"].astype(np.float32)),
+        ra, at, mu_c, lv_c, lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.25).item())
+    del ew["celeba_elbo_joint"]
+    np.savez_compressed(os.path.join(HERE, "elementwise_golden.npz"), **ew)
+    print("wrote", os.path.join(HERE, "mnist_golden.npz"), os.path.getsize(os.path.join(HERE, "mnist_golden.npz")))
+    print("wrote", os.path.join(HERE, "elementwise_golden.npz"), os.path.getsize(os.path.join(HERE, "elementwise_golden.npz")))
+
+
+if __name__ == "__main__":
+    main()
