@@ -1,0 +1,163 @@
+/* mvae_b200 -- C ABI of the B200-native MVAE training-step kernels (libmvae_b200.so).
+ *
+ * Drop-in boundary for the hot path of mhw32/multimodal-vae-public: the reference has no FFI of its
+ * own (pure Python on torch.nn / ATen), so every entry point below names the reference Python
+ * site(s) it replaces (file:line relative to the upstream repo).  All pointers are DEVICE pointers
+ * to fp32 (unless stated) owned by the caller; nothing is allocated behind the caller's back; every
+ * call only enqueues work on `stream` (cudaStream_t passed as void*) and is capturable in a CUDA
+ * graph.  Return value: 0 = ok, negative = error (see mvae_last_error()).  No C++ exceptions
+ * cross this boundary.
+ *
+ * Layout conventions: matrices are row-major with an explicit leading dimension `ld*` in ELEMENTS
+ * (ld % 4 == 0 and 16-byte aligned base pointers are required wherever a tensor is read by the
+ * tensor-core GEMM through TMA).
+ */
+#ifndef MVAE_B200_H_
+#define MVAE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVAE_OK 0
+#define MVAE_ERR_BAD_ARG (-1)
+#define MVAE_ERR_CUDA (-2)
+#define MVAE_ERR_UNSUPPORTED (-3)
+
+/* GEMM arithmetic modes (tcgen05.mma kind::tf32, fp32 accumulate in TMEM). */
+#define MVAE_PREC_TF32 0    /* one MMA per product: 10-bit mantissa operands                         */
+#define MVAE_PREC_3XTF32 1  /* hi/lo operand split in-kernel, 3 MMAs per product: fp32-class result  */
+
+/* Epilogues of mvae_gemm. */
+#define MVAE_EPI_STORE 0       /* C = acc (+ bias[n])                                               */
+#define MVAE_EPI_BIAS_SWISH 1  /* C = acc + bias[n] (pre-activation), out2 = C * sigmoid(C)         */
+#define MVAE_EPI_MUL_DSWISH 2  /* C = acc * swish'(aux[m,n])   (aux = saved pre-activation)         */
+
+#define MVAE_POE_VARIANT_A 0
+#define MVAE_POE_VARIANT_B 1
+#define MVAE_POE_NO_PRIOR 2
+
+int mvae_version(void);
+const char* mvae_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t mvae_launch_count(void);
+int mvae_device_sm_count(void);
+
+/* One GEMM problem  C[M,N] = A[M,K] * B[N,K]^T  with a fused epilogue.
+ *   a_mn_major = 0: A stored [M][K] (K contiguous, lda = row stride)
+ *   a_mn_major = 1: A stored [K][M] (M contiguous, lda = row stride)   -- same for B with N.
+ * Replaces torch addmm/mm inside nn.Linear forward and its autograd dgrad/wgrad:
+ *   mnist/model.py:75-78,95-98,117-119,136-139 (15 Linear sites), F.sigmoid*x Swish at :166-169.   */
+typedef struct {
+  const float* A; int64_t lda; int32_t a_mn_major;
+  const float* B; int64_t ldb; int32_t b_mn_major;
+  int32_t M, N, K;
+  float* C; int64_t ldc;
+  const float* bias;              /* [N] or NULL                                                    */
+  const float* aux; int64_t ldaux;/* [M,N] operand of the epilogue or NULL                          */
+  float* out2; int64_t ldout2;    /* second [M,N] output or NULL                                    */
+  int32_t epilogue;               /* MVAE_EPI_*                                                     */
+  int32_t split_k;                /* >= 1; > 1 => partial products are atomically added into C      */
+  int32_t accumulate;             /* 1 => C += result (atomic red.add), 0 => C = result             */
+} mvae_gemm_desc;
+
+/* Launch up to MVAE_GEMM_MAX_BATCH independent problems in ONE persistent kernel. */
+#define MVAE_GEMM_MAX_BATCH 4
+int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision, void* stream);
+
+/* y = x W^T + b (optionally also h = swish(y)):  nn.Linear.forward + Swish, mnist/model.py:81-84. */
+int mvae_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
+                    int64_t ldy, float* h, int64_t ldh, int M, int N, int K, int precision, void* stream);
+/* dx = dy W  (optionally * swish'(a_prev)):  autograd of nn.Linear w.r.t. its input. */
+int mvae_linear_dgrad(const float* dy, int64_t lddy, const float* w, int64_t ldw, const float* a_prev,
+                      int64_t lda_prev, float* dx, int64_t lddx, int M, int N, int K, int accumulate,
+                      int precision, void* stream);
+/* dw += dy^T x :  autograd of nn.Linear w.r.t. weight (accumulates; caller zeroes grads once per
+ * step like optimizer.zero_grad(), mnist/train.py:197). */
+int mvae_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, int64_t lddw, int M,
+                      int N, int K, int split_k, int precision, void* stream);
+/* db[n] += sum_m dy[m,n] : bias gradient. */
+int mvae_colsum_accumulate(const float* dy, int64_t lddy, float* db, int M, int N, void* stream);
+
+/* Swish forward/backward as stand-alone element-wise ops (mnist/model.py:166-169). */
+int mvae_swish_fwd(const float* x, float* y, int64_t n, void* stream);
+int mvae_swish_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+
+/* nn.Embedding(V,D) gather + Swish (mnist/model.py:116,123): a[b,:] = table[idx[b],:], h = swish(a). */
+int mvae_embedding_swish_fwd(const float* table, const int64_t* idx, float* a, float* h, int B, int D, int V,
+                             void* stream);
+/* dtable[v,:] += sum_{b: idx[b]==v} dh[b,:] * swish'(table[v,:])  (Embedding backward through Swish). */
+int mvae_embedding_swish_bwd(const float* table, const int64_t* idx, const float* dh, int64_t lddh, float* dtable,
+                             int B, int D, int V, void* stream);
+
+/* Fused ProductOfExperts + reparametrize + KL for P "passes" (modality subsets) over E encoder
+ * experts; the N(0,1) prior expert (prior_expert(), mnist/model.py:172-185) is implicit.
+ *   mu_e[e], lv_e[e] : [B, L] with row stride ld_e  (e < E <= 20)
+ *   pass_masks[p]    : bit e set => expert e present in pass p      (p < P <= 32)
+ *   z                : [P*B, L] row stride ldz, pass p at rows [p*B, (p+1)*B)
+ *   noise            : [P*B, L] N(0,1) draws or NULL.  NULL with training=1 => Philox(seed, offset)
+ *                      noise generated in-kernel and written to noise_out (must be non-NULL).
+ *   step_dev         : optional device int32 mixed into the Philox counter (so a replayed CUDA graph
+ *                      draws fresh noise every step); pass the Adam step counter.
+ *   training=0       : z = mu (MVAE.eval(), mnist/model.py:34-35)
+ *   mu_out/lv_out    : optional [P*B, L] fused posterior parameters (MVAE.infer outputs)
+ *   kl_acc           : double[P]; kl_acc[p] += sum_b KL_b (un-weighted, un-averaged), or NULL
+ *   variant          : 0 = "A" (mnist/model.py:156-163), 1 = "B" (celeba/model.py:200-207);
+ *                      | MVAE_POE_NO_PRIOR: the listed experts are the whole product (used by the
+ *                      stand-alone ProductOfExperts.forward(mu, logvar) module call)
+ * Replaces MVAE.infer's torch.cat chain + ProductOfExperts.forward + MVAE.reparametrize + the KLD
+ * line of elbo_loss (mnist/model.py:29-35,46-64,156-163; mnist/train.py:56).                       */
+int mvae_poe_fwd(const float* const* mu_e, const float* const* lv_e, int64_t ld_e, int E, const uint32_t* pass_masks,
+                 int P, int B, int L, int variant, int training, const float* noise, float* noise_out,
+                 uint64_t seed, uint64_t offset, const int32_t* step_dev, float* z, int64_t ldz, float* mu_out,
+                 float* lv_out, double* kl_acc, void* stream);
+/* Backward of the above w.r.t. every expert output, including d(beta/B * sum KL):
+ *   dz : [P*B, L] row stride lddz ;  noise: the draws used in forward (NULL iff training=0)
+ *   dmu_up, dlv_up : optional [P*B, L] upstream gradients w.r.t. the fused mu / logvar outputs
+ *   dmu_e[e], dlv_e[e] : [B, L] row stride ldd_e, OVERWRITTEN with the sum over passes
+ *   kl_scale = annealing_factor / B_global  (mnist/train.py:57: mean over the batch); if
+ *   kl_scale_dev != NULL the effective scale is kl_scale * (*kl_scale_dev) read on the device, so a
+ *   captured CUDA graph can follow the per-step KL annealing schedule (mnist/train.py:180-186).   */
+int mvae_poe_bwd(const float* const* mu_e, const float* const* lv_e, int64_t ld_e, int E, const uint32_t* pass_masks,
+                 int P, int B, int L, int variant, int training, const float* noise, const float* dz, int64_t lddz,
+                 const float* dmu_up, const float* dlv_up, float kl_scale, const float* kl_scale_dev,
+                 float* const* dmu_e, float* const* dlv_e, int64_t ldd_e, void* stream);
+
+/* KL(q(z|.) || N(0,1)) summed over all n = B*L elements (mnist/train.py:56) and its gradient:
+ *   kl_acc[0] += -0.5 * sum(1 + lv - mu^2 - exp(lv));  dmu = scale*mu;  dlogvar = scale*0.5*(exp(lv)-1). */
+int mvae_kl_fwd_bwd(const float* mu, const float* logvar, float* dmu, float* dlogvar, int64_t n, float scale,
+                    double* kl_acc, void* stream);
+
+/* Fused binary_cross_entropy_with_logits + row/batch sum + analytic gradient
+ * (mnist/train.py:62-74 and the torch.sum(dim=1)/torch.mean of :43-45,57):
+ *   x [R, D] logits (row stride ldx), target row r = t[(r % t_rows), :] (row stride ldt)
+ *   dx = scale * (sigmoid(x) - t)  written to dx (row stride lddx; may alias x)
+ *   loss_acc[r / seg_rows] += sum of BCE over row r (un-scaled), double accumulators, or NULL
+ *   (seg_rows <= 0: one accumulator for all rows; seg_rows = B keeps the passes separate)        */
+int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float* t, int64_t ldt, int t_rows, float* dx,
+                            int64_t lddx, int R, int D, float scale, double* loss_acc, int seg_rows, void* stream);
+/* Fused cross_entropy(input, target, eps=1e-6) row loss + gradient (mnist/train.py:77-94):
+ *   x [R, K] logits, target[r % t_rows] int64 class index; dx = scale*(softmax(x+eps) - onehot).   */
+int mvae_ce_fwd_bwd(const float* x, int64_t ldx, const int64_t* target, int t_rows, float* dx, int64_t lddx, int R,
+                    int K, float scale, double* loss_acc, int seg_rows, void* stream);
+
+/* Fused flat Adam over one contiguous parameter bucket (torch.optim.Adam defaults, mnist/train.py:168,219):
+ *   g is first multiplied by grad_scale (1/world_size after a sum-allreduce).
+ *   lr_mult_dev: optional device float multiplying lr.
+ *   step_count: device int32, incremented by the kernel AFTER use (1-based step = *step_count + 1). */
+int mvae_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_mult_dev,
+                   float beta1, float beta2, float eps, float grad_scale, int32_t* step_count, void* stream);
+
+/* elbo = sum_p ( recon_img[p] * lambda_image + recon_txt[p] * lambda_text + beta * kl[p] ) / B
+ * from the double accumulators above -> float32 out[0] = total, out[1..P] per pass
+ * (mnist/train.py:57-58,214); beta_dev: optional device float multiplying beta.                    */
+int mvae_elbo_finalize(const double* recon_img, const double* recon_txt, const double* kl, int P, float lambda_image,
+                       float lambda_text, float beta, const float* beta_dev, float inv_batch, float* out,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVAE_B200_H_ */

@@ -1,0 +1,547 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a (B200).
+//
+//   C[M,N] = A[M,K] * B[N,K]^T  (+ fused epilogue), fp32 in HBM, tf32 tensor-core products, fp32
+//   accumulation in TMEM.  A and B may each be K-major or MN-major in memory, so the same kernel serves
+//   nn.Linear forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without any transposed copies.
+//
+// Structure (one CTA per SM, static round-robin tile scheduler over a small batch of problems):
+//   warp 0      : TMA producer   -- cp.async.bulk.tensor 128B-swizzled boxes into a smem ring
+//   warp 1      : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N<=128, K=8 per instr)
+//   warps 2..5  : epilogue       -- tcgen05.ld TMEM -> registers -> bias / Swish / dSwish -> global
+//   warps 6..9  : operand split  -- (3xTF32 mode only) x -> hi = rna_tf32(x), lo = x - hi in smem,
+//                                   then 3 MMAs/product: hi*hi + hi*lo + lo*hi  (fp32-class accuracy)
+// Pipelines: smem full/ready/empty mbarrier ring; double-buffered TMEM accumulators (2 x 128 columns)
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Replaces: torch addmm/mm + F.sigmoid*x of the reference's Linear/Swish stacks
+// (mnist/model.py:75-78,81-84,95-98,101-105,117-119,122-125,136-139,142-146,166-169) and their autograd.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/mvae_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mvae {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N_MAX = 128;
+constexpr int BLOCK_K = 32;                                 // 32 fp32 = 128 B = one swizzle row
+constexpr int UMMA_K = 8;                                   // tf32: 32 B per MMA along K
+constexpr int OPERAND_BYTES = BLOCK_M * BLOCK_K * 4;        // 16 KiB per operand per stage
+constexpr int TMEM_COLS = 256;                              // 2 accumulator stages x 128 fp32 columns
+constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_SPLIT_WARPS = 4;
+
+template <bool kSplit>
+struct Cfg {
+  static constexpr int kStageBytes = kSplit ? 4 * OPERAND_BYTES : 2 * OPERAND_BYTES;  // 64 / 32 KiB
+  static constexpr int kStages = kSplit ? 3 : 6;                                       // 192 KiB ring
+  static constexpr int kThreads = 32 * (2 + NUM_EPI_WARPS + (kSplit ? NUM_SPLIT_WARPS : 0));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + slack for 1024 B alignment
+};
+
+struct alignas(64) GemmProblem {
+  CUtensorMap map_a;
+  CUtensorMap map_b;
+  float* C;
+  const float* bias;
+  const float* aux;
+  float* out2;
+  int64_t ldc, ldaux, ldout2;
+  int M, N, K;
+  int block_n;            // MMA N (multiple of 16, <= 128)
+  int tiles_m, tiles_n;   // output tiles
+  int split_k;            // k-range splits
+  int num_kblocks;        // ceil(K / BLOCK_K)
+  int kblocks_per_split;
+  int tile_begin;         // first global tile index of this problem
+  int a_mn, b_mn;         // operand majorness
+  // shared-memory matrix-descriptor parameters per operand (bytes; layout = UMMA LayoutType code)
+  uint32_t a_lbo, a_sbo, a_kstep, a_layout;
+  uint32_t b_lbo, b_sbo, b_kstep, b_layout;
+  int epilogue;
+  int atomic;             // accumulate with red.add instead of st
+};
+
+struct GemmBatch {
+  GemmProblem p[MVAE_GEMM_MAX_BATCH];
+  int num_problems;
+  int total_tiles;
+};
+
+struct TileInfo {
+  int prob, m_blk, n_blk, kb_begin, kb_end;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const GemmBatch& b, int t) {
+  TileInfo ti;
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < MVAE_GEMM_MAX_BATCH; ++i)
+    if (i < b.num_problems && t >= b.p[i].tile_begin) pi = i;
+  const GemmProblem& p = b.p[pi];
+  int local = t - p.tile_begin;
+  int per_split = p.tiles_m * p.tiles_n;
+  int split = local / per_split;
+  int rem = local - split * per_split;
+  ti.prob = pi;
+  ti.m_blk = rem / p.tiles_n;
+  ti.n_blk = rem - ti.m_blk * p.tiles_n;
+  ti.kb_begin = split * p.kblocks_per_split;
+  int e = ti.kb_begin + p.kblocks_per_split;
+  ti.kb_end = e < p.num_kblocks ? e : p.num_kblocks;
+  return ti;
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1").
+//  K-major  (layout 2 = SWIZZLE_128B, TMA SWIZZLE_128B): rows of 128 B (32 fp32 of K); 8-row swizzle
+//           atoms stacked at SBO = 1024 B; LBO unused; +32 B start address per K=8 slice.
+//  MN-major (layout 1 = SWIZZLE_128B_BASE32B, TMA SWIZZLE_128B_ATOM_32B -- the only MN-major layout the
+//           tensor core accepts for 32-bit operands): rows of 128 B (32 fp32 of M/N), one row per k;
+//           swizzle atoms of 4 k-rows (512 B) stacked at SBO = 512 B; next 32-wide MN chunk (next TMA
+//           box) at LBO = 4096 B; +1024 B start address per K=8 slice.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(layout & 7) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <bool kSplit>
+__global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __grid_constant__ GemmBatch batch) {
+  using C = Cfg<kSplit>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C::kStages];
+  __shared__ __align__(8) uint64_t ready_bar[C::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[C::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < batch.num_problems; ++i) {
+      ptx::prefetch_tmap(&batch.p[i].map_a);
+      ptx::prefetch_tmap(&batch.p[i].map_b);
+    }
+    for (int s = 0; s < C::kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&ready_bar[s], NUM_SPLIT_WARPS * 32);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x) {
+        const TileInfo ti = decode_tile(batch, t);
+        const GemmProblem& p = batch.p[ti.prob];
+        const int m0 = ti.m_blk * BLOCK_M;
+        const int n0 = ti.n_blk * p.block_n;
+        const uint32_t a_bytes = OPERAND_BYTES;
+        const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * BLOCK_K * 4;
+        for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + OPERAND_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn) {
+            ptx::tma_load_2d(sa, &p.map_a, &full_bar[stage], k0, m0);  // box {32 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 32; ++j)                       // 4 boxes {32 m, 32 k-rows}
+              ptx::tma_load_2d(sa + j * 4096, &p.map_a, &full_bar[stage], m0 + 32 * j, k0);
+          }
+          if (!p.b_mn) {
+            ptx::tma_load_2d(sb, &p.map_b, &full_bar[stage], k0, n0);  // box {32 k, block_n rows}
+          } else {
+            for (int j = 0; j < p.block_n / 32; ++j)
+              ptx::tma_load_2d(sb + j * 4096, &p.map_b, &full_bar[stage], n0 + 32 * j, k0);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x, ++iter) {
+        const TileInfo ti = decode_tile(batch, t);
+        const GemmProblem& p = batch.p[ti.prob];
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N_MAX;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(p.a_mn) << 15) |
+                               (static_cast<uint32_t>(p.b_mn) << 16) |
+                               (static_cast<uint32_t>(p.block_n >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
+        const uint32_t a_lbo = p.a_lbo, a_sbo = p.a_sbo, a_kstep = p.a_kstep, a_lay = p.a_layout;
+        const uint32_t b_lbo = p.b_lbo, b_sbo = p.b_sbo, b_kstep = p.b_kstep, b_lay = p.b_layout;
+        uint32_t accumulate = 0;
+        for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+          ptx::mbar_wait(kSplit ? &ready_bar[stage] : &full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+          const uint32_t sb = sa + OPERAND_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+            const uint64_t da = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t db = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lay);
+            if (kSplit) {
+              const uint64_t da_lo = make_desc(sa + 2 * OPERAND_BYTES + ks * a_kstep, a_lbo, a_sbo, a_lay);
+              const uint64_t db_lo = make_desc(sb + 2 * OPERAND_BYTES + ks * b_kstep, b_lbo, b_sbo, b_lay);
+              ptx::mma_tf32_ss(d_tmem, da_lo, db, idesc, accumulate);  // lo*hi
+              ptx::mma_tf32_ss(d_tmem, da, db_lo, idesc, 1u);          // hi*lo
+              ptx::mma_tf32_ss(d_tmem, da, db, idesc, 1u);             // hi*hi
+            } else {
+              ptx::mma_tf32_ss(d_tmem, da, db, idesc, accumulate);
+            }
+            accumulate = 1u;
+          }
+          ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp < 2 + NUM_EPI_WARPS) {
+    // ===================================================== epilogue warps
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    int iter = 0;
+    for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x, ++iter) {
+      const TileInfo ti = decode_tile(batch, t);
+      const GemmProblem& p = batch.p[ti.prob];
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      const int row = ti.m_blk * BLOCK_M + quarter * 32 + lane;
+      const int n0 = ti.n_blk * p.block_n;
+      const bool row_ok = row < p.M;
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N_MAX;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t r[32];
+        const int ncols = (p.block_n - c0) >= 32 ? 32 : 16;
+        if (ncols == 32) ptx::tmem_ld_32x32(taddr_row + c0, r);
+        else             ptx::tmem_ld_32x16(taddr_row + c0, r);
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= p.block_n) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (!row_ok) continue;
+        const int col0 = n0 + c0;
+        float* crow = p.C + static_cast<int64_t>(row) * p.ldc;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j >= ncols) break;
+          const int col = col0 + j;
+          if (col >= p.N) break;
+          float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                        __uint_as_float(r[j + 3])};
+          const bool full4 = (col + 3 < p.N);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (col + q < p.N) v[q] += __ldg(p.bias + col + q);
+          }
+          if (p.epilogue == MVAE_EPI_MUL_DSWISH) {
+            const float* arow = p.aux + static_cast<int64_t>(row) * p.ldaux + col;
+            float a[4];
+            if (full4) {
+              const float4 a4 = *reinterpret_cast<const float4*>(arow);
+              a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) a[q] = (col + q < p.N) ? arow[q] : 0.f;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float s = sigmoidf_acc(a[q]);
+              v[q] *= s * (1.0f + a[q] * (1.0f - s));
+            }
+          }
+          if (p.atomic) {
+            if (full4) ptx::red_add_v4_f32(crow + col, v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col + q < p.N) ptx::red_add_f32(crow + col + q, v[q]);
+            }
+          } else {
+            if (full4) *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
+            else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col + q < p.N) crow[col + q] = v[q];
+            }
+          }
+          if (p.epilogue == MVAE_EPI_BIAS_SWISH) {
+            float* hrow = p.out2 + static_cast<int64_t>(row) * p.ldout2 + col;
+            float h[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) h[q] = v[q] * sigmoidf_acc(v[q]);
+            if (full4) *reinterpret_cast<float4*>(hrow) = make_float4(h[0], h[1], h[2], h[3]);
+            else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (col + q < p.N) hrow[q] = h[q];
+            }
+          }
+        }
+      }
+    }
+  } else if (kSplit) {
+    // ===================================================== operand splitters (3xTF32 only)
+    const int tid = threadIdx.x - 32 * (2 + NUM_EPI_WARPS);  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x) {
+      const TileInfo ti = decode_tile(batch, t);
+      for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        float4* hi = reinterpret_cast<float4*>(smem + stage * C::kStageBytes);
+        float4* lo = hi + (2 * OPERAND_BYTES) / 16;
+#pragma unroll 4
+        for (int i = tid; i < (2 * OPERAND_BYTES) / 16; i += NUM_SPLIT_WARPS * 32) {
+          const float4 x = hi[i];
+          float4 h, l;
+          h.x = ptx::round_tf32(x.x); l.x = x.x - h.x;
+          h.y = ptx::round_tf32(x.y); l.y = x.y - h.y;
+          h.z = ptx::round_tf32(x.z); l.z = x.z - h.z;
+          h.w = ptx::round_tf32(x.w); l.w = x.w - h.w;
+          hi[i] = h;
+          lo[i] = l;
+        }
+        ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        ptx::mbar_arrive(&ready_bar[stage]);
+        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// 2-D fp32 tensor map over a row-major [rows][inner] array with row stride ld (elements).
+int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int64_t ld, int box_inner,
+             int box_rows, CUtensorMapSwizzle swizzle) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error(MVAE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0)
+    return set_error(MVAE_ERR_BAD_ARG, "GEMM operand must be 16-byte aligned with ld %% 4 == 0 (ptr=%p ld=%lld)",
+                     (const void*)base, (long long)ld);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MVAE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return MVAE_OK;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Debug knobs (environment) for the MN-major operand encoding; unset in normal operation.
+struct MnEncoding {
+  uint32_t lbo = 4096, sbo = 512, kstep = 1024, layout = 1;
+  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+};
+MnEncoding mn_encoding() {
+  MnEncoding e;
+  if (const char* v = getenv("MVAE_DBG_MN_LBO")) e.lbo = static_cast<uint32_t>(atoi(v));
+  if (const char* v = getenv("MVAE_DBG_MN_SBO")) e.sbo = static_cast<uint32_t>(atoi(v));
+  if (const char* v = getenv("MVAE_DBG_MN_KSTEP")) e.kstep = static_cast<uint32_t>(atoi(v));
+  if (const char* v = getenv("MVAE_DBG_MN_LAYOUT")) e.layout = static_cast<uint32_t>(atoi(v));
+  if (const char* v = getenv("MVAE_DBG_MN_SWIZZLE")) e.swizzle = static_cast<CUtensorMapSwizzle>(atoi(v));
+  return e;
+}
+
+}  // namespace
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision, void* stream) {
+  if (descs == nullptr || n < 1 || n > MVAE_GEMM_MAX_BATCH)
+    return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch: n must be in [1,%d]", MVAE_GEMM_MAX_BATCH);
+  if (precision != MVAE_PREC_TF32 && precision != MVAE_PREC_3XTF32)
+    return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch: unknown precision %d", precision);
+  GemmBatch batch;
+  memset(&batch, 0, sizeof(batch));
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {
+    const mvae_gemm_desc& d = descs[i];
+    GemmProblem& p = batch.p[i];
+    if (d.M < 1 || d.N < 1 || d.K < 1 || !d.A || !d.B || !d.C)
+      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: bad shape/pointer (M=%d N=%d K=%d)", i, d.M, d.N, d.K);
+    if (d.epilogue == MVAE_EPI_BIAS_SWISH && (!d.out2 || !d.bias))
+      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: BIAS_SWISH needs bias and out2", i);
+    if (d.epilogue == MVAE_EPI_MUL_DSWISH && !d.aux)
+      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: MUL_DSWISH needs aux", i);
+    if (d.epilogue < 0 || d.epilogue > MVAE_EPI_MUL_DSWISH)
+      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: unknown epilogue %d", i, d.epilogue);
+    const int split = d.split_k < 1 ? 1 : d.split_k;
+    const bool atomic = split > 1 || d.accumulate;
+    if (atomic && (d.bias || d.epilogue != MVAE_EPI_STORE))
+      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: split_k/accumulate only with plain STORE epilogue", i);
+    if ((d.ldc & 3) || (reinterpret_cast<uintptr_t>(d.C) & 15))
+      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: C must be 16B aligned with ldc %% 4 == 0", i);
+    // MMA N: multiple of 16; MN-major B is fetched in 32-wide boxes.
+    int block_n = d.N >= BLOCK_N_MAX ? BLOCK_N_MAX : round_up(d.N, d.b_mn_major ? 32 : 16);
+    p.block_n = block_n;
+    p.M = d.M; p.N = d.N; p.K = d.K;
+    p.tiles_m = (d.M + BLOCK_M - 1) / BLOCK_M;
+    p.tiles_n = (d.N + block_n - 1) / block_n;
+    p.num_kblocks = (d.K + BLOCK_K - 1) / BLOCK_K;
+    int s = split > p.num_kblocks ? p.num_kblocks : split;
+    p.kblocks_per_split = (p.num_kblocks + s - 1) / s;
+    s = (p.num_kblocks + p.kblocks_per_split - 1) / p.kblocks_per_split;  // no empty splits
+    p.split_k = s;
+    p.tile_begin = tiles;
+    tiles += p.tiles_m * p.tiles_n * s;
+    p.a_mn = d.a_mn_major ? 1 : 0;
+    p.b_mn = d.b_mn_major ? 1 : 0;
+    p.epilogue = d.epilogue;
+    p.atomic = atomic ? 1 : 0;
+    p.C = d.C; p.bias = d.bias; p.aux = d.aux; p.out2 = d.out2;
+    p.ldc = d.ldc; p.ldaux = d.ldaux; p.ldout2 = d.ldout2;
+    const MnEncoding mn = mn_encoding();
+    p.a_lbo = p.a_mn ? mn.lbo : 16u;  p.a_sbo = p.a_mn ? mn.sbo : 1024u;
+    p.a_kstep = p.a_mn ? mn.kstep : 32u;  p.a_layout = p.a_mn ? mn.layout : 2u;
+    p.b_lbo = p.b_mn ? mn.lbo : 16u;  p.b_sbo = p.b_mn ? mn.sbo : 1024u;
+    p.b_kstep = p.b_mn ? mn.kstep : 32u;  p.b_layout = p.b_mn ? mn.layout : 2u;
+    int rc;
+    if (!p.a_mn) rc = make_map(&p.map_a, d.A, d.K, d.M, d.lda, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
+    else         rc = make_map(&p.map_a, d.A, d.M, d.K, d.lda, 32, BLOCK_K, mn.swizzle);
+    if (rc) return rc;
+    if (!p.b_mn) rc = make_map(&p.map_b, d.B, d.K, d.N, d.ldb, BLOCK_K, block_n, CU_TENSOR_MAP_SWIZZLE_128B);
+    else         rc = make_map(&p.map_b, d.B, d.N, d.K, d.ldb, 32, BLOCK_K, mn.swizzle);
+    if (rc) return rc;
+  }
+  batch.num_problems = n;
+  batch.total_tiles = tiles;
+  const int sms = mvae_device_sm_count();
+  if (sms <= 0) return set_error(MVAE_ERR_CUDA, "no CUDA device");
+  const int grid = tiles < sms ? tiles : sms;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  static bool attr_set[2] = {false, false};
+  if (precision == MVAE_PREC_3XTF32) {
+    if (!attr_set[1]) {
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<true>::kSmemBytes));
+      attr_set[1] = true;
+    }
+    gemm_kernel<true><<<grid, Cfg<true>::kThreads, Cfg<true>::kSmemBytes, st>>>(batch);
+  } else {
+    if (!attr_set[0]) {
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<false>::kSmemBytes));
+      attr_set[0] = true;
+    }
+    gemm_kernel<false><<<grid, Cfg<false>::kThreads, Cfg<false>::kSmemBytes, st>>>(batch);
+  }
+  count_launch();
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  return MVAE_OK;
+}
+
+extern "C" int mvae_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
+                               int64_t ldy, float* h, int64_t ldh, int M, int N, int K, int precision,
+                               void* stream) {
+  mvae_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.A = x; d.lda = ldx; d.B = w; d.ldb = ldw; d.M = M; d.N = N; d.K = K;
+  d.C = y; d.ldc = ldy; d.bias = bias; d.out2 = h; d.ldout2 = ldh;
+  d.epilogue = h ? MVAE_EPI_BIAS_SWISH : MVAE_EPI_STORE;
+  d.split_k = 1;
+  return mvae_gemm_batch(&d, 1, precision, stream);
+}
+
+extern "C" int mvae_linear_dgrad(const float* dy, int64_t lddy, const float* w, int64_t ldw, const float* a_prev,
+                                 int64_t lda_prev, float* dx, int64_t lddx, int M, int N, int K, int accumulate,
+                                 int precision, void* stream) {
+  // dx[M,K] = dy[M,N] * W[N,K]:  A = dy (K-major over N), B[n'=K][k'=N] = W^T -> stored [N][K] => MN-major.
+  mvae_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.A = dy; d.lda = lddy; d.B = w; d.ldb = ldw; d.b_mn_major = 1;
+  d.M = M; d.N = K; d.K = N;
+  d.C = dx; d.ldc = lddx; d.aux = a_prev; d.ldaux = lda_prev;
+  d.epilogue = a_prev ? MVAE_EPI_MUL_DSWISH : MVAE_EPI_STORE;
+  d.split_k = 1; d.accumulate = accumulate;
+  return mvae_gemm_batch(&d, 1, precision, stream);
+}
+
+extern "C" int mvae_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, int64_t lddw,
+                                 int M, int N, int K, int split_k, int precision, void* stream) {
+  // dw[N,K] += dy[M,N]^T * x[M,K]:  A[m'=N][k'=M] = dy^T (MN-major), B[n'=K][k'=M] = x^T (MN-major).
+  mvae_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.A = dy; d.lda = lddy; d.a_mn_major = 1; d.B = x; d.ldb = ldx; d.b_mn_major = 1;
+  d.M = N; d.N = K; d.K = M;
+  d.C = dw; d.ldc = lddw;
+  d.epilogue = MVAE_EPI_STORE;
+  d.split_k = split_k < 1 ? 1 : split_k; d.accumulate = 1;
+  return mvae_gemm_batch(&d, 1, precision, stream);
+}

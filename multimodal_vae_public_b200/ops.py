@@ -1,0 +1,161 @@
+"""torch.Tensor-level wrappers over the C ABI (device pointers + sizes in, status out).
+
+torch is used for device memory and streams only.  Every function enqueues on the current CUDA
+stream and raises ``MvaeError`` on failure; there is no eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS_SWISH, EPI_MUL_DSWISH, EPI_STORE, GemmDesc, PREC_3XTF32, PREC_TF32  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk2d(t: torch.Tensor, name: str):
+    if t.dim() != 2 or t.dtype != torch.float32 or not t.is_cuda or t.stride(1) != 1:
+        raise _lib.MvaeError(f"{name}: expected a CUDA fp32 2-D tensor with unit inner stride, got "
+                             f"{tuple(t.shape)} {t.dtype} strides={t.stride()} device={t.device}")
+
+
+def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, out2=None, epilogue=EPI_STORE,
+              split_k=1, accumulate=False) -> GemmDesc:
+    d = GemmDesc()
+    d.A, d.lda, d.a_mn_major = A.data_ptr(), A.stride(0), int(a_mn)
+    d.B, d.ldb, d.b_mn_major = B.data_ptr(), B.stride(0), int(b_mn)
+    d.M, d.N, d.K = M, N, K
+    d.C, d.ldc = Cmat.data_ptr(), Cmat.stride(0)
+    d.bias = _p(bias)
+    d.aux, d.ldaux = _p(aux), (aux.stride(0) if aux is not None else 0)
+    d.out2, d.ldout2 = _p(out2), (out2.stride(0) if out2 is not None else 0)
+    d.epilogue, d.split_k, d.accumulate = epilogue, split_k, int(accumulate)
+    return d
+
+
+def gemm_batch(descs: Sequence[GemmDesc], precision: int = PREC_3XTF32) -> None:
+    arr = (GemmDesc * len(descs))(*descs)
+    _lib.check(_lib.load().mvae_gemm_batch(arr, len(descs), precision, _stream()), "mvae_gemm_batch")
+
+
+def linear_fwd(x, w, bias, y, h=None, precision=PREC_3XTF32):
+    """y = x @ w.T + bias ; optionally h = swish(y)."""
+    _chk2d(x, "x"); _chk2d(w, "w"); _chk2d(y, "y")
+    M, K = x.shape
+    N = w.shape[0]
+    _lib.check(_lib.load().mvae_linear_fwd(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias), y.data_ptr(),
+                                           y.stride(0), _p(h), h.stride(0) if h is not None else 0, M, N, K, precision,
+                                           _stream()), "mvae_linear_fwd")
+
+
+def linear_dgrad(dy, w, dx, a_prev=None, accumulate=False, precision=PREC_3XTF32):
+    """dx = dy @ w  (optionally * swish'(a_prev))."""
+    _chk2d(dy, "dy"); _chk2d(w, "w"); _chk2d(dx, "dx")
+    M, N = dy.shape
+    K = w.shape[1]
+    _lib.check(_lib.load().mvae_linear_dgrad(dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0), _p(a_prev),
+                                             a_prev.stride(0) if a_prev is not None else 0, dx.data_ptr(), dx.stride(0),
+                                             M, N, K, int(accumulate), precision, _stream()), "mvae_linear_dgrad")
+
+
+def linear_wgrad(dy, x, dw, split_k=1, precision=PREC_3XTF32):
+    """dw += dy.T @ x."""
+    _chk2d(dy, "dy"); _chk2d(x, "x"); _chk2d(dw, "dw")
+    M, N = dy.shape
+    K = x.shape[1]
+    _lib.check(_lib.load().mvae_linear_wgrad(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dw.data_ptr(),
+                                             dw.stride(0), M, N, K, split_k, precision, _stream()), "mvae_linear_wgrad")
+
+
+def colsum_accumulate(dy, db):
+    _chk2d(dy, "dy")
+    M, N = dy.shape
+    _lib.check(_lib.load().mvae_colsum_accumulate(dy.data_ptr(), dy.stride(0), db.data_ptr(), M, N, _stream()),
+               "mvae_colsum_accumulate")
+
+
+def swish_fwd(x, y):
+    _lib.check(_lib.load().mvae_swish_fwd(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "mvae_swish_fwd")
+
+
+def swish_bwd(x, dy, dx):
+    _lib.check(_lib.load().mvae_swish_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), _stream()),
+               "mvae_swish_bwd")
+
+
+def embedding_swish_fwd(table, idx, a, h):
+    B = idx.numel()
+    V, D = table.shape
+    _lib.check(_lib.load().mvae_embedding_swish_fwd(table.data_ptr(), idx.data_ptr(), _p(a), h.data_ptr(), B, D, V,
+                                                    _stream()), "mvae_embedding_swish_fwd")
+
+
+def embedding_swish_bwd(table, idx, dh, dtable):
+    B = idx.numel()
+    V, D = table.shape
+    _lib.check(_lib.load().mvae_embedding_swish_bwd(table.data_ptr(), idx.data_ptr(), dh.data_ptr(), dh.stride(0),
+                                                    dtable.data_ptr(), B, D, V, _stream()), "mvae_embedding_swish_bwd")
+
+
+def _ptr_array(ts):
+    return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def poe_fwd(mu_e, lv_e, masks, B, L, z, variant=0, training=True, noise=None, noise_out=None, seed=0, offset=0,
+            step_dev=None, mu_out=None, lv_out=None, kl_acc=None):
+    E, P = len(mu_e), len(masks)
+    m = (C.c_uint32 * P)(*masks)
+    _lib.check(_lib.load().mvae_poe_fwd(_ptr_array(mu_e), _ptr_array(lv_e), mu_e[0].stride(0), E, m, P, B, L, variant,
+                                        int(training), _p(noise), _p(noise_out), seed, offset, _p(step_dev), z.data_ptr(),
+                                        z.stride(0),
+                                        _p(mu_out), _p(lv_out), _p(kl_acc), _stream()), "mvae_poe_fwd")
+
+
+def poe_bwd(mu_e, lv_e, masks, B, L, dz, dmu_e, dlv_e, kl_scale, variant=0, training=True, noise=None,
+            kl_scale_dev=None, dmu_up=None, dlv_up=None):
+    E, P = len(mu_e), len(masks)
+    m = (C.c_uint32 * P)(*masks)
+    _lib.check(_lib.load().mvae_poe_bwd(_ptr_array(mu_e), _ptr_array(lv_e), mu_e[0].stride(0), E, m, P, B, L, variant,
+                                        int(training), _p(noise), dz.data_ptr(), dz.stride(0), _p(dmu_up), _p(dlv_up),
+                                        float(kl_scale), _p(kl_scale_dev), _ptr_array(dmu_e), _ptr_array(dlv_e), dmu_e[0].stride(0),
+                                        _stream()), "mvae_poe_bwd")
+
+
+def kl_fwd_bwd(mu, logvar, dmu, dlogvar, scale, kl_acc=None):
+    _lib.check(_lib.load().mvae_kl_fwd_bwd(mu.data_ptr(), logvar.data_ptr(), _p(dmu), _p(dlogvar), mu.numel(),
+                                           float(scale), _p(kl_acc), _stream()), "mvae_kl_fwd_bwd")
+
+
+def bce_logits_fwd_bwd(x, t, dx, scale, loss_acc=None, seg_rows=0):
+    """x [R,D] logits, t [t_rows,D] targets (row r uses t[r % t_rows])."""
+    R, D = x.shape
+    _lib.check(_lib.load().mvae_bce_logits_fwd_bwd(x.data_ptr(), x.stride(0), t.data_ptr(), t.stride(0), t.shape[0],
+                                                   _p(dx), dx.stride(0) if dx is not None else 0, R, D, float(scale),
+                                                   _p(loss_acc), seg_rows, _stream()), "mvae_bce_logits_fwd_bwd")
+
+
+def ce_fwd_bwd(x, target, dx, K, scale, loss_acc=None, seg_rows=0):
+    R = x.shape[0]
+    _lib.check(_lib.load().mvae_ce_fwd_bwd(x.data_ptr(), x.stride(0), target.data_ptr(), target.numel(), _p(dx),
+                                           dx.stride(0) if dx is not None else 0, R, K, float(scale), _p(loss_acc),
+                                           seg_rows, _stream()), "mvae_ce_fwd_bwd")
+
+
+def adam_flat(p, g, m, v, step_count, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, lr_mult_dev=None):
+    _lib.check(_lib.load().mvae_adam_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
+                                          _p(lr_mult_dev), beta1, beta2, eps, grad_scale, step_count.data_ptr(),
+                                          _stream()), "mvae_adam_flat")
+
+
+def elbo_finalize(recon_img, recon_txt, kl, P, lambda_image, lambda_text, beta, inv_batch, out, beta_dev=None):
+    _lib.check(_lib.load().mvae_elbo_finalize(_p(recon_img), _p(recon_txt), _p(kl), P, lambda_image, lambda_text, beta,
+                                              _p(beta_dev), inv_batch, out.data_ptr(), _stream()), "mvae_elbo_finalize")

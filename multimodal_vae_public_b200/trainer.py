@@ -1,0 +1,381 @@
+"""Fused MVAE training step for the MNIST-flavour (MLP) model on one B200 (one process per GPU).
+
+This is the hot path the benchmark measures: the whole body of the reference's training loop
+(mnist/train.py:196-219: zero_grad -> model(image,text), model(image), model(text=text) -> three
+elbo_loss terms -> sum -> backward -> Adam.step) as ~35 kernel launches of libmvae_b200.so over
+pre-allocated HBM buffers, captured once in a CUDA graph and replayed per step.
+
+Work the reference does that cannot change the result is not executed:
+  * the image/text encoders run once and feed both the joint and the uni-modal pass
+    (no BatchNorm/Dropout in this flavour, so the duplicate evaluations are bit-identical);
+  * the decoder whose output the loss ignores (text decoder in the image-only pass, image decoder in
+    the text-only pass) is skipped: its output has zero gradient and is not part of the objective.
+The three passes are stacked along the batch so each decoder layer is ONE GEMM over 2B rows.
+
+Layout in HBM (fp32, row-major; B = per-rank batch, L = n_latents):
+  flat arenas  params / grads / adam_m / adam_v   one contiguous bucket each (single NCCL all-reduce
+               and single fused Adam over the bucket); the nn.Parameter views of the drop-in module
+               alias `params`, their .grad alias `grads`.
+  Z [3B, L]    rows [0,B) image-only pass, [B,2B) joint pass, [2B,3B) text-only pass, so the image
+               decoder reads rows [0,2B) and the text decoder rows [B,3B) with no gather/concat.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+from ._lib import PREC_3XTF32, PREC_TF32
+
+# internal pass order (rows of Z) and the reference's order (joint, image, text) [mnist/train.py:200-202]
+_PASS_MASKS = (0b01, 0b11, 0b10)        # expert 0 = image encoder, expert 1 = text encoder
+_REF_TO_INTERNAL = (1, 0, 2)            # reference pass i lives at internal index _REF_TO_INTERNAL[i]
+
+
+def mnist_layout(n_latents: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Arena order of the MNIST MVAE parameters (names = reference state_dict keys,
+    mnist/model.py:75-78,95-98,116-119,136-139).  fc31/fc32 are adjacent so that the two encoder heads
+    run as one N = 2L GEMM."""
+    L = n_latents
+    out = []
+    for enc, first in (("image_encoder", ("fc1", (512, 784))), ("text_encoder", ("fc1", (10, 512)))):
+        out.append((f"{enc}.{first[0]}.weight", first[1]))
+        if enc == "image_encoder":
+            out.append((f"{enc}.fc1.bias", (512,)))
+        out += [(f"{enc}.fc2.weight", (512, 512)), (f"{enc}.fc2.bias", (512,)),
+                (f"{enc}.fc31.weight", (L, 512)), (f"{enc}.fc32.weight", (L, 512)),
+                (f"{enc}.fc31.bias", (L,)), (f"{enc}.fc32.bias", (L,))]
+    for dec, n_out in (("image_decoder", 784), ("text_decoder", 10)):
+        out += [(f"{dec}.fc1.weight", (512, L)), (f"{dec}.fc1.bias", (512,)),
+                (f"{dec}.fc2.weight", (512, 512)), (f"{dec}.fc2.bias", (512,)),
+                (f"{dec}.fc3.weight", (512, 512)), (f"{dec}.fc3.bias", (512,)),
+                (f"{dec}.fc4.weight", (n_out, 512)), (f"{dec}.fc4.bias", (n_out,))]
+    return out
+
+
+def mnist_reference_order(n_latents: int) -> List[str]:
+    """state_dict key order of the reference MVAE (registration order of mnist/model.py:20-27,75-78,...)."""
+    keys = []
+    for mod, layers in (("image_encoder", ("fc1", "fc2", "fc31", "fc32")), ("image_decoder", ("fc1", "fc2", "fc3", "fc4")),
+                        ("text_encoder", ("fc1", "fc2", "fc31", "fc32")), ("text_decoder", ("fc1", "fc2", "fc3", "fc4"))):
+        for l in layers:
+            keys.append(f"{mod}.{l}.weight")
+            if not (mod == "text_encoder" and l == "fc1"):
+                keys.append(f"{mod}.{l}.bias")
+    return keys
+
+
+class FlatArena:
+    """One contiguous fp32 bucket with named, 16-byte aligned views."""
+
+    def __init__(self, layout: Sequence[Tuple[str, Tuple[int, ...]]], device, n_buffers: int = 1):
+        self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in layout:
+            n = int(math.prod(shape))
+            self.offsets[name] = (off, tuple(shape))
+            off += (n + 3) // 4 * 4
+        self.numel = off
+        self.buffers = [torch.zeros(off, dtype=torch.float32, device=device) for _ in range(n_buffers)]
+
+    def view(self, buf: int, name: str) -> torch.Tensor:
+        off, shape = self.offsets[name]
+        return self.buffers[buf][off: off + int(math.prod(shape))].view(shape)
+
+    def span(self, buf: int, first: str, last: str) -> torch.Tensor:
+        """Contiguous 1-D slice covering parameters first..last (inclusive) -- they must be adjacent."""
+        o0, _ = self.offsets[first]
+        o1, s1 = self.offsets[last]
+        return self.buffers[buf][o0: o1 + int(math.prod(s1))]
+
+
+class MnistMVAETrainer:
+    """Whole-step trainer (MNIST flavour).  ``step(image, text)`` == one iteration of the reference loop."""
+
+    def __init__(self, n_latents: int = 64, batch_size: int = 4096, device="cuda", lr: float = 1e-3,
+                 lambda_image: float = 1.0, lambda_text: float = 10.0, precision: int = PREC_3XTF32,
+                 world_size: int = 1, seed: int = 0, rank: int = 0, use_graph: bool = True,
+                 process_group=None):
+        _lib.load()  # fail loudly if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise _lib.MvaeError("MnistMVAETrainer needs a CUDA device (no CPU fallback)")
+        self.L, self.B = n_latents, batch_size
+        if n_latents % 4:
+            raise _lib.MvaeError("n_latents must be a multiple of 4")
+        self.dev = torch.device(device)
+        self.lr, self.lam_i, self.lam_t = lr, lambda_image, lambda_text
+        self.prec = precision
+        self.world, self.rank, self.seed = world_size, rank, seed
+        self.pg = process_group
+        self.use_graph = use_graph
+        self.layout = mnist_layout(n_latents)
+        self.arena = FlatArena(self.layout, self.dev, n_buffers=4)  # params, grads, adam m, adam v
+        self.params = {k: self.arena.view(0, k) for k, _ in self.layout}
+        self.grads = {k: self.arena.view(1, k) for k, _ in self.layout}
+        self.flat_params, self.flat_grads, self.adam_m, self.adam_v = self.arena.buffers
+        B, L, dev = batch_size, n_latents, self.dev
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
+        # inputs (device-resident copies; step() fills them from host or device tensors)
+        self.x = f(B, 784)
+        self.text = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.noise = f(3 * B, L)           # internal pass order
+        # encoders
+        self.ie_a1, self.ie_h1, self.ie_a2, self.ie_h2 = f(B, 512), f(B, 512), f(B, 512), f(B, 512)
+        self.te_h1, self.te_a2, self.te_h2 = f(B, 512), f(B, 512), f(B, 512)
+        self.enc_i, self.enc_t = f(B, 2 * L), f(B, 2 * L)
+        self.Z = f(3 * B, L)
+        # decoders (2B rows each)
+        self.id_a = [f(2 * B, 512) for _ in range(3)]; self.id_h = [f(2 * B, 512) for _ in range(3)]
+        self.td_a = [f(2 * B, 512) for _ in range(3)]; self.td_h = [f(2 * B, 512) for _ in range(3)]
+        self.logit_i = f(2 * B, 784)
+        self.logit_t_buf = f(2 * B, 16)    # N = 10 padded to ld 16 for TMA
+        self.logit_t = self.logit_t_buf[:, :10]
+        # backward scratch
+        self.id_dA = [f(2 * B, 512) for _ in range(2)]; self.td_dA = [f(2 * B, 512) for _ in range(2)]
+        self.ie_dA = [f(B, 512) for _ in range(2)]; self.te_dA = [f(B, 512) for _ in range(2)]
+        self.d_enc_i, self.d_enc_t = f(B, 2 * L), f(B, 2 * L)
+        # one zero-initialised region per step: dZ + loss accumulators
+        self.dZ = torch.zeros(3 * B, L, dtype=torch.float32, device=dev)
+        self.acc = torch.zeros(9, dtype=torch.float64, device=dev)  # recon_img[3], recon_txt[3], kl[3]
+        self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)  # total, internal passes 0..2
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.beta_dev = torch.ones(1, dtype=torch.float32, device=dev)   # KL annealing factor
+        self.beta_host = torch.ones(1, dtype=torch.float32).pin_memory()
+        self.loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self._graphs: Dict[Tuple[bool, bool], object] = {}
+        self._stream = torch.cuda.Stream(device=dev)
+        self.launches_per_step = 0
+        self.init_parameters(seed)
+
+    # ------------------------------------------------------------------ parameters
+    def init_parameters(self, seed: int = 0) -> None:
+        """PyTorch-default initialisation scales (nn.Linear: U(+-1/sqrt(fan_in)); nn.Embedding: N(0,1))."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        for name, shape in self.layout:
+            if name == "text_encoder.fc1.weight":
+                v = torch.randn(shape, generator=g)
+            else:
+                wname = name.replace(".bias", ".weight")
+                fan_in = dict(self.layout)[wname][1]
+                bound = 1.0 / math.sqrt(fan_in)
+                v = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            self.params[name].copy_(v)
+        self.adam_m.zero_(); self.adam_v.zero_(); self.step_count.zero_()
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        missing = [k for k, _ in self.layout if k not in sd]
+        if missing:
+            raise KeyError(f"missing keys: {missing}")
+        for k, _ in self.layout:
+            self.params[k].copy_(sd[k].to(torch.float32))
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Copies of the parameters under the reference's state_dict keys, in the reference's order
+        (mnist/model.py:20-27), so ``ref_model.load_state_dict(trainer.state_dict())`` works."""
+        return {k: self.params[k].detach().clone() for k in mnist_reference_order(self.L)}
+
+    # ------------------------------------------------------------------ one step worth of launches
+    def _p(self, name):
+        return self.params[name]
+
+    def _g(self, name):
+        return self.grads[name]
+
+    def _enqueue_forward(self, training: bool, use_noise_input: bool) -> None:
+        B, L, P = self.B, self.L, self.prec
+        p = self.params
+        # image encoder fc1 (+ text embedding in parallel on the same stream)
+        ops.linear_fwd(self.x, p["image_encoder.fc1.weight"], p["image_encoder.fc1.bias"], self.ie_a1, self.ie_h1, P)
+        ops.embedding_swish_fwd(p["text_encoder.fc1.weight"], self.text, None, self.te_h1)
+        ops.gemm_batch([
+            ops.gemm_desc(self.ie_h1, p["image_encoder.fc2.weight"], self.ie_a2, B, 512, 512,
+                          bias=p["image_encoder.fc2.bias"], out2=self.ie_h2, epilogue=ops.EPI_BIAS_SWISH),
+            ops.gemm_desc(self.te_h1, p["text_encoder.fc2.weight"], self.te_a2, B, 512, 512,
+                          bias=p["text_encoder.fc2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)], P)
+        wi = self.arena.span(0, "image_encoder.fc31.weight", "image_encoder.fc32.weight").view(2 * L, 512)
+        bi = self.arena.span(0, "image_encoder.fc31.bias", "image_encoder.fc32.bias")
+        wt = self.arena.span(0, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512)
+        bt = self.arena.span(0, "text_encoder.fc31.bias", "text_encoder.fc32.bias")
+        ops.gemm_batch([ops.gemm_desc(self.ie_h2, wi, self.enc_i, B, 2 * L, 512, bias=bi),
+                        ops.gemm_desc(self.te_h2, wt, self.enc_t, B, 2 * L, 512, bias=bt)], P)
+        # PoE + reparametrise + KL for the three passes
+        mu_e = [self.enc_i[:, :L], self.enc_t[:, :L]]
+        lv_e = [self.enc_i[:, L:], self.enc_t[:, L:]]
+        ops.poe_fwd(mu_e, lv_e, _PASS_MASKS, B, L, self.Z, variant=0, training=training,
+                    noise=self.noise if (training and use_noise_input) else None,
+                    noise_out=self.noise if (training and not use_noise_input) else None,
+                    seed=self.seed * 1000003 + self.rank, offset=0, step_dev=self.step_count,
+                    kl_acc=self.acc[6:9])
+        # decoders: image decoder on rows [0,2B) (image-only, joint), text decoder on rows [B,3B) (joint, text-only)
+        zi, zt = self.Z[: 2 * B], self.Z[B:]
+        xin_i, xin_t = zi, zt
+        for l in range(3):
+            K = L if l == 0 else 512
+            ops.gemm_batch([
+                ops.gemm_desc(xin_i, p[f"image_decoder.fc{l + 1}.weight"], self.id_a[l], 2 * B, 512, K,
+                              bias=p[f"image_decoder.fc{l + 1}.bias"], out2=self.id_h[l], epilogue=ops.EPI_BIAS_SWISH),
+                ops.gemm_desc(xin_t, p[f"text_decoder.fc{l + 1}.weight"], self.td_a[l], 2 * B, 512, K,
+                              bias=p[f"text_decoder.fc{l + 1}.bias"], out2=self.td_h[l], epilogue=ops.EPI_BIAS_SWISH)], P)
+            xin_i, xin_t = self.id_h[l], self.td_h[l]
+        ops.gemm_batch([
+            ops.gemm_desc(xin_i, p["image_decoder.fc4.weight"], self.logit_i, 2 * B, 784, 512, bias=p["image_decoder.fc4.bias"]),
+            ops.gemm_desc(xin_t, p["text_decoder.fc4.weight"], self.logit_t, 2 * B, 10, 512, bias=p["text_decoder.fc4.bias"])], P)
+
+    def _enqueue_loss_and_backward(self, training: bool, b_global: int) -> None:
+        B, L, P = self.B, self.L, self.prec
+        p, g = self.params, self.grads
+        # reconstruction losses + dlogits (in place)
+        ops.bce_logits_fwd_bwd(self.logit_i, self.x, self.logit_i, self.lam_i / b_global, self.acc[0:3], seg_rows=B)
+        ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)
+        # ---- decoders backward, the two decoders batched per layer
+        dyi, dyt = self.logit_i, self.logit_t
+        nk = max(1, (2 * B) // 32)  # k-blocks of a decoder wgrad
+        for l in (4, 3, 2, 1):
+            n_i = 784 if l == 4 else 512
+            n_t = 10 if l == 4 else 512
+            K = L if l == 1 else 512
+            x_i = self.Z[: 2 * B] if l == 1 else self.id_h[l - 2]
+            x_t = self.Z[B:] if l == 1 else self.td_h[l - 2]
+            ops.colsum_accumulate(dyi, g[f"image_decoder.fc{l}.bias"])
+            ops.colsum_accumulate(dyt, g[f"text_decoder.fc{l}.bias"])
+            split = max(1, min(nk // 8, 8))
+            descs = [
+                ops.gemm_desc(dyi, x_i, g[f"image_decoder.fc{l}.weight"], n_i, K, 2 * B, a_mn=True, b_mn=True,
+                              split_k=split, accumulate=True),
+                ops.gemm_desc(dyt, x_t, g[f"text_decoder.fc{l}.weight"], n_t, K, 2 * B, a_mn=True, b_mn=True,
+                              split_k=split, accumulate=True)]
+            if l > 1:
+                dxi, dxt = self.id_dA[l % 2], self.td_dA[l % 2]
+                descs += [
+                    ops.gemm_desc(dyi, p[f"image_decoder.fc{l}.weight"], dxi, 2 * B, K, n_i, b_mn=True,
+                                  aux=self.id_a[l - 2], epilogue=ops.EPI_MUL_DSWISH),
+                    ops.gemm_desc(dyt, p[f"text_decoder.fc{l}.weight"], dxt, 2 * B, K, n_t, b_mn=True,
+                                  aux=self.td_a[l - 2], epilogue=ops.EPI_MUL_DSWISH)]
+            else:  # dZ is zero-initialised; both decoders add into it (the joint rows get both)
+                dxi, dxt = self.dZ[: 2 * B], self.dZ[B:]
+                descs += [
+                    ops.gemm_desc(dyi, p["image_decoder.fc1.weight"], dxi, 2 * B, K, n_i, b_mn=True, accumulate=True),
+                    ops.gemm_desc(dyt, p["text_decoder.fc1.weight"], dxt, 2 * B, K, n_t, b_mn=True, accumulate=True)]
+            ops.gemm_batch(descs, P)
+            dyi, dyt = dxi, dxt
+        # ---- PoE / reparam / KL backward -> gradients of both encoders' outputs (summed over passes)
+        mu_e = [self.enc_i[:, :L], self.enc_t[:, :L]]
+        lv_e = [self.enc_i[:, L:], self.enc_t[:, L:]]
+        dmu = [self.d_enc_i[:, :L], self.d_enc_t[:, :L]]
+        dlv = [self.d_enc_i[:, L:], self.d_enc_t[:, L:]]
+        ops.poe_bwd(mu_e, lv_e, _PASS_MASKS, B, L, self.dZ, dmu, dlv, kl_scale=1.0 / b_global, variant=0,
+                    training=training, noise=self.noise if training else None, kl_scale_dev=self.beta_dev)
+        # ---- encoders backward
+        nk = max(1, B // 32)
+        split = max(1, min(nk // 8, 8))
+        arena = self.arena
+        gwi = arena.span(1, "image_encoder.fc31.weight", "image_encoder.fc32.weight").view(2 * L, 512)
+        gbi = arena.span(1, "image_encoder.fc31.bias", "image_encoder.fc32.bias")
+        gwt = arena.span(1, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512)
+        gbt = arena.span(1, "text_encoder.fc31.bias", "text_encoder.fc32.bias")
+        wi = arena.span(0, "image_encoder.fc31.weight", "image_encoder.fc32.weight").view(2 * L, 512)
+        wt = arena.span(0, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512)
+        ops.colsum_accumulate(self.d_enc_i, gbi)
+        ops.colsum_accumulate(self.d_enc_t, gbt)
+        ops.gemm_batch([
+            ops.gemm_desc(self.d_enc_i, self.ie_h2, gwi, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True),
+            ops.gemm_desc(self.d_enc_t, self.te_h2, gwt, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True),
+            ops.gemm_desc(self.d_enc_i, wi, self.ie_dA[0], B, 512, 2 * L, b_mn=True, aux=self.ie_a2, epilogue=ops.EPI_MUL_DSWISH),
+            ops.gemm_desc(self.d_enc_t, wt, self.te_dA[0], B, 512, 2 * L, b_mn=True, aux=self.te_a2, epilogue=ops.EPI_MUL_DSWISH)], P)
+        ops.colsum_accumulate(self.ie_dA[0], g["image_encoder.fc2.bias"])
+        ops.colsum_accumulate(self.te_dA[0], g["text_encoder.fc2.bias"])
+        ops.gemm_batch([
+            ops.gemm_desc(self.ie_dA[0], self.ie_h1, g["image_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
+                          split_k=split, accumulate=True),
+            ops.gemm_desc(self.te_dA[0], self.te_h1, g["text_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
+                          split_k=split, accumulate=True),
+            ops.gemm_desc(self.ie_dA[0], p["image_encoder.fc2.weight"], self.ie_dA[1], B, 512, 512, b_mn=True,
+                          aux=self.ie_a1, epilogue=ops.EPI_MUL_DSWISH),
+            ops.gemm_desc(self.te_dA[0], p["text_encoder.fc2.weight"], self.te_dA[1], B, 512, 512, b_mn=True)], P)
+        ops.colsum_accumulate(self.ie_dA[1], g["image_encoder.fc1.bias"])
+        ops.gemm_batch([ops.gemm_desc(self.ie_dA[1], self.x, g["image_encoder.fc1.weight"], 512, 784, B, a_mn=True,
+                                      b_mn=True, split_k=split, accumulate=True)], P)
+        ops.embedding_swish_bwd(p["text_encoder.fc1.weight"], self.text, self.te_dA[1], g["text_encoder.fc1.weight"])
+
+    def _enqueue_step(self, training: bool, use_noise_input: bool, update: bool) -> None:
+        b_global = self.B * self.world
+        self.flat_grads.zero_()
+        self.dZ.zero_()
+        self.acc.zero_()
+        self._enqueue_forward(training, use_noise_input)
+        self._enqueue_loss_and_backward(training, b_global)
+        ops.elbo_finalize(self.acc[0:3], self.acc[3:6], self.acc[6:9], 3, self.lam_i, self.lam_t, 1.0, 1.0 / b_global,
+                          self.loss_out, beta_dev=self.beta_dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat_grads, group=self.pg)
+            dist.all_reduce(self.loss_out, group=self.pg)
+        if update:
+            ops.adam_flat(self.flat_params, self.flat_grads, self.adam_m, self.adam_v, self.step_count, lr=self.lr)
+
+    # ------------------------------------------------------------------ public API
+    def set_inputs(self, image: torch.Tensor, text: torch.Tensor, noise: Optional[torch.Tensor] = None,
+                   annealing_factor: float = 1.0) -> None:
+        """Stage one batch (host or device tensors) into the device-resident input buffers on the step stream.
+        ``noise``: optional [3,B,L] N(0,1) draws in the REFERENCE's pass order (joint, image, text)."""
+        B, L = self.B, self.L
+        with torch.cuda.stream(self._stream):
+            self.x.copy_(image.reshape(B, 784), non_blocking=True)
+            self.text.copy_(text.reshape(B), non_blocking=True)
+            self.beta_host[0] = float(annealing_factor)
+            self.beta_dev.copy_(self.beta_host, non_blocking=True)
+            if noise is not None:
+                nz = self.noise.view(3, B, L)
+                for ref_i, int_i in enumerate(_REF_TO_INTERNAL):
+                    nz[int_i].copy_(noise[ref_i], non_blocking=True)
+
+    def run(self, training: bool = True, noise_given: bool = False, update: bool = True) -> None:
+        """Enqueue one step (graph replay when enabled).  Does not synchronise."""
+        key = (training, noise_given, update)
+        with torch.cuda.stream(self._stream):
+            if not self.use_graph:
+                n0 = _lib.launch_count()
+                self._enqueue_step(training, noise_given, update)
+                self.launches_per_step = _lib.launch_count() - n0
+                return
+            gr = self._graphs.get(key)
+            if gr is None:
+                # warm-up once eagerly (sets func attributes, loads modules), then capture
+                saved = (self.flat_params.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count.clone())
+                self._enqueue_step(training, noise_given, update)
+                self._stream.synchronize()
+                self.flat_params.copy_(saved[0]); self.adam_m.copy_(saved[1]); self.adam_v.copy_(saved[2])
+                self.step_count.copy_(saved[3])
+                self._stream.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(gr, stream=self._stream):
+                    self._enqueue_step(training, noise_given, update)
+                self.launches_per_step = _lib.launch_count() - n0
+                self._graphs[key] = gr
+            gr.replay()
+
+    def step(self, image: torch.Tensor, text: torch.Tensor, annealing_factor: float = 1.0,
+             noise: Optional[torch.Tensor] = None, training: bool = True, update: bool = True,
+             sync: bool = True) -> Optional[float]:
+        """One training iteration of mnist/train.py:196-219 on this rank's shard.  Returns the loss
+        (joint + image + text ELBO, global-batch mean) if ``sync`` else None (read ``loss_host`` later)."""
+        self.set_inputs(image, text, noise, annealing_factor)
+        self.run(training=training, noise_given=noise is not None, update=update)
+        with torch.cuda.stream(self._stream):
+            self.loss_host.copy_(self.loss_out, non_blocking=True)
+        if sync:
+            self._stream.synchronize()
+            return float(self.loss_host[0])
+        return None
+
+    def losses(self) -> Dict[str, float]:
+        """(after a synchronised step) the reference's three ELBO terms and their sum."""
+        v = self.loss_host
+        return {"total": float(v[0]), "joint": float(v[1 + _REF_TO_INTERNAL[0]]),
+                "image": float(v[1 + _REF_TO_INTERNAL[1]]), "text": float(v[1 + _REF_TO_INTERNAL[2]])}
+
+    def synchronize(self) -> None:
+        self._stream.synchronize()
