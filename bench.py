@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the MVAE training-step hot path (BASELINE.json metric: MVAE train samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision 3xtf32|tf32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one iteration of the reference training loop (mnist/train.py:196-219) on one synthetic
+batch: 3 forwards, 3 ELBO terms, backward, Adam.  Workload at N=1 = BASELINE.json configs[1]
+(MNIST MVAE, n_latents=64, batch=4096, 1xB200).  Prints ONE JSON line (rank 0).
+
+--impl reference times the CPU port of the reference step (oracle/, torch CPU fp32, all host threads)
+on a bounded sample of the same workload; it is the reported CPU baseline, never the product path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LATENTS = 64
+BATCH = 4096
+POOL = 16                      # rotating pool of distinct input batches (> L2: 16 x 12.9 MB = 206 MB)
+LAMBDA_IMAGE, LAMBDA_TEXT = 1.0, 10.0
+ANNEAL_EPOCHS, N_MINI = 200, 15  # KL annealing schedule of mnist/train.py:180-186 with 60000/4096 ~ 15 batches/epoch
+
+# algorithmic work per sample per step
+FLOP_PER_SAMPLE_REFERENCE = 32.4e6     # everything the reference executes (incl. dead decoder passes, duplicate encoders)
+ELEMENTWISE_BYTES_PER_SAMPLE = 30512   # K1 fwd/bwd + K2 image/label terms
+
+
+def executed_gemm_flops_per_sample(L: int = N_LATENTS) -> float:
+    """2*MAC of the GEMMs this implementation launches per sample (fwd + dgrad + wgrad), see DESIGN.md."""
+    enc_i = 784 * 512 + 512 * 512 + 512 * 2 * L
+    enc_t = 512 * 512 + 512 * 2 * L                       # embedding row gather is not a GEMM
+    dec_i = L * 512 + 512 * 512 * 2 + 512 * 784
+    dec_t = L * 512 + 512 * 512 * 2 + 512 * 10
+    fwd = enc_i + enc_t + 2 * (dec_i + dec_t)              # each decoder sees 2 of the 3 passes
+    wgrad = fwd
+    dgrad = (enc_i - 784 * 512) + (enc_t) + 2 * (dec_i + dec_t)   # no dgrad into the image; text enc fc2 dgrad kept
+    return 2.0 * (fwd + wgrad + dgrad)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def synth_batches(n: int, batch: int, seed: int = 0):
+    """Synthetic MNIST-shape data: image ~ U[0,1) [B,1,28,28] fp32, label ~ randint(0,10) int64."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.rand(batch, 1, 28, 28, generator=g), torch.randint(0, 10, (batch,), generator=g)) for _ in range(n)]
+
+
+def annealing(step: int) -> float:
+    epoch, idx = 1 + step // N_MINI, step % N_MINI
+    return min(1.0, float(idx + (epoch - 1) * N_MINI + 1) / float(ANNEAL_EPOCHS * N_MINI))
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline
+def cpu_baseline(batch: int, budget_s: float, steps: int | None = None):
+    """Time the CPU port of the reference step (oracle/, kind "port") on all host threads."""
+    import torch
+    from oracle.mvae_oracle import MnistCpuBaseline
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = MnistCpuBaseline(N_LATENTS, seed=0)
+    data = synth_batches(2, batch, seed=1)
+    t0 = time.perf_counter(); model.step(*data[0]); model.step(*data[1]); warm = (time.perf_counter() - t0) / 2
+    n = steps if steps is not None else max(3, min(200, int(budget_s / max(warm, 1e-3))))
+    t0 = time.perf_counter()
+    for i in range(n):
+        model.step(*data[i % 2], annealing=annealing(i))
+    dt = time.perf_counter() - t0
+    return {"value": batch * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of B={batch} (same workload) in {dt:.1f}s, torch {torch.__version__} CPU fp32, "
+                      f"{torch.get_num_threads()} threads", "ms_per_step": 1e3 * dt / n}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    steps = args.steps
+    r = cpu_baseline(BATCH, budget_s=60.0, steps=None if steps <= 0 else min(steps, 200))
+    line = {"impl": "reference", "metric": "mvae_train_samples_per_sec", "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"MNIST MVAE (image 28x28x1 + label), n_latents={N_LATENTS}, global batch {BATCH}, "
+                                   "CPU port of mnist/train.py step body (3 fwd + 3 ELBO + bwd + Adam)"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    from multimodal_vae_public_b200 import _lib, ops
+    from multimodal_vae_public_b200.trainer import MnistMVAETrainer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    strong = args.scaling == "strong"
+    b_local = BATCH // world if strong else BATCH
+    b_global = b_local * world
+    prec = ops.PREC_3XTF32 if args.precision == "3xtf32" else ops.PREC_TF32
+    tr = MnistMVAETrainer(N_LATENTS, b_local, device=dev, lr=1e-3, lambda_image=LAMBDA_IMAGE, lambda_text=LAMBDA_TEXT,
+                          precision=prec, world_size=world, rank=rank, seed=0, use_graph=not args.no_graph)
+    host = synth_batches(POOL, b_local, seed=100 + rank)
+    host = [(im.pin_memory(), tx.pin_memory()) for im, tx in host]
+    pool = [(im.to(dev), tx.to(dev)) for im, tx in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(tr._stream)
+        for i in range(steps):
+            fn(i)
+        e.record(tr._stream)
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident(i):
+        im, tx = pool[i % POOL]
+        tr.step(im, tx, annealing_factor=annealing(i), sync=False)
+
+    def step_e2e(i):
+        im, tx = host[i % POOL]
+        return tr.step(im, tx, annealing_factor=annealing(i), sync=True)   # loss is read on the host every step
+
+    # warm-up (also captures the CUDA graph) -- long enough for the clocks to ramp
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    tr.synchronize()
+    t0 = time.time()
+    while time.time() - t0 < 1.0:
+        for i in range(20):
+            step_resident(i)
+        tr.synchronize()
+
+    sampler = ClockSampler(local_rank); sampler.start()
+    n0 = _lib.launch_count()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    launches = tr.launches_per_step * args.steps if tr.use_graph else _lib.launch_count() - n0
+    value = b_global * args.steps / (ms * 1e-3)
+
+    for i in range(3):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = b_global * args.steps / (ms_e2e * 1e-3)
+    loss = float(tr.loss_host[0])
+
+    # ---- per-kernel roofline, measured live with CUDA events on the launching stream (eager pass, same buffers)
+    roof = measure_rooflines(tr, dev, prec, args)
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+        gemm = roof["gemm"]
+        ach = gemm["algorithmic_flops_per_step"] / (gemm["ms_per_step"] * 1e-3) / 1e12
+        cpu = cpu_baseline(BATCH, budget_s=15.0) if world == 1 and not args.no_cpu_baseline else None
+        line = {
+            "metric": "mvae_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "fp32 (3xTF32 tensor-core split products, fp32 accumulate)" if prec == ops.PREC_3XTF32
+                     else "tf32 (fp32 storage/accumulate)",
+            "data": "synthetic",
+            "config": {"workload": f"MNIST MVAE (image 28x28x1 + label one-of-10), n_latents={N_LATENTS}, "
+                                   f"global batch {b_global} ({b_local}/GPU), full train step "
+                                   "(3 passes + ELBO + backward + Adam), BASELINE.json configs[1]",
+                       "parallelism": f"dp{world}", "global_batch": b_global,
+                       "l2": f"rotating pool of {POOL} distinct input batches ({POOL * b_local * 3144 / 1e6:.0f} MB) and a "
+                             f"~{working_set_mb(b_local):.0f} MB per-step working set, both larger than the 126 MB L2",
+                       "cuda_graph": tr.use_graph, "loss_last": loss},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": b_local * (784 * 4 + 8) + 4, "d2h_bytes_per_step": 16,
+                    "note": "trainer.step(pinned host image, pinned host labels) with the loss read back every step"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 kind::tf32, all GEMM launches of a step)",
+                         "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+                         "traffic": None,
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained/2 (tf32 rate = half bf16) [{peaks['source']}]",
+                         "algorithmic_flops_per_launch_avg": gemm["algorithmic_flops_per_step"] / max(gemm["launches"], 1),
+                         "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms_per_step"] / max(gemm["launches"], 1),
+                         "executed_tensor_flops_factor": 3 if prec == ops.PREC_3XTF32 else 1,
+                         "share_of_step": gemm["ms_per_step"] / (ms / args.steps)},
+            "roofline_hbm": roof["hbm"],
+            "kernel_breakdown_ms": roof["breakdown"],
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def working_set_mb(b: int) -> float:
+    rows512 = 4 * b + 3 * b + 12 * 2 * b + 4 * 2 * b + 4 * b      # 512-wide activation / gradient buffers
+    return (rows512 * 512 + 2 * b * 784 + b * 784) * 4 / 1e6 + 4 * 10.4
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        d["source"] = "measured"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def measure_rooflines(tr, dev, prec, args):
+    """Eager (non-graph) passes with CUDA events around every library call on the launching stream."""
+    import torch
+    from multimodal_vae_public_b200 import ops
+    st = tr._stream
+    names = ["gemm_batch", "linear_fwd", "bce_logits_fwd_bwd", "ce_fwd_bwd", "poe_fwd", "poe_bwd", "colsum_accumulate",
+             "embedding_swish_fwd", "embedding_swish_bwd", "adam_flat", "elbo_finalize"]
+    records = []
+    orig = {n: getattr(ops, n) for n in names}
+
+    def wrap(n):
+        def f(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(st); r = orig[n](*a, **k); e.record(st)
+            records.append((n, s, e))
+            return r
+        return f
+    reps = 5
+    try:
+        for n in names:
+            setattr(ops, n, wrap(n))
+        with torch.cuda.stream(st):
+            for _ in range(reps):
+                tr._enqueue_step(True, False, True)
+        st.synchronize()
+    finally:
+        for n in names:
+            setattr(ops, n, orig[n])
+    per = {}
+    cnt = {}
+    for n, s, e in records:
+        per[n] = per.get(n, 0.0) + s.elapsed_time(e) / reps
+        cnt[n] = cnt.get(n, 0) + 1
+    gemm_ms = per.get("gemm_batch", 0.0) + per.get("linear_fwd", 0.0)
+    gemm_launches = (cnt.get("gemm_batch", 0) + cnt.get("linear_fwd", 0)) // reps
+    out = {"gemm": {"ms_per_step": gemm_ms, "launches": gemm_launches,
+                    "algorithmic_flops_per_step": executed_gemm_flops_per_sample(tr.L) * tr.B},
+           "breakdown": {k: round(v, 5) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
+    # HBM roofline of the fused reconstruction-loss kernel at roofline size (inputs >> L2), L2 not reusable
+    R, D = 65536, 784
+    x = torch.randn(R, D, device=dev); t = torch.rand(R // 2, D, device=dev); dx = torch.empty_like(x)
+    acc = torch.zeros(2, dtype=torch.float64, device=dev)
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            ops.bce_logits_fwd_bwd(x, t, dx, 1e-3, acc, seg_rows=R // 2)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(st)
+        for _ in range(10):
+            ops.bce_logits_fwd_bwd(x, t, dx, 1e-3, acc, seg_rows=R // 2)
+        e.record(st)
+    st.synchronize()
+    ms = s.elapsed_time(e) / 10
+    peaks = load_peaks()
+    alg = (2 * R * D + R * D // 1) * 4.0   # read x, write dx, read t once per row (t re-read by the 2nd pass) = 12 B/elem
+    out["hbm"] = {"bound": "hbm", "kernel": "bce_kernel (fused BCE-with-logits loss + gradient), roofline-size run "
+                                            f"R={R} D={D}", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
+                  "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                  "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms, "peak_source": peaks["source"]}
+    del x, t, dx
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--precision", choices=["3xtf32", "tf32"], default="3xtf32")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun
+            import subprocess
+            port = 29500 + os.getpid() % 1000
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,14 @@ int mvae_poe_bwd(const float* const* mu_e, const float* const* lv_e, int64_t ld_
                  const float* dmu_up, const float* dlv_up, float kl_scale, const float* kl_scale_dev,
                  float* const* dmu_e, float* const* dlv_e, int64_t ldd_e, void* stream);
 
+/* Stand-alone MVAE.reparametrize (mnist/model.py:29-35, training branch): z = noise*exp(0.5*logvar) + mu.
+ * noise == NULL => Philox(seed, offset) draws written to noise_out.  Backward: dmu = dz (identity),
+ * dlogvar = dz * noise * 0.5 * exp(0.5*logvar). */
+int mvae_reparam_fwd(const float* mu, const float* logvar, const float* noise, float* noise_out, uint64_t seed,
+                     uint64_t offset, float* z, int64_t n, void* stream);
+int mvae_reparam_bwd(const float* logvar, const float* noise, const float* dz, float* dlogvar, int64_t n,
+                     void* stream);
+
 /* KL(q(z|.) || N(0,1)) summed over all n = B*L elements (mnist/train.py:56) and its gradient:
  *   kl_acc[0] += -0.5 * sum(1 + lv - mu^2 - exp(lv));  dmu = scale*mu;  dlogvar = scale*0.5*(exp(lv)-1). */
 int mvae_kl_fwd_bwd(const float* mu, const float* logvar, float* dmu, float* dlogvar, int64_t n, float scale,

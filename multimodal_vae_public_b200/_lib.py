@@ -52,6 +52,8 @@ SIGNATURES = {
     "mvae_poe_bwd": [C.POINTER(_P), C.POINTER(_P), _L, _I, C.POINTER(C.c_uint32), _I, _I, _I, _I, _I, _P, _P, _L, _P,
                      _P, _F, _P, C.POINTER(_P), C.POINTER(_P), _L, _P],
     "mvae_kl_fwd_bwd": [_P, _P, _P, _P, _L, _F, _P, _P],
+    "mvae_reparam_fwd": [_P, _P, _P, _P, _U64, _U64, _P, _L, _P],
+    "mvae_reparam_bwd": [_P, _P, _P, _P, _L, _P],
     "mvae_bce_logits_fwd_bwd": [_P, _L, _P, _L, _I, _P, _L, _I, _I, _F, _P, _I, _P],
     "mvae_ce_fwd_bwd": [_P, _L, _P, _I, _P, _L, _I, _I, _F, _P, _I, _P],
     "mvae_adam_flat": [_P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _F, _P, _P],

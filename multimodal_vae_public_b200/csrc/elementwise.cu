@@ -303,6 +303,30 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const __grid_constant__ Po
   }
 }
 
+// ---------------------------------------------------------------- stand-alone reparametrise (module API)
+__global__ void __launch_bounds__(256) reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                                          const float* noise, float* noise_out, uint64_t seed,
+                                                          uint64_t offset, float* z, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float e;
+  if (noise != nullptr) {
+    e = noise[i];
+  } else {
+    float n4[4];
+    normal4(seed, offset + static_cast<uint64_t>(i), 0u, n4);
+    e = n4[0];
+    noise_out[i] = e;
+  }
+  z[i] = e * expf(0.5f * lv[i]) + mu[i];
+}
+__global__ void __launch_bounds__(256) reparam_bwd_kernel(const float* __restrict__ lv, const float* __restrict__ noise,
+                                                          const float* __restrict__ dz, float* dlv, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dlv[i] = dz[i] * noise[i] * 0.5f * expf(0.5f * lv[i]);
+}
+
 // ---------------------------------------------------------------- stand-alone KL(q || N(0,1)): sum + grad
 __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, const float* __restrict__ lv, float* dmu,
                                                  float* dlv, int64_t n, float scale, double* acc) {
@@ -623,6 +647,25 @@ extern "C" int mvae_poe_bwd(const float* const* mu_e, const float* const* lv_e, 
     const int64_t n = static_cast<int64_t>(B) * L;
     poe_bwd_kernel<1, kMaxExperts><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a);
   }
+  count_launch();
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  return MVAE_OK;
+}
+
+extern "C" int mvae_reparam_fwd(const float* mu, const float* logvar, const float* noise, float* noise_out,
+                                uint64_t seed, uint64_t offset, float* z, int64_t n, void* stream) {
+  if (!mu || !logvar || !z || n < 1 || (!noise && !noise_out)) return set_error(MVAE_ERR_BAD_ARG, "reparam_fwd: bad args");
+  reparam_fwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      mu, logvar, noise, noise_out, seed, offset, z, n);
+  count_launch();
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  return MVAE_OK;
+}
+extern "C" int mvae_reparam_bwd(const float* logvar, const float* noise, const float* dz, float* dlogvar, int64_t n,
+                                void* stream) {
+  if (!logvar || !noise || !dz || !dlogvar || n < 1) return set_error(MVAE_ERR_BAD_ARG, "reparam_bwd: bad args");
+  reparam_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logvar, noise, dz, dlogvar, n);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;

@@ -37,13 +37,15 @@ constexpr int OPERAND_BYTES = BLOCK_M * BLOCK_K * 4;        // 16 KiB per operan
 constexpr int TMEM_COLS = 256;                              // 2 accumulator stages x 128 fp32 columns
 constexpr int NUM_EPI_WARPS = 4;
 constexpr int NUM_SPLIT_WARPS = 4;
+constexpr int EPI_LD = 36;                                  // padded row (floats) of the epilogue staging tile
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * EPI_LD * 4;
 
 template <bool kSplit>
 struct Cfg {
   static constexpr int kStageBytes = kSplit ? 4 * OPERAND_BYTES : 2 * OPERAND_BYTES;  // 64 / 32 KiB
   static constexpr int kStages = kSplit ? 3 : 6;                                       // 192 KiB ring
   static constexpr int kThreads = 32 * (2 + NUM_EPI_WARPS + (kSplit ? NUM_SPLIT_WARPS : 0));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + slack for 1024 B alignment
+  static constexpr int kSmemBytes = kStages * kStageBytes + EPI_STAGE_BYTES + 1024;  // + 1024 B alignment slack
 };
 
 struct alignas(64) GemmProblem {
@@ -243,18 +245,23 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
   } else if (warp < 2 + NUM_EPI_WARPS) {
     // ===================================================== epilogue warps
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
+    float* stage_buf = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes) + (warp - 2) * (32 * EPI_LD);
     int iter = 0;
     for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x, ++iter) {
       const TileInfo ti = decode_tile(batch, t);
       const GemmProblem& p = batch.p[ti.prob];
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
-      const int row = ti.m_blk * BLOCK_M + quarter * 32 + lane;
       const int n0 = ti.n_blk * p.block_n;
-      const bool row_ok = row < p.M;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N_MAX;
+      // Coalescing transpose: TMEM hands each lane one accumulator ROW (32 consecutive columns); the lanes park
+      // their rows in a padded smem tile and re-read it so that one warp instruction covers 4 rows x 128 B of
+      // C / aux / out2 (full 32-byte sectors, 16 per instruction) instead of 32 rows x 16 B.
+      const int sub = lane >> 3;          // row within a group of 4
+      const int c4 = (lane & 7) * 4;      // 4 consecutive columns of the 32-column chunk
+      const int row_base = ti.m_blk * BLOCK_M + quarter * 32;
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         uint32_t r[32];
         const int ncols = (p.block_n - c0) >= 32 ? 32 : 16;
@@ -267,22 +274,30 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (!row_ok) continue;
-        const int col0 = n0 + c0;
-        float* crow = p.C + static_cast<int64_t>(row) * p.ldc;
+        float4* myrow = reinterpret_cast<float4*>(stage_buf + lane * EPI_LD);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (j >= ncols) break;
-          const int col = col0 + j;
-          if (col >= p.N) break;
-          float v[4] = {__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                        __uint_as_float(r[j + 3])};
-          const bool full4 = (col + 3 < p.N);
-          if (p.bias != nullptr) {
+        for (int j = 0; j < 8; ++j)
+          if (4 * j < ncols)
+            myrow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + c4;
+        const bool col_ok = (c4 < ncols) && (col < p.N);
+        const bool full4 = (col + 3 < p.N);
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias != nullptr && col_ok) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (col + q < p.N) v[q] += __ldg(p.bias + col + q);
-          }
+          for (int q = 0; q < 4; ++q)
+            if (col + q < p.N) bv[q] = __ldg(p.bias + col + q);
+        }
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + sub;
+          const int row = row_base + rl;
+          if (!col_ok || row >= p.M) continue;
+          const float4 s4 = *reinterpret_cast<const float4*>(stage_buf + rl * EPI_LD + c4);
+          float v[4] = {s4.x + bv[0], s4.y + bv[1], s4.z + bv[2], s4.w + bv[3]};
+          float* crow = p.C + static_cast<int64_t>(row) * p.ldc;
           if (p.epilogue == MVAE_EPI_MUL_DSWISH) {
             const float* arow = p.aux + static_cast<int64_t>(row) * p.ldaux + col;
             float a[4];
@@ -295,8 +310,8 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float s = sigmoidf_acc(a[q]);
-              v[q] *= s * (1.0f + a[q] * (1.0f - s));
+              const float sg = sigmoidf_acc(a[q]);
+              v[q] *= sg * (1.0f + a[q] * (1.0f - sg));
             }
           }
           if (p.atomic) {
@@ -327,6 +342,7 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
             }
           }
         }
+        __syncwarp();  // staging tile is rewritten by the next chunk
       }
     }
   } else if (kSplit) {

@@ -1,0 +1,305 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels: the building blocks of the drop-in
+``MVAE`` modules (``mnist/model.py``-style surface).  Forward AND backward run in libmvae_b200.so;
+there is no eager fallback -- CPU tensors raise ``MvaeError``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import _lib, ops
+
+DEFAULT_PRECISION = ops.PREC_3XTF32
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MvaeError("mvae_b200 modules run on CUDA tensors only (no CPU fallback for the hot path)")
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def _padded(rows: int, cols: int, like: torch.Tensor, zero: bool = False) -> torch.Tensor:
+    """[rows, cols] fp32 view whose row stride is a multiple of 4 elements (TMA requirement)."""
+    mk = torch.zeros if zero else torch.empty
+    return mk(rows, _pad4(cols), dtype=torch.float32, device=like.device)[:, :cols]
+
+
+def _as_operand(t: torch.Tensor) -> torch.Tensor:
+    """fp32, unit inner stride, row stride % 4 == 0, 16-byte aligned -- copy into a padded buffer if not."""
+    t = t.to(torch.float32)
+    if t.dim() != 2:
+        t = t.reshape(t.shape[0], -1)
+    if t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    out = _padded(t.shape[0], t.shape[1], t)
+    out.copy_(t)
+    return out
+
+
+def _split_k(m_rows: int) -> int:
+    return max(1, min(m_rows // 256, 16))
+
+
+class _LinearFn(Function):
+    """y = x W^T + b  (nn.Linear.forward, mnist/model.py:81-84) and, with ``act``, Swish fused in the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act: bool, prec: int):
+        _need_cuda(x, w, b)
+        x = _as_operand(x.detach()); w2 = _as_operand(w.detach())
+        M, N = x.shape[0], w2.shape[0]
+        a = _padded(M, N, x)
+        h = _padded(M, N, x) if act else None
+        ops.linear_fwd(x, w2, b.detach() if b is not None else None, a, h, prec)
+        ctx.act, ctx.prec, ctx.has_bias = act, prec, b is not None
+        ctx.save_for_backward(x, w2, a if act else None)
+        return h if act else a
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, a = ctx.saved_tensors
+        M, K = x.shape
+        N = w.shape[0]
+        dy = _as_operand(dy)
+        if ctx.act:
+            da = _padded(M, N, x)
+            if da.stride(0) == N and dy.stride(0) == N and a.stride(0) == N:
+                ops.swish_bwd(a, dy, da)
+            else:  # ragged widths never carry an activation in the MVAE nets; keep a general path anyway
+                da.copy_(dy * torch.sigmoid(a) * (1 + a * (1 - torch.sigmoid(a))))
+            dy = da
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _padded(M, K, x)
+            ops.linear_dgrad(dy, w, dx, precision=ctx.prec)
+        if ctx.needs_input_grad[1]:
+            dwp = _padded(N, K, x, zero=True)
+            ops.linear_wgrad(dy, x, dwp, split_k=_split_k(M), precision=ctx.prec)
+            dw = dwp
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.zeros(N, dtype=torch.float32, device=x.device)
+            ops.colsum_accumulate(dy, db)
+        return dx, dw, db, None, None
+
+
+def linear(x, w, b=None, precision: int = DEFAULT_PRECISION):
+    return _LinearFn.apply(x, w, b, False, precision)
+
+
+def linear_swish(x, w, b, precision: int = DEFAULT_PRECISION):
+    return _LinearFn.apply(x, w, b, True, precision)
+
+
+class _SwishFn(Function):
+    """x * sigmoid(x)  (Swish, mnist/model.py:166-169)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x)
+        xc = x.detach().to(torch.float32).contiguous()
+        y = torch.empty_like(xc)
+        ops.swish_fwd(xc, y)
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        dx = torch.empty_like(xc)
+        ops.swish_bwd(xc, dy.to(torch.float32).contiguous(), dx)
+        return dx
+
+
+def swish(x):
+    return _SwishFn.apply(x)
+
+
+class _EmbeddingSwishFn(Function):
+    """swish(table[idx])  (nn.Embedding + Swish, mnist/model.py:116,123)."""
+
+    @staticmethod
+    def forward(ctx, idx, table):
+        _need_cuda(idx, table)
+        t = table.detach().to(torch.float32).contiguous()
+        idx = idx.detach().to(torch.int64).contiguous().view(-1)
+        h = torch.empty(idx.numel(), t.shape[1], dtype=torch.float32, device=t.device)
+        ops.embedding_swish_fwd(t, idx, None, h)
+        ctx.save_for_backward(idx, t)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        idx, t = ctx.saved_tensors
+        dt = torch.zeros_like(t)
+        ops.embedding_swish_bwd(t, idx, _as_operand(dh), dt)
+        return None, dt
+
+
+def embedding_swish(idx, table):
+    return _EmbeddingSwishFn.apply(idx, table)
+
+
+class _PoEFn(Function):
+    """Product of Gaussian experts -> (mu, logvar).  ``with_prior``: the N(0,1) prior expert is implicit
+    (MVAE.infer, mnist/model.py:46-64); otherwise the given experts are the whole product
+    (ProductOfExperts.forward on an explicit stack, mnist/model.py:156-163)."""
+
+    @staticmethod
+    def forward(ctx, variant: int, with_prior: bool, n_experts: int, *tensors):
+        mus = [t.detach().to(torch.float32).contiguous() for t in tensors[:n_experts]]
+        lvs = [t.detach().to(torch.float32).contiguous() for t in tensors[n_experts:]]
+        _need_cuda(*mus, *lvs)
+        B, L = mus[0].shape
+        code = variant | (0 if with_prior else 2)
+        z = torch.empty(B, L, dtype=torch.float32, device=mus[0].device)
+        mu = torch.empty_like(z); lv = torch.empty_like(z)
+        mask = (1 << n_experts) - 1
+        ops.poe_fwd(mus, lvs, [mask], B, L, z, variant=code, training=False, mu_out=mu, lv_out=lv)
+        ctx.code, ctx.n = code, n_experts
+        ctx.save_for_backward(*mus, *lvs)
+        return mu, lv
+
+    @staticmethod
+    def backward(ctx, dmu, dlv):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        mus, lvs = list(saved[:n]), list(saved[n:])
+        B, L = mus[0].shape
+        gm = [torch.empty_like(m) for m in mus]; gl = [torch.empty_like(m) for m in mus]
+        dz = torch.zeros(B, L, dtype=torch.float32, device=mus[0].device)
+        ops.poe_bwd(mus, lvs, [(1 << n) - 1], B, L, dz, gm, gl, kl_scale=0.0, variant=ctx.code, training=False,
+                    dmu_up=dmu.to(torch.float32).contiguous() if dmu is not None else None,
+                    dlv_up=dlv.to(torch.float32).contiguous() if dlv is not None else None)
+        return (None, None, None, *gm, *gl)
+
+
+def product_of_experts(mus: Sequence[torch.Tensor], logvars: Sequence[torch.Tensor], variant: int = 0,
+                       with_prior: bool = True):
+    if len(mus) > 20:
+        raise _lib.MvaeError("at most 20 experts are supported")
+    return _PoEFn.apply(variant, with_prior, len(mus), *mus, *logvars)
+
+
+class _ReparamFn(Function):
+    """z = eps * exp(0.5 logvar) + mu with eps ~ N(0,1) (MVAE.reparametrize training branch, mnist/model.py:29-33)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, noise, seed, offset):
+        _need_cuda(mu, logvar)
+        m = mu.detach().to(torch.float32).contiguous(); lv = logvar.detach().to(torch.float32).contiguous()
+        z = torch.empty_like(m)
+        if noise is None:
+            noise = torch.empty_like(m)
+            ops.reparam_fwd(m, lv, z, noise=None, noise_out=noise, seed=seed, offset=offset)
+        else:
+            noise = noise.detach().to(torch.float32).contiguous()
+            ops.reparam_fwd(m, lv, z, noise=noise)
+        ctx.save_for_backward(lv, noise)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        lv, noise = ctx.saved_tensors
+        dz = dz.to(torch.float32).contiguous()
+        dlv = torch.empty_like(lv)
+        ops.reparam_bwd(lv, noise, dz, dlv)
+        return dz, dlv, None, None, None
+
+
+_noise_counter = [0]
+
+
+def reparametrize(mu, logvar, noise: Optional[torch.Tensor] = None, seed: Optional[int] = None):
+    if seed is None:
+        seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+    off = _noise_counter[0]
+    _noise_counter[0] += mu.numel()
+    return _ReparamFn.apply(mu, logvar, noise, seed, off)
+
+
+class _BceSumFn(Function):
+    """sum over ALL elements of binary_cross_entropy_with_logits (mnist/train.py:62-74); gradient
+    sigmoid(x) - t computed in the same pass."""
+
+    @staticmethod
+    def forward(ctx, x, t):
+        _need_cuda(x, t)
+        if t.size() != x.size():
+            raise ValueError("Target size ({}) must be the same as input size ({})".format(t.size(), x.size()))
+        x2 = _as_operand(x.detach().reshape(x.shape[0], -1) if x.dim() > 1 else x.detach().reshape(1, -1))
+        t2 = _as_operand(t.detach().reshape(x2.shape))
+        D = x2.shape[1]
+        if D % 4:
+            raise _lib.MvaeError("bce: inner size must be a multiple of 4")
+        acc = torch.zeros(1, dtype=torch.float64, device=x.device)
+        dx = torch.empty(x2.shape, dtype=torch.float32, device=x.device)
+        ops.bce_logits_fwd_bwd(x2, t2, dx, 1.0, acc)
+        ctx.save_for_backward(dx)
+        ctx.shape = x.shape
+        return acc[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return (dx * g).reshape(ctx.shape), None
+
+
+class _CeSumFn(Function):
+    """sum over rows of cross_entropy(input, target, eps=1e-6) (mnist/train.py:77-94)."""
+
+    @staticmethod
+    def forward(ctx, x, target):
+        _need_cuda(x, target)
+        if target.size(0) != x.size(0):
+            raise ValueError("Target size ({}) must be the same as input size ({})".format(target.size(0), x.size(0)))
+        x2 = x.detach().to(torch.float32)
+        if x2.stride(1) != 1:
+            x2 = x2.contiguous()
+        R, K = x2.shape
+        acc = torch.zeros(1, dtype=torch.float64, device=x.device)
+        dx = torch.empty(R, K, dtype=torch.float32, device=x.device)
+        ops.ce_fwd_bwd(x2, target.detach().to(torch.int64).contiguous(), dx, K, 1.0, acc)
+        ctx.save_for_backward(dx)
+        return acc[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None
+
+
+class _KlSumFn(Function):
+    """sum over the batch of KLD = -0.5 * sum(1 + logvar - mu^2 - exp(logvar)) (mnist/train.py:56)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar):
+        _need_cuda(mu, logvar)
+        m = mu.detach().to(torch.float32).contiguous(); lv = logvar.detach().to(torch.float32).contiguous()
+        acc = torch.zeros(1, dtype=torch.float64, device=m.device)
+        dm = torch.empty_like(m); dl = torch.empty_like(m)
+        ops.kl_fwd_bwd(m, lv, dm, dl, 1.0, acc)
+        ctx.save_for_backward(dm, dl)
+        return acc[0].to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        dm, dl = ctx.saved_tensors
+        return dm * g, dl * g
+
+
+def bce_with_logits_sum(x, t):
+    return _BceSumFn.apply(x, t)
+
+
+def cross_entropy_sum(x, target):
+    return _CeSumFn.apply(x, target)
+
+
+def kl_sum(mu, logvar):
+    return _KlSumFn.apply(mu, logvar)

@@ -130,6 +130,16 @@ def poe_bwd(mu_e, lv_e, masks, B, L, dz, dmu_e, dlv_e, kl_scale, variant=0, trai
                                         _stream()), "mvae_poe_bwd")
 
 
+def reparam_fwd(mu, logvar, z, noise=None, noise_out=None, seed=0, offset=0):
+    _lib.check(_lib.load().mvae_reparam_fwd(mu.data_ptr(), logvar.data_ptr(), _p(noise), _p(noise_out), seed, offset,
+                                            z.data_ptr(), mu.numel(), _stream()), "mvae_reparam_fwd")
+
+
+def reparam_bwd(logvar, noise, dz, dlogvar):
+    _lib.check(_lib.load().mvae_reparam_bwd(logvar.data_ptr(), noise.data_ptr(), dz.data_ptr(), dlogvar.data_ptr(),
+                                            logvar.numel(), _stream()), "mvae_reparam_bwd")
+
+
 def kl_fwd_bwd(mu, logvar, dmu, dlogvar, scale, kl_acc=None):
     _lib.check(_lib.load().mvae_kl_fwd_bwd(mu.data_ptr(), logvar.data_ptr(), _p(dmu), _p(dlogvar), mu.numel(),
                                            float(scale), _p(kl_acc), _stream()), "mvae_kl_fwd_bwd")

@@ -1,0 +1,99 @@
+"""GPU parity of the drop-in module surface (mnist/model.py + mnist/train.py names) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B=24, L=64, seed=2):
+    from multimodal_vae_public_b200.mnist import model as M
+    rs = np.random.RandomState(seed)
+    image = torch.from_numpy(rs.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32))
+    text = torch.from_numpy(rs.randint(0, 10, B).astype(np.int64))
+    p32 = O.make_params(O.mnist_param_shapes(L), seed=seed)
+    m = M.MVAE(L)
+    m.load_state_dict(p32)
+    return m.cuda(), image, text, p32
+
+
+def test_state_dict_and_surface():
+    from multimodal_vae_public_b200.mnist import model as M, train as T
+    m = M.MVAE(64)
+    assert list(m.state_dict().keys()) == [k for k, _ in O.mnist_param_shapes(64)]
+    for name in ("MVAE", "ImageEncoder", "ImageDecoder", "TextEncoder", "TextDecoder", "ProductOfExperts", "Swish", "prior_expert"):
+        assert hasattr(M, name)
+    for name in ("elbo_loss", "binary_cross_entropy_with_logits", "cross_entropy", "AverageMeter", "save_checkpoint", "load_checkpoint"):
+        assert hasattr(T, name)
+    mu, lv = M.prior_expert((1, 5, 64))
+    assert mu.shape == (1, 5, 64) and float(mu.abs().sum() + lv.abs().sum()) == 0.0
+
+
+def test_eval_forward_and_elbo_backward_match_oracle():
+    from multimodal_vae_public_b200.mnist import train as T
+    m, image, text, p32 = _setup()
+    m.eval()
+    L = 64
+    ic, tc = image.cuda(), text.cuda()
+    outs = [m(ic, tc), m(ic), m(text=tc)]
+    j = T.elbo_loss(outs[0][0], ic, outs[0][1], tc, outs[0][2], outs[0][3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    i = T.elbo_loss(outs[1][0], ic, None, None, outs[1][2], outs[1][3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    t = T.elbo_loss(None, None, outs[2][1], tc, outs[2][2], outs[2][3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    loss = j + i + t
+    loss.backward()
+    p64 = {k: v.double() for k, v in p32.items()}
+    ref, terms, grads, aux = O.mnist_step_grads(p64, image.double(), text, L, [None] * 3, 1.0, 10.0, 0.5)
+    assert abs(loss.item() - ref.item()) <= 5e-6 * abs(ref.item())
+    for got, want in zip((j, i, t), terms):
+        assert abs(got.item() - want.item()) <= 5e-6 * abs(want.item()) + 1e-5
+    for pi in range(3):
+        np.testing.assert_allclose(outs[pi][2].detach().cpu().numpy(), aux["mu"][pi].detach().numpy(), rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(outs[pi][3].detach().cpu().numpy(), aux["logvar"][pi].detach().numpy(), rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(outs[pi][0].detach().cpu().numpy(), aux["recon_image"][pi].detach().numpy(), rtol=1e-3, atol=5e-5)
+        np.testing.assert_allclose(outs[pi][1].detach().cpu().numpy(), aux["recon_text"][pi].detach().numpy(), rtol=1e-3, atol=5e-5)
+    for k, v in m.named_parameters():
+        g = grads[k]
+        err = (v.grad.cpu().double() - g).abs().max().item() / max(g.abs().max().item(), 1e-12)
+        assert err < 3e-4, (k, err)
+
+
+def test_train_mode_reparam_and_poe_module():
+    from multimodal_vae_public_b200 import functional as F
+    from multimodal_vae_public_b200.mnist import model as M
+    m, image, text, _ = _setup(B=16)
+    m.train()
+    r1 = m(image.cuda(), text.cuda()); r2 = m(image.cuda(), text.cuda())
+    assert not torch.equal(r1[0], r2[0]) and torch.equal(r1[2], r2[2])       # fresh noise, same posterior
+    # explicit-noise reparametrisation and its gradient
+    mu = torch.randn(16, 64, device="cuda", requires_grad=True); lv = torch.randn(16, 64, device="cuda", requires_grad=True)
+    nz = torch.randn(16, 64, device="cuda")
+    z = F.reparametrize(mu, lv, noise=nz)
+    w = torch.randn_like(z)
+    (z * w).sum().backward()
+    zr = O.reparametrize(mu.detach().cpu().double(), lv.detach().cpu().double(), nz.cpu().double())
+    np.testing.assert_allclose(z.detach().cpu().numpy(), zr.numpy(), rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(mu.grad.cpu().numpy(), w.cpu().numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(lv.grad.cpu().numpy(), (w * nz * 0.5 * torch.exp(0.5 * lv.detach())).cpu().numpy(), rtol=2e-5, atol=1e-6)
+    # ProductOfExperts on an explicit [M,B,D] stack (prior as row 0, like the reference's infer)
+    poe = M.ProductOfExperts()
+    smu = torch.randn(3, 8, 64, device="cuda"); slv = 0.5 * torch.randn(3, 8, 64, device="cuda"); smu[0] = 0; slv[0] = 0
+    smu.requires_grad_(True); slv.requires_grad_(True)
+    pm, pl = poe(smu, slv)
+    (pm.sum() + 2 * pl.sum()).backward()
+    tm = smu.detach().cpu().double().requires_grad_(True); tl = slv.detach().cpu().double().requires_grad_(True)
+    rm, rl = O.product_of_experts(tm, tl, variant="A")
+    (rm.sum() + 2 * rl.sum()).backward()
+    np.testing.assert_allclose(pm.detach().cpu().numpy(), rm.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(pl.detach().cpu().numpy(), rl.detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(smu.grad.cpu().numpy(), tm.grad.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(slv.grad.cpu().numpy(), tl.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_errors_like_reference():
+    from multimodal_vae_public_b200.mnist import train as T
+    with pytest.raises(ValueError):
+        T.binary_cross_entropy_with_logits(torch.zeros(3, 4, device="cuda"), torch.zeros(3, 5, device="cuda"))
+    with pytest.raises(ValueError):
+        T.cross_entropy(torch.zeros(3, 10, device="cuda"), torch.zeros(4, dtype=torch.long, device="cuda"))
