@@ -58,6 +58,8 @@ typedef struct {
   const float* bias;              /* [N] or NULL                                                    */
   const float* aux; int64_t ldaux;/* [M,N] operand of the epilogue or NULL                          */
   float* out2; int64_t ldout2;    /* second [M,N] output or NULL                                    */
+  float* colsum;                  /* optional [N]: colsum[n] += sum_m C[m,n] of the stored values   */
+                                  /* (bias gradient fused into the dgrad that produces dA)          */
   int32_t epilogue;               /* MVAE_EPI_*                                                     */
   int32_t split_k;                /* >= 1; > 1 => partial products are atomically added into C      */
   int32_t accumulate;             /* 1 => C += result (atomic red.add), 0 => C = result             */
@@ -143,13 +145,16 @@ int mvae_kl_fwd_bwd(const float* mu, const float* logvar, float* dmu, float* dlo
  *   x [R, D] logits (row stride ldx), target row r = t[(r % t_rows), :] (row stride ldt)
  *   dx = scale * (sigmoid(x) - t)  written to dx (row stride lddx; may alias x)
  *   loss_acc[r / seg_rows] += sum of BCE over row r (un-scaled), double accumulators, or NULL
- *   (seg_rows <= 0: one accumulator for all rows; seg_rows = B keeps the passes separate)        */
+ *   (seg_rows <= 0: one accumulator for all rows; seg_rows = B keeps the passes separate)
+ *   loss_elem: optional [R, D] (row stride ldl) element-wise BCE values (the function's own return value) */
 int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float* t, int64_t ldt, int t_rows, float* dx,
-                            int64_t lddx, int R, int D, float scale, double* loss_acc, int seg_rows, void* stream);
+                            int64_t lddx, int R, int D, float scale, double* loss_acc, int seg_rows,
+                            float* loss_elem, int64_t ldl, void* stream);
 /* Fused cross_entropy(input, target, eps=1e-6) row loss + gradient (mnist/train.py:77-94):
- *   x [R, K] logits, target[r % t_rows] int64 class index; dx = scale*(softmax(x+eps) - onehot).   */
+ *   x [R, K] logits, target[r % t_rows] int64 class index; dx = scale*(softmax(x+eps) - onehot).
+ *   loss_rows: optional [R, K] (row stride ldl) = -onehot * log_softmax, the function's own return value.  */
 int mvae_ce_fwd_bwd(const float* x, int64_t ldx, const int64_t* target, int t_rows, float* dx, int64_t lddx, int R,
-                    int K, float scale, double* loss_acc, int seg_rows, void* stream);
+                    int K, float scale, double* loss_acc, int seg_rows, float* loss_rows, int64_t ldl, void* stream);
 
 /* Fused flat Adam over one contiguous parameter bucket (torch.optim.Adam defaults, mnist/train.py:168,219):
  *   g is first multiplied by grad_scale (1/world_size after a sum-allreduce).

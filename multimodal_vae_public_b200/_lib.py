@@ -30,6 +30,7 @@ class GemmDesc(C.Structure):
         ("bias", C.c_void_p),
         ("aux", C.c_void_p), ("ldaux", C.c_int64),
         ("out2", C.c_void_p), ("ldout2", C.c_int64),
+        ("colsum", C.c_void_p),
         ("epilogue", C.c_int32), ("split_k", C.c_int32), ("accumulate", C.c_int32),
     ]
 
@@ -54,8 +55,8 @@ SIGNATURES = {
     "mvae_kl_fwd_bwd": [_P, _P, _P, _P, _L, _F, _P, _P],
     "mvae_reparam_fwd": [_P, _P, _P, _P, _U64, _U64, _P, _L, _P],
     "mvae_reparam_bwd": [_P, _P, _P, _P, _L, _P],
-    "mvae_bce_logits_fwd_bwd": [_P, _L, _P, _L, _I, _P, _L, _I, _I, _F, _P, _I, _P],
-    "mvae_ce_fwd_bwd": [_P, _L, _P, _I, _P, _L, _I, _I, _F, _P, _I, _P],
+    "mvae_bce_logits_fwd_bwd": [_P, _L, _P, _L, _I, _P, _L, _I, _I, _F, _P, _I, _P, _L, _P],
+    "mvae_ce_fwd_bwd": [_P, _L, _P, _I, _P, _L, _I, _I, _F, _P, _I, _P, _L, _P],
     "mvae_adam_flat": [_P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _F, _P, _P],
     "mvae_elbo_finalize": [_P, _P, _P, _I, _F, _F, _F, _P, _F, _P, _P],
 }

@@ -346,13 +346,14 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, c
 constexpr int kBceUnroll = 4;
 __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ t,
                                                   int64_t ldt, int t_rows, float* dx, int64_t lddx, int R, int D4,
-                                                  float scale, double* loss_acc, int seg_rows) {
+                                                  float scale, double* loss_acc, int seg_rows, float* loss_elem,
+                                                  int64_t ldl) {
   __shared__ double scratch[32];
   __shared__ int seg_smem;
   const int64_t n4 = static_cast<int64_t>(R) * D4;
   const int64_t base = static_cast<int64_t>(blockIdx.x) * (blockDim.x * kBceUnroll) + threadIdx.x;
   float4 xv[kBceUnroll], tv[kBceUnroll];
-  int64_t off_dx[kBceUnroll];
+  int64_t off_dx[kBceUnroll], off_l[kBceUnroll];
   int seg[kBceUnroll];
   bool ok[kBceUnroll];
 #pragma unroll
@@ -365,6 +366,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ x, i
       xv[u] = __ldcs(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * ldx + c));
       tv[u] = __ldg(reinterpret_cast<const float4*>(t + static_cast<int64_t>(r % t_rows) * ldt + c));
       off_dx[u] = static_cast<int64_t>(r) * lddx + c;
+      off_l[u] = static_cast<int64_t>(r) * ldl + c;
       seg[u] = r / seg_rows;
     }
   }
@@ -377,14 +379,15 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ x, i
     if (!ok[u]) continue;
     const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
     const float ts[4] = {tv[u].x, tv[u].y, tv[u].z, tv[u].w};
-    float g[4];
+    float g[4], le[4];
     float lsum = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float xq = xs[q];
       const float e = expf(-fabsf(xq));
       const float inv = 1.0f / (1.0f + e);
-      lsum += fmaxf(xq, 0.f) - xq * ts[q] + logf(1.0f + e);
+      le[q] = fmaxf(xq, 0.f) - xq * ts[q] + logf(1.0f + e);
+      lsum += le[q];
       const float s = xq >= 0.f ? inv : e * inv;
       g[q] = scale * (s - ts[q]);
     }
@@ -392,6 +395,8 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ x, i
     if (seg[u] == seg_first) part += lsum;
     else if (loss_acc != nullptr) atomicAdd(loss_acc + seg[u], static_cast<double>(lsum));
     if (dx != nullptr) __stcs(reinterpret_cast<float4*>(dx + off_dx[u]), make_float4(g[0], g[1], g[2], g[3]));
+    if (loss_elem != nullptr)
+      __stcs(reinterpret_cast<float4*>(loss_elem + off_l[u]), make_float4(le[0], le[1], le[2], le[3]));
   }
   if (loss_acc != nullptr)
     block_atomic_add_seg(static_cast<double>(part), seg_first < 0 ? 0 : seg_first, loss_acc, scratch, &seg_smem);
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ x, i
 // ---------------------------------------------------------------- cross entropy (K small): one thread per row
 __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ x, int64_t ldx, const int64_t* __restrict__ target,
                                                  int t_rows, float* dx, int64_t lddx, int R, int K, float scale,
-                                                 double* loss_acc, int seg_rows) {
+                                                 double* loss_acc, int seg_rows, float* loss_rows, int64_t ldl) {
   __shared__ double scratch[32];
   __shared__ int seg_smem;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -414,6 +419,10 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ x, in
     for (int k = 0; k < K; ++k) se += expf((xr[k] + 1e-6f) - mx);
     const float lse = mx + logf(se);
     loss = -static_cast<double>((xr[tg] + 1e-6f) - lse);
+    if (loss_rows != nullptr) {
+      float* lr = loss_rows + static_cast<int64_t>(r) * ldl;
+      for (int k = 0; k < K; ++k) lr[k] = (k == tg) ? -((xr[k] + 1e-6f) - lse) : 0.0f;
+    }
     if (dx != nullptr) {
       float* dr = dx + static_cast<int64_t>(r) * lddx;
       for (int k = 0; k < K; ++k) {
@@ -483,19 +492,29 @@ __global__ void emb_swish_fwd_kernel(const float* __restrict__ table, const int6
   reinterpret_cast<float4*>(h)[i] =
       make_float4(v.x * sigmoid_f(v.x), v.y * sigmoid_f(v.y), v.z * sigmoid_f(v.z), v.w * sigmoid_f(v.w));
 }
-// grid = (V, ceil(D/128), row chunks); block = 128 threads (one column each)
-constexpr int kEmbRows = 512;
+// Embedding backward through Swish = segmented row sum by class (only V rows receive gradient).
+// grid = (ceil(D/128), row chunks of kEmbRows); block = 128 threads (one column each); per-class partial sums
+// live in shared memory, one atomic per (class, column) per block.
+constexpr int kEmbRows = 128;
+constexpr int kEmbMaxV = 32;
 __global__ void __launch_bounds__(128) emb_swish_bwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
                                                             const float* __restrict__ dh, int64_t lddh, float* dtable,
-                                                            int B, int D) {
-  const int v = blockIdx.x;
-  const int d = blockIdx.y * 128 + threadIdx.x;
-  const int r0 = blockIdx.z * kEmbRows, r1 = min(B, r0 + kEmbRows);
-  if (d >= D) return;
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r)
-    if (idx[r] == v) s += dh[static_cast<int64_t>(r) * lddh + d];
-  if (s != 0.f) atomicAdd(dtable + static_cast<int64_t>(v) * D + d, s * dswish_f(table[static_cast<int64_t>(v) * D + d]));
+                                                            int B, int D, int V) {
+  __shared__ float acc[kEmbMaxV][128];
+  __shared__ int sidx[kEmbRows];
+  const int d = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * kEmbRows, r1 = min(B, r0 + kEmbRows);
+  for (int v = 0; v < V; ++v) acc[v][threadIdx.x] = 0.f;
+  for (int r = r0 + threadIdx.x; r < r1; r += 128) sidx[r - r0] = static_cast<int>(idx[r]);
+  __syncthreads();
+  if (d < D) {
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) acc[sidx[r - r0]][threadIdx.x] += dh[static_cast<int64_t>(r) * lddh + d];
+    for (int v = 0; v < V; ++v) {
+      const float s = acc[v][threadIdx.x];
+      if (s != 0.f) atomicAdd(dtable + static_cast<int64_t>(v) * D + d, s * dswish_f(table[static_cast<int64_t>(v) * D + d]));
+    }
+  }
 }
 
 // ---------------------------------------------------------------- Adam
@@ -683,16 +702,17 @@ extern "C" int mvae_kl_fwd_bwd(const float* mu, const float* logvar, float* dmu,
 
 extern "C" int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float* t, int64_t ldt, int t_rows,
                                        float* dx, int64_t lddx, int R, int D, float scale, double* loss_acc,
-                                       int seg_rows, void* stream) {
+                                       int seg_rows, float* loss_elem, int64_t ldl, void* stream) {
   if (!x || !t || R < 1 || D < 1 || t_rows < 1) return set_error(MVAE_ERR_BAD_ARG, "bce: bad pointers/shape");
   if (seg_rows < 1) seg_rows = R;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if ((D & 3) || (ldx & 3) || (ldt & 3) || (dx && (lddx & 3)) || !al(x) || !al(t) || !al(dx))
+  if ((D & 3) || (ldx & 3) || (ldt & 3) || (dx && (lddx & 3)) || !al(x) || !al(t) || !al(dx) ||
+      (loss_elem && ((ldl & 3) || !al(loss_elem))))
     return set_error(MVAE_ERR_UNSUPPORTED, "bce: D and leading dims must be multiples of 4 and pointers 16B aligned");
   const int64_t n4 = static_cast<int64_t>(R) * (D / 4);
   const int per_block = 256 * kBceUnroll;
   bce_kernel<<<static_cast<unsigned>((n4 + per_block - 1) / per_block), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, ldx, t, ldt, t_rows, dx, lddx, R, D / 4, scale, loss_acc, seg_rows);
+      x, ldx, t, ldt, t_rows, dx, lddx, R, D / 4, scale, loss_acc, seg_rows, loss_elem, ldl);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
@@ -700,11 +720,11 @@ extern "C" int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float*
 
 extern "C" int mvae_ce_fwd_bwd(const float* x, int64_t ldx, const int64_t* target, int t_rows, float* dx,
                                int64_t lddx, int R, int K, float scale, double* loss_acc, int seg_rows,
-                               void* stream) {
+                               float* loss_rows, int64_t ldl, void* stream) {
   if (!x || !target || R < 1 || K < 1 || t_rows < 1) return set_error(MVAE_ERR_BAD_ARG, "ce: bad pointers/shape");
   if (seg_rows < 1) seg_rows = R;
   ce_kernel<<<(R + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, target, t_rows, dx, lddx, R,
-                                                                                  K, scale, loss_acc, seg_rows);
+                                                                                  K, scale, loss_acc, seg_rows, loss_rows, ldl);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
@@ -755,8 +775,9 @@ extern "C" int mvae_embedding_swish_bwd(const float* table, const int64_t* idx, 
                                         float* dtable, int B, int D, int V, void* stream) {
   if (!table || !idx || !dh || !dtable || B < 1 || D < 1 || V < 1)
     return set_error(MVAE_ERR_BAD_ARG, "embedding_swish_bwd: bad args");
-  dim3 grid(V, (D + 127) / 128, (B + kEmbRows - 1) / kEmbRows);
-  emb_swish_bwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, idx, dh, lddh, dtable, B, D);
+  if (V > kEmbMaxV) return set_error(MVAE_ERR_UNSUPPORTED, "embedding_swish_bwd: V=%d > %d", V, kEmbMaxV);
+  dim3 grid((D + 127) / 128, (B + kEmbRows - 1) / kEmbRows);
+  emb_swish_bwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(table, idx, dh, lddh, dtable, B, D, V);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;

@@ -7,8 +7,9 @@
 // Structure (one CTA per SM, static round-robin tile scheduler over a small batch of problems):
 //   warp 0      : TMA producer   -- cp.async.bulk.tensor 128B-swizzled boxes into a smem ring
 //   warp 1      : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N<=128, K=8 per instr)
-//   warps 2..5  : epilogue       -- tcgen05.ld TMEM -> registers -> bias / Swish / dSwish -> global
-//   warps 6..9  : operand split  -- (3xTF32 mode only) x -> hi = rna_tf32(x), lo = x - hi in smem,
+//   warps 2..9  : epilogue       -- tcgen05.ld TMEM -> registers -> smem transpose -> bias / Swish / dSwish /
+//                                   bias-gradient column sums -> coalesced global stores (or red.add)
+//   warps 10..13: operand split  -- (3xTF32 mode only) x -> hi = rna_tf32(x), lo = x - hi in smem,
 //                                   then 3 MMAs/product: hi*hi + hi*lo + lo*hi  (fp32-class accuracy)
 // Pipelines: smem full/ready/empty mbarrier ring; double-buffered TMEM accumulators (2 x 128 columns)
 // so the epilogue of tile i overlaps the main loop of tile i+1.
@@ -35,9 +36,9 @@ constexpr int BLOCK_K = 32;                                 // 32 fp32 = 128 B =
 constexpr int UMMA_K = 8;                                   // tf32: 32 B per MMA along K
 constexpr int OPERAND_BYTES = BLOCK_M * BLOCK_K * 4;        // 16 KiB per operand per stage
 constexpr int TMEM_COLS = 256;                              // 2 accumulator stages x 128 fp32 columns
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_SPLIT_WARPS = 4;
-constexpr int EPI_LD = 36;                                  // padded row (floats) of the epilogue staging tile
+constexpr int EPI_LD = 33;                                  // padded row (floats) of the epilogue staging tile (conflict-free scalar access)
 constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * EPI_LD * 4;
 
 template <bool kSplit>
@@ -55,6 +56,7 @@ struct alignas(64) GemmProblem {
   const float* bias;
   const float* aux;
   float* out2;
+  float* colsum;          // optional [N]: += column sums of the stored C tile (bias gradient)
   int64_t ldc, ldaux, ldout2;
   int M, N, K;
   int block_n;            // MMA N (multiple of 16, <= 128)
@@ -243,9 +245,17 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       }
     }
   } else if (warp < 2 + NUM_EPI_WARPS) {
-    // ===================================================== epilogue warps
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are accessible to this warp
-    float* stage_buf = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes) + (warp - 2) * (32 * EPI_LD);
+    // ===================================================== epilogue warps (8: two per TMEM lane quarter)
+    // TMEM hands each lane one accumulator ROW (32 consecutive columns of a chunk).  The lanes park their rows
+    // in a padded smem tile and re-read it transposed so that one warp instruction covers 4 rows x 128 B of
+    // C / aux / out2 (full sectors) instead of 32 rows x 16 B.  The two warps of a quarter take alternate
+    // 32-column chunks.  Bias and the first aux slab are fetched BEFORE waiting for the accumulator.
+    const int ew = warp - 2;
+    const int quarter = warp & 3;       // TMEM lanes [32*quarter, +32) are accessible to this warp
+    const int half = ew >> 2;           // chunks half, half+2
+    const int sub = lane >> 3;          // row within a group of 4
+    const int c4 = (lane & 7) * 4;      // 4 consecutive columns of the 32-column chunk
+    float* stage_buf = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes) + ew * (32 * EPI_LD);
     int iter = 0;
     for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x, ++iter) {
       const TileInfo ti = decode_tile(batch, t);
@@ -253,67 +263,92 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int n0 = ti.n_blk * p.block_n;
+      const int row_base = ti.m_blk * BLOCK_M + quarter * 32;
+      const int nchunks = (p.block_n + 31) >> 5;
+      const int last_c = (half + 2 < nchunks) ? half + 2 : half;
+      const bool dsw = p.epilogue == MVAE_EPI_MUL_DSWISH;
+      // ---- prefetch (independent of the accumulator): bias of my columns, aux slab of my first chunk
+      float bv[2][4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int col = n0 + 32 * (half + 2 * k) + c4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          bv[k][q] = (p.bias != nullptr && (half + 2 * k) < nchunks && col + q < p.N) ? __ldg(p.bias + col + q) : 0.f;
+      }
+      float4 ax[8];
+      auto load_aux = [&](int c) {
+        const int col = n0 + 32 * c + c4;
+        const bool full4 = (col + 3 < p.N);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row_base + 4 * i + sub;
+          ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row < p.M && col < p.N) {
+            const float* arow = p.aux + static_cast<int64_t>(row) * p.ldaux + col;
+            if (full4) ax[i] = *reinterpret_cast<const float4*>(arow);
+            else {
+              ax[i].x = arow[0];
+              if (col + 1 < p.N) ax[i].y = arow[1];
+              if (col + 2 < p.N) ax[i].z = arow[2];
+            }
+          }
+        }
+      };
+      if (dsw && half < nchunks) load_aux(half);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
+      if (half >= nchunks) {  // nothing to do for this warp on a narrow tile: release immediately
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N_MAX;
-      // Coalescing transpose: TMEM hands each lane one accumulator ROW (32 consecutive columns); the lanes park
-      // their rows in a padded smem tile and re-read it so that one warp instruction covers 4 rows x 128 B of
-      // C / aux / out2 (full 32-byte sectors, 16 per instruction) instead of 32 rows x 16 B.
-      const int sub = lane >> 3;          // row within a group of 4
-      const int c4 = (lane & 7) * 4;      // 4 consecutive columns of the 32-column chunk
-      const int row_base = ti.m_blk * BLOCK_M + quarter * 32;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int c = half + 2 * k;
+        if (c >= nchunks) break;
+        const int c0 = 32 * c;
+        if (k == 1 && dsw) load_aux(c);
         uint32_t r[32];
         const int ncols = (p.block_n - c0) >= 32 ? 32 : 16;
         if (ncols == 32) ptx::tmem_ld_32x32(taddr_row + c0, r);
         else             ptx::tmem_ld_32x16(taddr_row + c0, r);
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= p.block_n) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+        if (c == last_c) {
+          // all TMEM reads of this warp for this accumulator are done: hand it back to the MMA warp early
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-        float4* myrow = reinterpret_cast<float4*>(stage_buf + lane * EPI_LD);
+        float* myrow = stage_buf + lane * EPI_LD;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (4 * j < ncols)
-            myrow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        for (int j = 0; j < 32; ++j)
+          if (j < ncols) myrow[j] = __uint_as_float(r[j]);
         __syncwarp();
         const int col = n0 + c0 + c4;
         const bool col_ok = (c4 < ncols) && (col < p.N);
         const bool full4 = (col + 3 < p.N);
-        float bv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.bias != nullptr && col_ok) {
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (col + q < p.N) bv[q] = __ldg(p.bias + col + q);
-        }
-#pragma unroll 2
         for (int i = 0; i < 8; ++i) {
           const int rl = 4 * i + sub;
           const int row = row_base + rl;
           if (!col_ok || row >= p.M) continue;
-          const float4 s4 = *reinterpret_cast<const float4*>(stage_buf + rl * EPI_LD + c4);
-          float v[4] = {s4.x + bv[0], s4.y + bv[1], s4.z + bv[2], s4.w + bv[3]};
+          const float* sp = stage_buf + rl * EPI_LD + c4;
+          float v[4] = {sp[0] + bv[k][0], sp[1] + bv[k][1], sp[2] + bv[k][2], sp[3] + bv[k][3]};
           float* crow = p.C + static_cast<int64_t>(row) * p.ldc;
-          if (p.epilogue == MVAE_EPI_MUL_DSWISH) {
-            const float* arow = p.aux + static_cast<int64_t>(row) * p.ldaux + col;
-            float a[4];
-            if (full4) {
-              const float4 a4 = *reinterpret_cast<const float4*>(arow);
-              a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) a[q] = (col + q < p.N) ? arow[q] : 0.f;
-            }
+          if (dsw) {
+            const float a[4] = {ax[i].x, ax[i].y, ax[i].z, ax[i].w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float sg = sigmoidf_acc(a[q]);
               v[q] *= sg * (1.0f + a[q] * (1.0f - sg));
             }
           }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cs[q] += (col + q < p.N) ? v[q] : 0.f;
           if (p.atomic) {
             if (full4) ptx::red_add_v4_f32(crow + col, v[0], v[1], v[2], v[3]);
             else {
@@ -342,12 +377,25 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
             }
           }
         }
+        if (p.colsum != nullptr) {
+          // bias gradient: column sums of the stored tile (32 rows of this warp) -> one red.add per column
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
+            cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
+          }
+          if (sub == 0 && col_ok) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (col + q < p.N) ptx::red_add_f32(p.colsum + col + q, cs[q]);
+          }
+        }
         __syncwarp();  // staging tile is rewritten by the next chunk
       }
     }
   } else if (kSplit) {
     // ===================================================== operand splitters (3xTF32 only)
-    const int tid = threadIdx.x - 32 * (2 + NUM_EPI_WARPS);  // 0..127
+    const int tid = threadIdx.x - 32 * (2 + NUM_EPI_WARPS);  // 0..127 (warps 10..13)
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x) {
@@ -460,7 +508,7 @@ extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision
       return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: unknown epilogue %d", i, d.epilogue);
     const int split = d.split_k < 1 ? 1 : d.split_k;
     const bool atomic = split > 1 || d.accumulate;
-    if (atomic && (d.bias || d.epilogue != MVAE_EPI_STORE))
+    if (atomic && (d.bias || d.epilogue != MVAE_EPI_STORE || d.colsum))
       return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: split_k/accumulate only with plain STORE epilogue", i);
     if ((d.ldc & 3) || (reinterpret_cast<uintptr_t>(d.C) & 15))
       return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: C must be 16B aligned with ldc %% 4 == 0", i);
@@ -481,7 +529,7 @@ extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision
     p.b_mn = d.b_mn_major ? 1 : 0;
     p.epilogue = d.epilogue;
     p.atomic = atomic ? 1 : 0;
-    p.C = d.C; p.bias = d.bias; p.aux = d.aux; p.out2 = d.out2;
+    p.C = d.C; p.bias = d.bias; p.aux = d.aux; p.out2 = d.out2; p.colsum = d.colsum;
     p.ldc = d.ldc; p.ldaux = d.ldaux; p.ldout2 = d.ldout2;
     const MnEncoding mn = mn_encoding();
     p.a_lbo = p.a_mn ? mn.lbo : 16u;  p.a_sbo = p.a_mn ? mn.sbo : 1024u;

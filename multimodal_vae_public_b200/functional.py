@@ -250,6 +250,51 @@ class _BceSumFn(Function):
         return (dx * g).reshape(ctx.shape), None
 
 
+class _BceElemFn(Function):
+    """Element-wise binary_cross_entropy_with_logits (same-shape output, mnist/train.py:62-74)."""
+
+    @staticmethod
+    def forward(ctx, x, t):
+        _need_cuda(x, t)
+        if t.size() != x.size():
+            raise ValueError("Target size ({}) must be the same as input size ({})".format(t.size(), x.size()))
+        n = x.numel()
+        pad = (-n) % 4
+        xf = torch.zeros(n + pad, dtype=torch.float32, device=x.device); xf[:n] = x.detach().reshape(-1)
+        tf = torch.zeros(n + pad, dtype=torch.float32, device=x.device); tf[:n] = t.detach().reshape(-1)
+        le = torch.empty_like(xf); dx = torch.empty_like(xf)
+        ops.bce_logits_fwd_bwd(xf.view(1, -1), tf.view(1, -1), dx.view(1, -1), 1.0, None, loss_elem=le.view(1, -1))
+        ctx.save_for_backward(dx[:n].view(x.shape))
+        return le[:n].view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None
+
+
+class _CeRowsFn(Function):
+    """cross_entropy(input, target, eps=1e-6) -> [N, K] = -onehot * log_softmax (mnist/train.py:77-94)."""
+
+    @staticmethod
+    def forward(ctx, x, target):
+        _need_cuda(x, target)
+        if target.size(0) != x.size(0):
+            raise ValueError("Target size ({}) must be the same as input size ({})".format(target.size(0), x.size(0)))
+        x2 = x.detach().to(torch.float32).contiguous()
+        R, K = x2.shape
+        out = torch.empty(R, K, dtype=torch.float32, device=x.device); dx = torch.empty_like(out)
+        ops.ce_fwd_bwd(x2, target.detach().to(torch.int64).contiguous(), dx, K, 1.0, None, loss_rows=out)
+        ctx.save_for_backward(dx, target.detach().to(torch.int64))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        dx, tg = ctx.saved_tensors
+        # d/dx sum_k g[r,k]*out[r,k] = g[r,target_r] * (softmax - onehot)
+        return dx * g.gather(1, tg.view(-1, 1)), None
+
+
 class _CeSumFn(Function):
     """sum over rows of cross_entropy(input, target, eps=1e-6) (mnist/train.py:77-94)."""
 
@@ -295,6 +340,14 @@ class _KlSumFn(Function):
 
 def bce_with_logits_sum(x, t):
     return _BceSumFn.apply(x, t)
+
+
+def bce_with_logits(x, t):
+    return _BceElemFn.apply(x, t)
+
+
+def cross_entropy_rows(x, target):
+    return _CeRowsFn.apply(x, target)
 
 
 def cross_entropy_sum(x, target):

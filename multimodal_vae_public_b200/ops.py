@@ -29,7 +29,7 @@ def _chk2d(t: torch.Tensor, name: str):
 
 
 def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, out2=None, epilogue=EPI_STORE,
-              split_k=1, accumulate=False) -> GemmDesc:
+              split_k=1, accumulate=False, colsum=None) -> GemmDesc:
     d = GemmDesc()
     d.A, d.lda, d.a_mn_major = A.data_ptr(), A.stride(0), int(a_mn)
     d.B, d.ldb, d.b_mn_major = B.data_ptr(), B.stride(0), int(b_mn)
@@ -38,6 +38,7 @@ def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, 
     d.bias = _p(bias)
     d.aux, d.ldaux = _p(aux), (aux.stride(0) if aux is not None else 0)
     d.out2, d.ldout2 = _p(out2), (out2.stride(0) if out2 is not None else 0)
+    d.colsum = _p(colsum)
     d.epilogue, d.split_k, d.accumulate = epilogue, split_k, int(accumulate)
     return d
 
@@ -145,19 +146,22 @@ def kl_fwd_bwd(mu, logvar, dmu, dlogvar, scale, kl_acc=None):
                                            float(scale), _p(kl_acc), _stream()), "mvae_kl_fwd_bwd")
 
 
-def bce_logits_fwd_bwd(x, t, dx, scale, loss_acc=None, seg_rows=0):
+def bce_logits_fwd_bwd(x, t, dx, scale, loss_acc=None, seg_rows=0, loss_elem=None):
     """x [R,D] logits, t [t_rows,D] targets (row r uses t[r % t_rows])."""
     R, D = x.shape
     _lib.check(_lib.load().mvae_bce_logits_fwd_bwd(x.data_ptr(), x.stride(0), t.data_ptr(), t.stride(0), t.shape[0],
                                                    _p(dx), dx.stride(0) if dx is not None else 0, R, D, float(scale),
-                                                   _p(loss_acc), seg_rows, _stream()), "mvae_bce_logits_fwd_bwd")
+                                                   _p(loss_acc), seg_rows, _p(loss_elem),
+                                                   loss_elem.stride(0) if loss_elem is not None else 0, _stream()),
+               "mvae_bce_logits_fwd_bwd")
 
 
-def ce_fwd_bwd(x, target, dx, K, scale, loss_acc=None, seg_rows=0):
+def ce_fwd_bwd(x, target, dx, K, scale, loss_acc=None, seg_rows=0, loss_rows=None):
     R = x.shape[0]
     _lib.check(_lib.load().mvae_ce_fwd_bwd(x.data_ptr(), x.stride(0), target.data_ptr(), target.numel(), _p(dx),
                                            dx.stride(0) if dx is not None else 0, R, K, float(scale), _p(loss_acc),
-                                           seg_rows, _stream()), "mvae_ce_fwd_bwd")
+                                           seg_rows, _p(loss_rows), loss_rows.stride(0) if loss_rows is not None else 0,
+                                           _stream()), "mvae_ce_fwd_bwd")
 
 
 def adam_flat(p, g, m, v, step_count, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, lr_mult_dev=None):

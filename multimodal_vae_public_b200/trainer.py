@@ -232,27 +232,29 @@ class MnistMVAETrainer:
         # ---- decoders backward, the two decoders batched per layer
         dyi, dyt = self.logit_i, self.logit_t
         nk = max(1, (2 * B) // 32)  # k-blocks of a decoder wgrad
+        ops.colsum_accumulate(dyi, g["image_decoder.fc4.bias"])
+        ops.colsum_accumulate(dyt, g["text_decoder.fc4.bias"])
         for l in (4, 3, 2, 1):
             n_i = 784 if l == 4 else 512
             n_t = 10 if l == 4 else 512
             K = L if l == 1 else 512
             x_i = self.Z[: 2 * B] if l == 1 else self.id_h[l - 2]
             x_t = self.Z[B:] if l == 1 else self.td_h[l - 2]
-            ops.colsum_accumulate(dyi, g[f"image_decoder.fc{l}.bias"])
-            ops.colsum_accumulate(dyt, g[f"text_decoder.fc{l}.bias"])
             split = max(1, min(nk // 8, 8))
             descs = [
                 ops.gemm_desc(dyi, x_i, g[f"image_decoder.fc{l}.weight"], n_i, K, 2 * B, a_mn=True, b_mn=True,
                               split_k=split, accumulate=True),
                 ops.gemm_desc(dyt, x_t, g[f"text_decoder.fc{l}.weight"], n_t, K, 2 * B, a_mn=True, b_mn=True,
                               split_k=split, accumulate=True)]
-            if l > 1:
+            if l > 1:  # dA_{l-1} = (dy W_l) * swish'(a_{l-1}); its column sums are the bias gradient of layer l-1
                 dxi, dxt = self.id_dA[l % 2], self.td_dA[l % 2]
                 descs += [
                     ops.gemm_desc(dyi, p[f"image_decoder.fc{l}.weight"], dxi, 2 * B, K, n_i, b_mn=True,
-                                  aux=self.id_a[l - 2], epilogue=ops.EPI_MUL_DSWISH),
+                                  aux=self.id_a[l - 2], epilogue=ops.EPI_MUL_DSWISH,
+                                  colsum=g[f"image_decoder.fc{l - 1}.bias"]),
                     ops.gemm_desc(dyt, p[f"text_decoder.fc{l}.weight"], dxt, 2 * B, K, n_t, b_mn=True,
-                                  aux=self.td_a[l - 2], epilogue=ops.EPI_MUL_DSWISH)]
+                                  aux=self.td_a[l - 2], epilogue=ops.EPI_MUL_DSWISH,
+                                  colsum=g[f"text_decoder.fc{l - 1}.bias"])]
             else:  # dZ is zero-initialised; both decoders add into it (the joint rows get both)
                 dxi, dxt = self.dZ[: 2 * B], self.dZ[B:]
                 descs += [
@@ -282,19 +284,18 @@ class MnistMVAETrainer:
         ops.gemm_batch([
             ops.gemm_desc(self.d_enc_i, self.ie_h2, gwi, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True),
             ops.gemm_desc(self.d_enc_t, self.te_h2, gwt, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True),
-            ops.gemm_desc(self.d_enc_i, wi, self.ie_dA[0], B, 512, 2 * L, b_mn=True, aux=self.ie_a2, epilogue=ops.EPI_MUL_DSWISH),
-            ops.gemm_desc(self.d_enc_t, wt, self.te_dA[0], B, 512, 2 * L, b_mn=True, aux=self.te_a2, epilogue=ops.EPI_MUL_DSWISH)], P)
-        ops.colsum_accumulate(self.ie_dA[0], g["image_encoder.fc2.bias"])
-        ops.colsum_accumulate(self.te_dA[0], g["text_encoder.fc2.bias"])
+            ops.gemm_desc(self.d_enc_i, wi, self.ie_dA[0], B, 512, 2 * L, b_mn=True, aux=self.ie_a2,
+                          epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc2.bias"]),
+            ops.gemm_desc(self.d_enc_t, wt, self.te_dA[0], B, 512, 2 * L, b_mn=True, aux=self.te_a2,
+                          epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_encoder.fc2.bias"])], P)
         ops.gemm_batch([
             ops.gemm_desc(self.ie_dA[0], self.ie_h1, g["image_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
                           split_k=split, accumulate=True),
             ops.gemm_desc(self.te_dA[0], self.te_h1, g["text_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
                           split_k=split, accumulate=True),
             ops.gemm_desc(self.ie_dA[0], p["image_encoder.fc2.weight"], self.ie_dA[1], B, 512, 512, b_mn=True,
-                          aux=self.ie_a1, epilogue=ops.EPI_MUL_DSWISH),
+                          aux=self.ie_a1, epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc1.bias"]),
             ops.gemm_desc(self.te_dA[0], p["text_encoder.fc2.weight"], self.te_dA[1], B, 512, 512, b_mn=True)], P)
-        ops.colsum_accumulate(self.ie_dA[1], g["image_encoder.fc1.bias"])
         ops.gemm_batch([ops.gemm_desc(self.ie_dA[1], self.x, g["image_encoder.fc1.weight"], 512, 784, B, a_mn=True,
                                       b_mn=True, split_k=split, accumulate=True)], P)
         ops.embedding_swish_bwd(p["text_encoder.fc1.weight"], self.text, self.te_dA[1], g["text_encoder.fc1.weight"])

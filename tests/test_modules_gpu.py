@@ -97,3 +97,25 @@ def test_errors_like_reference():
         T.binary_cross_entropy_with_logits(torch.zeros(3, 4, device="cuda"), torch.zeros(3, 5, device="cuda"))
     with pytest.raises(ValueError):
         T.cross_entropy(torch.zeros(3, 10, device="cuda"), torch.zeros(4, dtype=torch.long, device="cuda"))
+
+
+def test_elementwise_loss_functions_match_oracle():
+    from multimodal_vae_public_b200.mnist import train as T
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy((3 * rs.standard_normal((5, 7))).astype(np.float32)).cuda().requires_grad_(True)
+    t = torch.from_numpy(rs.uniform(0, 1, (5, 7)).astype(np.float32)).cuda()
+    out = T.binary_cross_entropy_with_logits(x, t)
+    w = torch.from_numpy(rs.standard_normal((5, 7)).astype(np.float32)).cuda()
+    (out * w).sum().backward()
+    xr = x.detach().cpu().double().requires_grad_(True)
+    ro = O.bce_with_logits(xr, t.cpu().double()); (ro * w.cpu().double()).sum().backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), ro.detach().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), xr.grad.numpy(), rtol=2e-5, atol=1e-6)
+    lg = torch.from_numpy((2 * rs.standard_normal((6, 10))).astype(np.float32)).cuda().requires_grad_(True)
+    tg = torch.from_numpy(rs.randint(0, 10, 6)).cuda()
+    ce = T.cross_entropy(lg, tg)
+    ce.sum(dim=1).mean().backward()
+    lr = lg.detach().cpu().double().requires_grad_(True)
+    rce = O.cross_entropy_rows(lr, tg.cpu()); rce.sum(dim=1).mean().backward()
+    np.testing.assert_allclose(ce.detach().cpu().numpy(), rce.detach().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(lg.grad.cpu().numpy(), lr.grad.numpy(), rtol=2e-5, atol=1e-7)
