@@ -9,8 +9,9 @@
 //   warp 1      : MMA issuer     -- one elected lane issues tcgen05.mma (M=128, N<=128, K=8 per instr)
 //   warps 2..9  : epilogue       -- tcgen05.ld TMEM -> registers -> smem transpose -> bias / Swish / dSwish /
 //                                   bias-gradient column sums -> coalesced global stores (or red.add)
-//   warps 10..13: operand split  -- (3xTF32 mode only) x -> hi = rna_tf32(x), lo = x - hi in smem,
-//                                   then 3 MMAs/product: hi*hi + hi*lo + lo*hi  (fp32-class accuracy)
+//   warps 10..13: operand split  -- (3xTF32 mode only) A -> hi|lo in TENSOR MEMORY (tcgen05.st), B -> lo tile in
+//                                   smem (raw B is the hi operand: kind::tf32 truncates), then 3 MMAs/product:
+//                                   lo*hi + hi*lo + hi*hi with A read from TMEM (fp32-class accuracy)
 // Pipelines: smem full/ready/empty mbarrier ring; double-buffered TMEM accumulators (2 x 128 columns)
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 //
@@ -35,7 +36,8 @@ constexpr int BLOCK_N_MAX = 128;
 constexpr int BLOCK_K = 32;                                 // 32 fp32 = 128 B = one swizzle row
 constexpr int UMMA_K = 8;                                   // tf32: 32 B per MMA along K
 constexpr int OPERAND_BYTES = BLOCK_M * BLOCK_K * 4;        // 16 KiB per operand per stage
-constexpr int TMEM_COLS = 256;                              // 2 accumulator stages x 128 fp32 columns
+constexpr int ACC_COLS = 256;                               // 2 accumulator stages x 128 fp32 columns
+constexpr int A_STAGE_COLS = 64;                            // 3xTF32: A operand hi (32 cols) | lo (32 cols) per stage
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_SPLIT_WARPS = 4;
 constexpr int EPI_LD = 33;                                  // padded row (floats) of the epilogue staging tile (conflict-free scalar access)
@@ -43,8 +45,11 @@ constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * EPI_LD * 4;
 
 template <bool kSplit>
 struct Cfg {
-  static constexpr int kStageBytes = kSplit ? 4 * OPERAND_BYTES : 2 * OPERAND_BYTES;  // 64 / 32 KiB
-  static constexpr int kStages = kSplit ? 3 : 6;                                       // 192 KiB ring
+  // tf32 : [A][B]            32 KiB x 6 stages
+  // 3x   : [A raw][B raw][B lo] 48 KiB x 4 stages; the A operand is re-staged as hi|lo in TENSOR MEMORY
+  static constexpr int kStageBytes = kSplit ? 3 * OPERAND_BYTES : 2 * OPERAND_BYTES;
+  static constexpr int kStages = kSplit ? 4 : 6;                                       // 192 KiB ring
+  static constexpr int kTmemCols = kSplit ? 512 : 256;
   static constexpr int kThreads = 32 * (2 + NUM_EPI_WARPS + (kSplit ? NUM_SPLIT_WARPS : 0));
   static constexpr int kSmemBytes = kStages * kStageBytes + EPI_STAGE_BYTES + 1024;  // + 1024 B alignment slack
 };
@@ -155,7 +160,7 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    ptx::tmem_alloc(&tmem_base_smem, C::kTmemCols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N_MAX;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(p.a_mn) << 15) |
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kSplit ? 0 : p.a_mn) << 15) |
                                (static_cast<uint32_t>(p.b_mn) << 16) |
                                (static_cast<uint32_t>(p.block_n >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
         const uint32_t a_lbo = p.a_lbo, a_sbo = p.a_sbo, a_kstep = p.a_kstep, a_lay = p.a_layout;
@@ -225,15 +230,17 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
           const uint32_t sb = sa + OPERAND_BYTES;
 #pragma unroll
           for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-            const uint64_t da = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lay);
             const uint64_t db = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lay);
             if (kSplit) {
-              const uint64_t da_lo = make_desc(sa + 2 * OPERAND_BYTES + ks * a_kstep, a_lbo, a_sbo, a_lay);
-              const uint64_t db_lo = make_desc(sb + 2 * OPERAND_BYTES + ks * b_kstep, b_lbo, b_sbo, b_lay);
-              ptx::mma_tf32_ss(d_tmem, da_lo, db, idesc, accumulate);  // lo*hi
-              ptx::mma_tf32_ss(d_tmem, da, db_lo, idesc, 1u);          // hi*lo
-              ptx::mma_tf32_ss(d_tmem, da, db, idesc, 1u);             // hi*hi
+              // A (hi | lo) comes from tensor memory, B raw (= hi by hardware truncation) and B lo from smem
+              const uint32_t a_hi = tmem_base + ACC_COLS + stage * A_STAGE_COLS + ks * UMMA_K;
+              const uint32_t a_lo = a_hi + 32;
+              const uint64_t db_lo = make_desc(sb + OPERAND_BYTES + ks * b_kstep, b_lbo, b_sbo, b_lay);
+              ptx::mma_tf32_ts(d_tmem, a_lo, db, idesc, accumulate);  // lo*hi
+              ptx::mma_tf32_ts(d_tmem, a_hi, db_lo, idesc, 1u);       // hi*lo
+              ptx::mma_tf32_ts(d_tmem, a_hi, db, idesc, 1u);          // hi*hi
             } else {
+              const uint64_t da = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lay);
               ptx::mma_tf32_ss(d_tmem, da, db, idesc, accumulate);
             }
             accumulate = 1u;
@@ -394,28 +401,69 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       }
     }
   } else if (kSplit) {
-    // ===================================================== operand splitters (3xTF32 only)
-    const int tid = threadIdx.x - 32 * (2 + NUM_EPI_WARPS);  // 0..127 (warps 10..13)
+    // ===================================================== operand splitters (3xTF32 only), warps 10..13
+    // A: each thread owns one of the 128 tile rows; it gathers the row's 32 k-values from the swizzled smem tile,
+    //    splits x = hi + lo (hi = rna_tf32(x), exact remainder lo) and stores both halves to TENSOR MEMORY
+    //    (lane = row, 32 + 32 columns), from where the MMA reads its A operand -- this halves the tensor core's
+    //    shared-memory traffic.  B: raw fp32 stays in smem and IS the hi operand (kind::tf32 truncates its
+    //    operands: measured), only lo = x - trunc_tf32(x) is written to a second smem tile.
+    const int tid = threadIdx.x - 32 * (2 + NUM_EPI_WARPS);  // 0..127
+    const int quarter = warp & 3;                              // TMEM lanes [32*quarter, +32) are writable by this warp
+    const int row = quarter * 32 + lane;                       // tile row owned by this thread
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x) {
       const TileInfo ti = decode_tile(batch, t);
+      const int a_mn = batch.p[ti.prob].a_mn;
       for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
-        float4* hi = reinterpret_cast<float4*>(smem + stage * C::kStageBytes);
-        float4* lo = hi + (2 * OPERAND_BYTES) / 16;
-#pragma unroll 4
-        for (int i = tid; i < (2 * OPERAND_BYTES) / 16; i += NUM_SPLIT_WARPS * 32) {
-          const float4 x = hi[i];
-          float4 h, l;
-          h.x = ptx::round_tf32(x.x); l.x = x.x - h.x;
-          h.y = ptx::round_tf32(x.y); l.y = x.y - h.y;
-          h.z = ptx::round_tf32(x.z); l.z = x.z - h.z;
-          h.w = ptx::round_tf32(x.w); l.w = x.w - h.w;
-          hi[i] = h;
-          lo[i] = l;
+        const uint8_t* sa = smem + stage * C::kStageBytes;
+        uint32_t hi[32], lo[32];
+        if (!a_mn) {
+          // K-major tile: row r at r*128 B, 16-byte chunks XOR-swizzled with (r & 7)
+          const uint8_t* rp = sa + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(rp + ((j ^ (row & 7)) << 4));
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float h = ptx::round_tf32(xs[q]);
+              hi[4 * j + q] = __float_as_uint(h);
+              lo[4 * j + q] = __float_as_uint(xs[q] - h);
+            }
+          }
+        } else {
+          // MN-major tile: 4 boxes of [32 k-rows][32 m]; box = quarter; 32-byte chunks XOR-swizzled with (k & 3)
+          const uint8_t* bp = sa + quarter * 4096 + ((lane & 7) << 2);
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float x = *reinterpret_cast<const float*>(bp + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+            const float h = ptx::round_tf32(x);
+            hi[k] = __float_as_uint(h);
+            lo[k] = __float_as_uint(x - h);
+          }
         }
-        ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ACC_COLS + stage * A_STAGE_COLS;
+        ptx::tmem_st_32x32(ta, hi);
+        ptx::tmem_st_32x32(ta + 32, lo);
+        // B: lo tile only
+        const float4* braw = reinterpret_cast<const float4*>(sa + OPERAND_BYTES);
+        float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(sa) + 2 * OPERAND_BYTES);
+#pragma unroll
+        for (int i = 0; i < OPERAND_BYTES / 16 / (NUM_SPLIT_WARPS * 32); ++i) {
+          const int idx = tid + i * (NUM_SPLIT_WARPS * 32);
+          const float4 x = braw[idx];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          blo[idx] = l;
+        }
+        ptx::tmem_st_wait();
+        ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        ptx::tc_fence_before();
         ptx::mbar_arrive(&ready_bar[stage]);
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
       }
@@ -426,7 +474,7 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 

@@ -240,7 +240,7 @@ class MnistMVAETrainer:
             K = L if l == 1 else 512
             x_i = self.Z[: 2 * B] if l == 1 else self.id_h[l - 2]
             x_t = self.Z[B:] if l == 1 else self.td_h[l - 2]
-            split = max(1, min(nk // 8, 8))
+            split = max(1, min(nk // 16, 32))   # ~16 k-blocks per wgrad tile, like the dgrad tiles of the same launch
             descs = [
                 ops.gemm_desc(dyi, x_i, g[f"image_decoder.fc{l}.weight"], n_i, K, 2 * B, a_mn=True, b_mn=True,
                               split_k=split, accumulate=True),
@@ -271,7 +271,7 @@ class MnistMVAETrainer:
                     training=training, noise=self.noise if training else None, kl_scale_dev=self.beta_dev)
         # ---- encoders backward
         nk = max(1, B // 32)
-        split = max(1, min(nk // 8, 8))
+        split = max(1, min(nk // 16, 32))
         arena = self.arena
         gwi = arena.span(1, "image_encoder.fc31.weight", "image_encoder.fc32.weight").view(2 * L, 512)
         gbi = arena.span(1, "image_encoder.fc31.bias", "image_encoder.fc32.bias")
