@@ -40,8 +40,7 @@ constexpr int ACC_COLS = 256;                               // 2 accumulator sta
 constexpr int A_STAGE_COLS = 64;                            // 3xTF32: A operand hi (32 cols) | lo (32 cols) per stage
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_SPLIT_WARPS = 4;
-constexpr int EPI_LD = 33;                                  // padded row (floats) of the epilogue staging tile (conflict-free scalar access)
-constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * EPI_LD * 4;
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // one swizzled 32x32 fp32 staging tile per epilogue warp
 
 template <bool kSplit>
 struct Cfg {
@@ -82,7 +81,16 @@ struct GemmBatch {
   GemmProblem p[MVAE_GEMM_MAX_BATCH];
   int num_problems;
   int total_tiles;
+  long long* dbg;   // optional timeline buffer (MVAE_DBG_TIMELINE): [block < 8][role < 4][64] clock64 stamps
+  int dbg_flags;    // MVAE_DBG_EPI: 1 = skip global stores, 2 = skip sigmoid math, 4 = skip smem transpose
 };
+
+__device__ __forceinline__ void dbg_stamp(const GemmBatch& b, int role, int& n) {
+  if (b.dbg != nullptr && blockIdx.x < 8 && n < 64) {
+    b.dbg[(blockIdx.x * 4 + role) * 64 + n] = clock64();
+    ++n;
+  }
+}
 
 struct TileInfo {
   int prob, m_blk, n_blk, kb_begin, kb_end;
@@ -126,7 +134,129 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Epilogue sigmoid: ex2.approx + rcp.approx (5 instructions; max relative error ~ (2 + |x|) * 2^-23).  The epilogue
+// runs on 8 warps next to a tensor-core main loop of ~9 K cycles per tile, so instructions per element are the
+// budget: the IEEE expf / correctly rounded reciprocal version cost ~45 instructions per element and made the
+// epilogue (not the MMA) the critical path (profiles/r01_epilogue_ablation.txt).
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// Per-tile epilogue parameters, copied into registers once per tile (the problem table lives in kernel-parameter
+// space and is indexed dynamically; re-reading it inside the element loops is slow).
+struct EpiParams {
+  float* C;
+  const float* bias;
+  const float* aux;
+  float* out2;
+  float* colsum;
+  int64_t ldc, ldaux, ldout2;
+  int M, N;
+  int epilogue, atomic;
+};
+
+__device__ __forceinline__ float4 load_aux4(const EpiParams& e, int row, int col, int nvalid) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row < e.M && nvalid > 0) {
+    const float* arow = e.aux + static_cast<int64_t>(row) * e.ldaux + col;
+    if (nvalid == 4) a = *reinterpret_cast<const float4*>(arow);
+    else {
+      a.x = arow[0];
+      if (nvalid > 1) a.y = arow[1];
+      if (nvalid > 2) a.z = arow[2];
+    }
+  }
+  return a;
+}
+
+// One 32x32 accumulator chunk of one epilogue warp.  `st4` is the warp's 4 KiB staging tile (32 rows x 8 float4,
+// float4 index XOR-swizzled with (row & 7): conflict-free for the row-wise writes and the transposed reads).
+// The row loop is deliberately NOT unrolled: the fully unrolled version was instruction-fetch bound (the epilogue
+// is executed once per tile, ~25 KiB of straight-line code per pass, see profiles/r01_epilogue_ablation.txt).
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float4* st4, const uint32_t (&r)[32], int ncols,
+                                               int lane, int row_base, int col0, const float (&bv)[4], float4 a_next,
+                                               int dbg_flags) {
+  const int sub = lane >> 3, cq = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (4 * j < ncols)
+      st4[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+  __syncwarp();
+  const int col = col0 + 4 * cq;
+  int nvalid = e.N - col;                       // valid columns of this lane's float4 (0..4)
+  nvalid = (4 * cq < ncols) ? (nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid)) : 0;
+  const bool dsw = e.epilogue == MVAE_EPI_MUL_DSWISH;
+  const bool bsw = e.epilogue == MVAE_EPI_BIAS_SWISH;
+  const bool want_cs = e.colsum != nullptr;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + sub;
+    const int row = row_base + rl;
+    const float4 a_cur = a_next;
+    if (dsw && i < 7) a_next = load_aux4(e, row + 4, col, nvalid);   // one row group ahead
+    if (nvalid == 0 || row >= e.M) continue;
+    const float4 s4 = st4[rl * 8 + (cq ^ (rl & 7))];
+    float v[4] = {s4.x + bv[0], s4.y + bv[1], s4.z + bv[2], s4.w + bv[3]};
+    if (dsw && !(dbg_flags & 2)) {
+      const float a[4] = {a_cur.x, a_cur.y, a_cur.z, a_cur.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float sg = sigmoidf_acc(a[q]);
+        v[q] *= sg * (1.0f + a[q] * (1.0f - sg));
+      }
+    }
+    if (want_cs) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cs[q] += (q < nvalid) ? v[q] : 0.f;
+    }
+    float* cptr = e.C + static_cast<int64_t>(row) * e.ldc + col;
+    if (dbg_flags & 1) {
+      if (v[0] == 123.456f) *cptr = v[1] + v[2] + v[3];
+    } else if (e.atomic) {
+      if (nvalid == 4) ptx::red_add_v4_f32(cptr, v[0], v[1], v[2], v[3]);
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nvalid) ptx::red_add_f32(cptr + q, v[q]);
+      }
+    } else {
+      if (nvalid == 4) *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nvalid) cptr[q] = v[q];
+      }
+    }
+    if (bsw) {
+      float* hptr = e.out2 + static_cast<int64_t>(row) * e.ldout2 + col;
+      float h[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) h[q] = (dbg_flags & 2) ? v[q] * 0.5f : v[q] * sigmoidf_acc(v[q]);
+      if (dbg_flags & 1) {
+        if (h[0] == 123.456f) *hptr = h[1] + h[2] + h[3];
+      } else if (nvalid == 4) *reinterpret_cast<float4*>(hptr) = make_float4(h[0], h[1], h[2], h[3]);
+      else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nvalid) hptr[q] = h[q];
+      }
+    }
+  }
+  if (want_cs) {
+    // bias gradient: column sums of the stored tile (32 rows of this warp) -> one red.add per column
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
+      cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
+    }
+    if (sub == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < nvalid) ptx::red_add_f32(e.colsum + col + q, cs[q]);
+    }
+  }
+  __syncwarp();  // the staging tile is rewritten by the next chunk
+}
 
 template <bool kSplit>
 __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __grid_constant__ GemmBatch batch) {
@@ -173,32 +303,38 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int dn = 0;
+      dbg_stamp(batch, 0, dn);
       for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x) {
         const TileInfo ti = decode_tile(batch, t);
         const GemmProblem& p = batch.p[ti.prob];
+        const int block_n = p.block_n, a_mn = p.a_mn, b_mn = p.b_mn;
+        const CUtensorMap* map_a = &p.map_a;
+        const CUtensorMap* map_b = &p.map_b;
         const int m0 = ti.m_blk * BLOCK_M;
-        const int n0 = ti.n_blk * p.block_n;
+        const int n0 = ti.n_blk * block_n;
         const uint32_t a_bytes = OPERAND_BYTES;
-        const uint32_t b_bytes = static_cast<uint32_t>(p.block_n) * BLOCK_K * 4;
+        const uint32_t b_bytes = static_cast<uint32_t>(block_n) * BLOCK_K * 4;
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + OPERAND_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
           const int k0 = kb * BLOCK_K;
-          if (!p.a_mn) {
-            ptx::tma_load_2d(sa, &p.map_a, &full_bar[stage], k0, m0);  // box {32 k, 128 rows}
+          if (!a_mn) {
+            ptx::tma_load_2d(sa, map_a, &full_bar[stage], k0, m0);  // box {32 k, 128 rows}
           } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 32; ++j)                       // 4 boxes {32 m, 32 k-rows}
-              ptx::tma_load_2d(sa + j * 4096, &p.map_a, &full_bar[stage], m0 + 32 * j, k0);
+            for (int j = 0; j < BLOCK_M / 32; ++j)                    // 4 boxes {32 m, 32 k-rows}
+              ptx::tma_load_2d(sa + j * 4096, map_a, &full_bar[stage], m0 + 32 * j, k0);
           }
-          if (!p.b_mn) {
-            ptx::tma_load_2d(sb, &p.map_b, &full_bar[stage], k0, n0);  // box {32 k, block_n rows}
+          if (!b_mn) {
+            ptx::tma_load_2d(sb, map_b, &full_bar[stage], k0, n0);  // box {32 k, block_n rows}
           } else {
-            for (int j = 0; j < p.block_n / 32; ++j)
-              ptx::tma_load_2d(sb + j * 4096, &p.map_b, &full_bar[stage], n0 + 32 * j, k0);
+            for (int j = 0; j < block_n / 32; ++j)
+              ptx::tma_load_2d(sb + j * 4096, map_b, &full_bar[stage], n0 + 32 * j, k0);
           }
+          dbg_stamp(batch, 0, dn);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -209,6 +345,8 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
+      int dn = 0;
+      dbg_stamp(batch, 1, dn);
       for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x, ++iter) {
         const TileInfo ti = decode_tile(batch, t);
         const GemmProblem& p = batch.p[ti.prob];
@@ -226,6 +364,7 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           ptx::mbar_wait(kSplit ? &ready_bar[stage] : &full_bar[stage], phase);
           ptx::tc_fence_after();
+          dbg_stamp(batch, 1, dn);
           const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
           const uint32_t sb = sa + OPERAND_BYTES;
 #pragma unroll
@@ -262,8 +401,9 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
     const int half = ew >> 2;           // chunks half, half+2
     const int sub = lane >> 3;          // row within a group of 4
     const int c4 = (lane & 7) * 4;      // 4 consecutive columns of the 32-column chunk
-    float* stage_buf = reinterpret_cast<float*>(smem + C::kStages * C::kStageBytes) + ew * (32 * EPI_LD);
+    float4* stage_buf = reinterpret_cast<float4*>(smem + C::kStages * C::kStageBytes) + ew * (32 * 8);
     int iter = 0;
+    int dn = 0, dn3 = 0;
     for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x, ++iter) {
       const TileInfo ti = decode_tile(batch, t);
       const GemmProblem& p = batch.p[ti.prob];
@@ -271,40 +411,30 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int n0 = ti.n_blk * p.block_n;
       const int row_base = ti.m_blk * BLOCK_M + quarter * 32;
-      const int nchunks = (p.block_n + 31) >> 5;
+      const int block_n = p.block_n;
+      const int nchunks = (block_n + 31) >> 5;
       const int last_c = (half + 2 < nchunks) ? half + 2 : half;
-      const bool dsw = p.epilogue == MVAE_EPI_MUL_DSWISH;
-      // ---- prefetch (independent of the accumulator): bias of my columns, aux slab of my first chunk
-      float bv[2][4];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int col = n0 + 32 * (half + 2 * k) + c4;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          bv[k][q] = (p.bias != nullptr && (half + 2 * k) < nchunks && col + q < p.N) ? __ldg(p.bias + col + q) : 0.f;
-      }
-      float4 ax[8];
-      auto load_aux = [&](int c) {
+      EpiParams e;
+      e.C = p.C; e.bias = p.bias; e.aux = p.aux; e.out2 = p.out2; e.colsum = p.colsum;
+      e.ldc = p.ldc; e.ldaux = p.ldaux; e.ldout2 = p.ldout2; e.M = p.M; e.N = p.N;
+      e.epilogue = p.epilogue; e.atomic = p.atomic;
+      const bool dsw = e.epilogue == MVAE_EPI_MUL_DSWISH;
+      // ---- prefetch (independent of the accumulator): bias of my columns, first aux row group of my first chunk
+      float bv[4];
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto prefetch = [&](int c) {
         const int col = n0 + 32 * c + c4;
-        const bool full4 = (col + 3 < p.N);
+        int nvalid = e.N - col;
+        nvalid = (c4 < block_n - 32 * c) ? (nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid)) : 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = row_base + 4 * i + sub;
-          ax[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < p.M && col < p.N) {
-            const float* arow = p.aux + static_cast<int64_t>(row) * p.ldaux + col;
-            if (full4) ax[i] = *reinterpret_cast<const float4*>(arow);
-            else {
-              ax[i].x = arow[0];
-              if (col + 1 < p.N) ax[i].y = arow[1];
-              if (col + 2 < p.N) ax[i].z = arow[2];
-            }
-          }
-        }
+        for (int q = 0; q < 4; ++q) bv[q] = (e.bias != nullptr && q < nvalid) ? __ldg(e.bias + col + q) : 0.f;
+        if (dsw) a0 = load_aux4(e, row_base + sub, col, nvalid);
       };
-      if (dsw && half < nchunks) load_aux(half);
+      if (half < nchunks) prefetch(half);
+      if (ew == 0 && lane == 0) dbg_stamp(batch, 2, dn);
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
+      if (ew == 0 && lane == 0) dbg_stamp(batch, 2, dn);
       if (half >= nchunks) {  // nothing to do for this warp on a narrow tile: release immediately
         ptx::tc_fence_before();
         __syncwarp();
@@ -312,14 +442,12 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
         continue;
       }
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N_MAX;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int c = half + 2 * k;
-        if (c >= nchunks) break;
+#pragma unroll 1
+      for (int c = half; c < nchunks; c += 2) {
         const int c0 = 32 * c;
-        if (k == 1 && dsw) load_aux(c);
+        if (c != half) prefetch(c);
         uint32_t r[32];
-        const int ncols = (p.block_n - c0) >= 32 ? 32 : 16;
+        const int ncols = (block_n - c0) >= 32 ? 32 : 16;
         if (ncols == 32) ptx::tmem_ld_32x32(taddr_row + c0, r);
         else             ptx::tmem_ld_32x16(taddr_row + c0, r);
         ptx::tmem_ld_wait();
@@ -329,76 +457,11 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-        float* myrow = stage_buf + lane * EPI_LD;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncols) myrow[j] = __uint_as_float(r[j]);
-        __syncwarp();
-        const int col = n0 + c0 + c4;
-        const bool col_ok = (c4 < ncols) && (col < p.N);
-        const bool full4 = (col + 3 < p.N);
-        float cs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = 4 * i + sub;
-          const int row = row_base + rl;
-          if (!col_ok || row >= p.M) continue;
-          const float* sp = stage_buf + rl * EPI_LD + c4;
-          float v[4] = {sp[0] + bv[k][0], sp[1] + bv[k][1], sp[2] + bv[k][2], sp[3] + bv[k][3]};
-          float* crow = p.C + static_cast<int64_t>(row) * p.ldc;
-          if (dsw) {
-            const float a[4] = {ax[i].x, ax[i].y, ax[i].z, ax[i].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float sg = sigmoidf_acc(a[q]);
-              v[q] *= sg * (1.0f + a[q] * (1.0f - sg));
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) cs[q] += (col + q < p.N) ? v[q] : 0.f;
-          if (p.atomic) {
-            if (full4) ptx::red_add_v4_f32(crow + col, v[0], v[1], v[2], v[3]);
-            else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (col + q < p.N) ptx::red_add_f32(crow + col + q, v[q]);
-            }
-          } else {
-            if (full4) *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
-            else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (col + q < p.N) crow[col + q] = v[q];
-            }
-          }
-          if (p.epilogue == MVAE_EPI_BIAS_SWISH) {
-            float* hrow = p.out2 + static_cast<int64_t>(row) * p.ldout2 + col;
-            float h[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) h[q] = v[q] * sigmoidf_acc(v[q]);
-            if (full4) *reinterpret_cast<float4*>(hrow) = make_float4(h[0], h[1], h[2], h[3]);
-            else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (col + q < p.N) hrow[q] = h[q];
-            }
-          }
-        }
-        if (p.colsum != nullptr) {
-          // bias gradient: column sums of the stored tile (32 rows of this warp) -> one red.add per column
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
-            cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
-          }
-          if (sub == 0 && col_ok) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (col + q < p.N) ptx::red_add_f32(p.colsum + col + q, cs[q]);
-          }
-        }
-        __syncwarp();  // staging tile is rewritten by the next chunk
+        if (ew == 0 && lane == 0) dbg_stamp(batch, 3, dn3);
+        epilogue_chunk(e, stage_buf, r, ncols, lane, row_base, n0 + c0, bv, a0, batch.dbg_flags);
+        if (ew == 0 && lane == 0) dbg_stamp(batch, 3, dn3);
       }
+      if (ew == 0 && lane == 0) dbg_stamp(batch, 2, dn);
     }
   } else if (kSplit) {
     // ===================================================== operand splitters (3xTF32 only), warps 10..13
@@ -594,6 +657,8 @@ extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision
   }
   batch.num_problems = n;
   batch.total_tiles = tiles;
+  if (const char* v = getenv("MVAE_DBG_TIMELINE")) batch.dbg = reinterpret_cast<long long*>(strtoull(v, nullptr, 0));
+  if (const char* v = getenv("MVAE_DBG_EPI")) batch.dbg_flags = atoi(v);
   const int sms = mvae_device_sm_count();
   if (sms <= 0) return set_error(MVAE_ERR_CUDA, "no CUDA device");
   const int grid = tiles < sms ? tiles : sms;

@@ -1,0 +1,30 @@
+"""Per-role clock64 timeline of the first CTAs of one GEMM launch (debug aid; MVAE_DBG_TIMELINE)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from multimodal_vae_public_b200 import ops  # noqa: E402
+
+prec = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+M, N, K = 8192, 512, 512
+x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda"); b = torch.randn(N, device="cuda")
+y = torch.empty(M, N, device="cuda"); h = torch.empty(M, N, device="cuda")
+for _ in range(20):
+    ops.linear_fwd(x, w, b, y, h, precision=prec)
+torch.cuda.synchronize()
+dbg = torch.zeros(8 * 4 * 64, dtype=torch.int64, device="cuda")
+os.environ["MVAE_DBG_TIMELINE"] = str(dbg.data_ptr())
+ops.linear_fwd(x, w, b, y, h, precision=prec)
+torch.cuda.synchronize()
+del os.environ["MVAE_DBG_TIMELINE"]
+d = dbg.cpu().view(8, 4, 64)
+for blk in (0,):
+    if blk >= 8:
+        continue
+    t0 = int(d[blk][d[blk] > 0].min())
+    for role, name in enumerate(("producer", "mma", "epilogue", "epi-chunk")):
+        ev = [int(v) - t0 for v in d[blk, role] if v > 0]
+        print(f"block {blk} {name:9s} n={len(ev):2d}:", " ".join(str(e) for e in ev))
