@@ -343,38 +343,37 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, c
 }
 
 // ---------------------------------------------------------------- BCE with logits: loss + grad
-// Persistent grid-stride kernel: each block streams 16 KiB slabs (4 x float4 per thread in flight), keeps its
-// loss partial in registers and issues ONE double atomic per (block, segment) at the end -- a per-slab atomic on
-// one address serialises in L2 and capped the first version at 43 % of HBM bandwidth.
+// Each block streams `slabs` consecutive 16 KiB slabs (4 x float4 per thread in flight), keeps its loss partial
+// in a register and issues ONE double atomic per (block, segment): with one slab per block the same-address
+// atomics serialised in L2 and capped the kernel at 43 % of HBM bandwidth at roofline size.  32-bit index math
+// keeps the kernel at 4 blocks/SM.
 constexpr int kBceUnroll = 4;
-__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ t,
-                                                  int64_t ldt, int t_rows, float* dx, int64_t lddx, int R, int D4,
-                                                  float scale, double* loss_acc, int seg_rows, float* loss_elem,
-                                                  int64_t ldl) {
+__global__ void __launch_bounds__(256, 4) bce_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ t,
+                                                     int ldt, int t_rows, float* dx, int lddx, int R, int D4,
+                                                     float scale, double* loss_acc, int seg_rows, float* loss_elem,
+                                                     int ldl, int slabs) {
   __shared__ double scratch[32];
   __shared__ int seg_smem;
-  const int64_t n4 = static_cast<int64_t>(R) * D4;
-  const int64_t slab = static_cast<int64_t>(blockDim.x) * kBceUnroll;
+  const unsigned n4 = static_cast<unsigned>(R) * static_cast<unsigned>(D4);
+  const unsigned slab = 256u * kBceUnroll;
   double acc = 0.0;
   int cur_seg = -1;
-  for (int64_t base0 = static_cast<int64_t>(blockIdx.x) * slab; base0 < n4; base0 += static_cast<int64_t>(gridDim.x) * slab) {
-    const int64_t base = base0 + threadIdx.x;
+  for (int sidx = 0; sidx < slabs; ++sidx) {
+    const unsigned base = (blockIdx.x * static_cast<unsigned>(slabs) + sidx) * slab + threadIdx.x;
+    if (base - threadIdx.x >= n4) break;
     float4 xv[kBceUnroll], tv[kBceUnroll];
-    int64_t off_dx[kBceUnroll], off_l[kBceUnroll];
-    int seg[kBceUnroll];
+    unsigned rr[kBceUnroll], cc[kBceUnroll];
     bool ok[kBceUnroll];
 #pragma unroll
     for (int u = 0; u < kBceUnroll; ++u) {
-      const int64_t i = base + static_cast<int64_t>(u) * blockDim.x;
+      const unsigned i = base + u * 256u;
       ok[u] = i < n4;
       if (ok[u]) {
-        const int r = static_cast<int>(i / D4);
-        const int c = static_cast<int>(i - static_cast<int64_t>(r) * D4) * 4;
-        xv[u] = __ldcs(reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * ldx + c));
-        tv[u] = __ldg(reinterpret_cast<const float4*>(t + static_cast<int64_t>(r % t_rows) * ldt + c));
-        off_dx[u] = static_cast<int64_t>(r) * lddx + c;
-        off_l[u] = static_cast<int64_t>(r) * ldl + c;
-        seg[u] = r / seg_rows;
+        const unsigned r = i / static_cast<unsigned>(D4);
+        const unsigned c = (i - r * D4) * 4u;
+        rr[u] = r; cc[u] = c;
+        xv[u] = __ldcs(reinterpret_cast<const float4*>(x + static_cast<size_t>(r) * ldx + c));
+        tv[u] = __ldg(reinterpret_cast<const float4*>(t + static_cast<size_t>(r % static_cast<unsigned>(t_rows)) * ldt + c));
       }
     }
 #pragma unroll
@@ -394,15 +393,18 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ x, i
         const float s = xq >= 0.f ? inv : e * inv;
         g[q] = scale * (s - ts[q]);
       }
-      if (seg[u] != cur_seg) {  // rows are visited in increasing order: flush the finished segment (rare)
+      const int seg = static_cast<int>(rr[u] / static_cast<unsigned>(seg_rows));
+      if (seg != cur_seg) {  // rows are visited in increasing order: flush the finished segment (rare)
         if (cur_seg >= 0 && loss_acc != nullptr && acc != 0.0) atomicAdd(loss_acc + cur_seg, acc);
-        cur_seg = seg[u];
+        cur_seg = seg;
         acc = 0.0;
       }
       acc += static_cast<double>(lsum);
-      if (dx != nullptr) __stcs(reinterpret_cast<float4*>(dx + off_dx[u]), make_float4(g[0], g[1], g[2], g[3]));
+      if (dx != nullptr)
+        __stcs(reinterpret_cast<float4*>(dx + static_cast<size_t>(rr[u]) * lddx + cc[u]), make_float4(g[0], g[1], g[2], g[3]));
       if (loss_elem != nullptr)
-        __stcs(reinterpret_cast<float4*>(loss_elem + off_l[u]), make_float4(le[0], le[1], le[2], le[3]));
+        __stcs(reinterpret_cast<float4*>(loss_elem + static_cast<size_t>(rr[u]) * ldl + cc[u]),
+               make_float4(le[0], le[1], le[2], le[3]));
     }
   }
   if (loss_acc != nullptr) block_atomic_add_seg(acc, cur_seg < 0 ? 0 : cur_seg, loss_acc, scratch, &seg_smem);
@@ -716,12 +718,18 @@ extern "C" int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float*
       (loss_elem && ((ldl & 3) || !al(loss_elem))))
     return set_error(MVAE_ERR_UNSUPPORTED, "bce: D and leading dims must be multiples of 4 and pointers 16B aligned");
   const int64_t n4 = static_cast<int64_t>(R) * (D / 4);
+  if (n4 >= (int64_t(1) << 31) || ldx >= (int64_t(1) << 31) || ldt >= (int64_t(1) << 31) || lddx >= (int64_t(1) << 31) ||
+      ldl >= (int64_t(1) << 31))
+    return set_error(MVAE_ERR_UNSUPPORTED, "bce: tensor too large for 32-bit indexing");
   const int per_block = 256 * kBceUnroll;
-  int64_t blocks = (n4 + per_block - 1) / per_block;
-  const int64_t max_blocks = static_cast<int64_t>(mvae_device_sm_count() > 0 ? mvae_device_sm_count() : 148) * 8;
-  if (blocks > max_blocks) blocks = max_blocks;
+  const int64_t nslabs = (n4 + per_block - 1) / per_block;
+  const int sms = mvae_device_sm_count() > 0 ? mvae_device_sm_count() : 148;
+  int slabs = static_cast<int>(nslabs / (static_cast<int64_t>(sms) * 8));   // aim for >= 8 blocks per SM
+  slabs = slabs < 1 ? 1 : (slabs > 16 ? 16 : slabs);
+  const int64_t blocks = (nslabs + slabs - 1) / slabs;
   bce_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, ldx, t, ldt, t_rows, dx, lddx, R, D / 4, scale, loss_acc, seg_rows, loss_elem, ldl);
+      x, static_cast<int>(ldx), t, static_cast<int>(ldt), t_rows, dx, static_cast<int>(lddx), R, D / 4, scale, loss_acc,
+      seg_rows, loss_elem, static_cast<int>(ldl), slabs);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
