@@ -165,10 +165,17 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     from multimodal_vae_public_b200 import _lib, ops
     from multimodal_vae_public_b200.trainer import MnistMVAETrainer
 
+    if os.environ.get("MVAE_DIST_BACKEND", "nccl") != "nccl":
+        local_rank = local_rank % max(torch.cuda.device_count(), 1)   # functional test: ranks may share a GPU
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        backend = os.environ.get("MVAE_DIST_BACKEND", "nccl")   # "gloo" only for single-GPU functional tests
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
+        else:
+            dist.init_process_group(backend, timeout=datetime.timedelta(seconds=90))
     strong = args.scaling == "strong"
     b_local = BATCH // world if strong else BATCH
     b_global = b_local * world
@@ -201,11 +208,16 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         im, tx = pool[i % POOL]
         tr.step(im, tx, annealing_factor=annealing(i), sync=False)
 
+    def log(msg):
+        if args.verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     def step_e2e(i):
         im, tx = host[i % POOL]
         return tr.step(im, tx, annealing_factor=annealing(i), sync=True)   # loss is read on the host every step
 
     # warm-up (also captures the CUDA graph) -- long enough for the clocks to ramp
+    log("warm-up / graph capture")
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     tr.synchronize()
@@ -215,6 +227,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             step_resident(i)
         tr.synchronize()
 
+    log("timed region (device-resident inputs)")
     sampler = ClockSampler(local_rank); sampler.start()
     n0 = _lib.launch_count()
     ms = timed(step_resident, args.steps)
@@ -222,6 +235,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     launches = tr.launches_per_step * args.steps if tr.use_graph else _lib.launch_count() - n0
     value = b_global * args.steps / (ms * 1e-3)
 
+    log("timed region (end to end from pinned host memory)")
     for i in range(3):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
@@ -229,7 +243,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     loss = float(tr.loss_host[0])
 
     # ---- per-kernel roofline, measured live with CUDA events on the launching stream (eager pass, same buffers)
+    log("per-kernel roofline pass")
     roof = measure_rooflines(tr, dev, prec, args)
+    log("done")
 
     line = None
     if rank == 0:
@@ -363,6 +379,7 @@ def main():
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -70,7 +70,7 @@ def mnist_reference_order(n_latents: int) -> List[str]:
 class FlatArena:
     """One contiguous fp32 bucket with named, 16-byte aligned views."""
 
-    def __init__(self, layout: Sequence[Tuple[str, Tuple[int, ...]]], device, n_buffers: int = 1):
+    def __init__(self, layout: Sequence[Tuple[str, Tuple[int, ...]]], device, n_buffers: int = 1, tail: int = 0):
         self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         off = 0
         for name, shape in layout:
@@ -78,7 +78,9 @@ class FlatArena:
             self.offsets[name] = (off, tuple(shape))
             off += (n + 3) // 4 * 4
         self.numel = off
-        self.buffers = [torch.zeros(off, dtype=torch.float32, device=device) for _ in range(n_buffers)]
+        # `tail` extra floats after the parameters (the gradient bucket carries the loss scalars there so that ONE
+        # all-reduce moves gradients and loss)
+        self.buffers = [torch.zeros(off + tail, dtype=torch.float32, device=device) for _ in range(n_buffers)]
 
     def view(self, buf: int, name: str) -> torch.Tensor:
         off, shape = self.offsets[name]
@@ -111,10 +113,13 @@ class MnistMVAETrainer:
         self.pg = process_group
         self.use_graph = use_graph
         self.layout = mnist_layout(n_latents)
-        self.arena = FlatArena(self.layout, self.dev, n_buffers=4)  # params, grads, adam m, adam v
+        self.arena = FlatArena(self.layout, self.dev, n_buffers=4, tail=4)  # params, grads(+loss tail), adam m, adam v
         self.params = {k: self.arena.view(0, k) for k, _ in self.layout}
         self.grads = {k: self.arena.view(1, k) for k, _ in self.layout}
-        self.flat_params, self.flat_grads, self.adam_m, self.adam_v = self.arena.buffers
+        n = self.arena.numel
+        self.flat_params, self.adam_m, self.adam_v = (self.arena.buffers[i][:n] for i in (0, 2, 3))
+        self.grad_bucket = self.arena.buffers[1]          # gradients + 4 loss floats: the all-reduce payload
+        self.flat_grads = self.grad_bucket[:n]
         B, L, dev = batch_size, n_latents, self.dev
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)  # noqa: E731
         # inputs (device-resident copies; step() fills them from host or device tensors)
@@ -139,7 +144,7 @@ class MnistMVAETrainer:
         # one zero-initialised region per step: dZ + loss accumulators
         self.dZ = torch.zeros(3 * B, L, dtype=torch.float32, device=dev)
         self.acc = torch.zeros(9, dtype=torch.float64, device=dev)  # recon_img[3], recon_txt[3], kl[3]
-        self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)  # total, internal passes 0..2
+        self.loss_out = self.grad_bucket[n:n + 4]           # total, internal passes 0..2 (tail of the gradient bucket)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.beta_dev = torch.ones(1, dtype=torch.float32, device=dev)   # KL annealing factor
         self.beta_host = torch.ones(1, dtype=torch.float32).pin_memory()
@@ -300,21 +305,31 @@ class MnistMVAETrainer:
                                       b_mn=True, split_k=split, accumulate=True)], P)
         ops.embedding_swish_bwd(p["text_encoder.fc1.weight"], self.text, self.te_dA[1], g["text_encoder.fc1.weight"])
 
-    def _enqueue_step(self, training: bool, use_noise_input: bool, update: bool) -> None:
+    def _enqueue_fwd_bwd(self, training: bool, use_noise_input: bool) -> None:
         b_global = self.B * self.world
-        self.flat_grads.zero_()
+        self.grad_bucket.zero_()
         self.dZ.zero_()
         self.acc.zero_()
         self._enqueue_forward(training, use_noise_input)
         self._enqueue_loss_and_backward(training, b_global)
         ops.elbo_finalize(self.acc[0:3], self.acc[3:6], self.acc[6:9], 3, self.lam_i, self.lam_t, 1.0, 1.0 / b_global,
                           self.loss_out, beta_dev=self.beta_dev)
+
+    def _enqueue_allreduce(self) -> None:
+        """The one exchange step of the data-parallel path: SUM all-reduce of the flat gradient bucket (+ loss tail)
+        over NCCL.  Kept OUT of the CUDA graphs (capturing NCCL needs every rank's watchdog to stay quiet)."""
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(self.flat_grads, group=self.pg)
-            dist.all_reduce(self.loss_out, group=self.pg)
+            dist.all_reduce(self.grad_bucket, group=self.pg)
+
+    def _enqueue_update(self) -> None:
+        ops.adam_flat(self.flat_params, self.flat_grads, self.adam_m, self.adam_v, self.step_count, lr=self.lr)
+
+    def _enqueue_step(self, training: bool, use_noise_input: bool, update: bool) -> None:
+        self._enqueue_fwd_bwd(training, use_noise_input)
+        self._enqueue_allreduce()
         if update:
-            ops.adam_flat(self.flat_params, self.flat_grads, self.adam_m, self.adam_v, self.step_count, lr=self.lr)
+            self._enqueue_update()
 
     # ------------------------------------------------------------------ public API
     def set_inputs(self, image: torch.Tensor, text: torch.Tensor, noise: Optional[torch.Tensor] = None,
@@ -332,8 +347,16 @@ class MnistMVAETrainer:
                 for ref_i, int_i in enumerate(_REF_TO_INTERNAL):
                     nz[int_i].copy_(noise[ref_i], non_blocking=True)
 
+    def _capture(self, fn):
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(g, stream=self._stream, capture_error_mode="thread_local"):
+            fn()
+        return g, _lib.launch_count() - n0
+
     def run(self, training: bool = True, noise_given: bool = False, update: bool = True) -> None:
-        """Enqueue one step (graph replay when enabled).  Does not synchronise."""
+        """Enqueue one step (graph replay when enabled).  Does not synchronise.
+        world == 1: one graph for the whole step.  world > 1: graph(fwd+bwd) -> NCCL all-reduce -> graph(Adam)."""
         key = (training, noise_given, update)
         with torch.cuda.stream(self._stream):
             if not self.use_graph:
@@ -343,20 +366,27 @@ class MnistMVAETrainer:
                 return
             gr = self._graphs.get(key)
             if gr is None:
-                # warm-up once eagerly (sets func attributes, loads modules), then capture
+                # warm-up once eagerly (sets func attributes, loads modules, inits NCCL), then capture
                 saved = (self.flat_params.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count.clone())
                 self._enqueue_step(training, noise_given, update)
                 self._stream.synchronize()
                 self.flat_params.copy_(saved[0]); self.adam_m.copy_(saved[1]); self.adam_v.copy_(saved[2])
                 self.step_count.copy_(saved[3])
                 self._stream.synchronize()
-                gr = torch.cuda.CUDAGraph()
-                n0 = _lib.launch_count()
-                with torch.cuda.graph(gr, stream=self._stream):
-                    self._enqueue_step(training, noise_given, update)
-                self.launches_per_step = _lib.launch_count() - n0
+                if self.world == 1:
+                    g, n = self._capture(lambda: self._enqueue_step(training, noise_given, update))
+                    gr = (g, None)
+                else:
+                    g1, n1 = self._capture(lambda: self._enqueue_fwd_bwd(training, noise_given))
+                    g2, n2 = self._capture(self._enqueue_update) if update else (None, 0)
+                    gr, n = (g1, g2), n1 + n2
+                self.launches_per_step = n
                 self._graphs[key] = gr
-            gr.replay()
+            gr[0].replay()
+            if self.world > 1:
+                self._enqueue_allreduce()
+                if gr[1] is not None:
+                    gr[1].replay()
 
     def step(self, image: torch.Tensor, text: torch.Tensor, annealing_factor: float = 1.0,
              noise: Optional[torch.Tensor] = None, training: bool = True, update: bool = True,

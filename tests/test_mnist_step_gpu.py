@@ -136,7 +136,7 @@ def test_full_size_properties():
         sl = slice(r * B // 2, (r + 1) * B // 2)
         half.set_inputs(image[sl], text[sl], noise[:, sl], 0.5)
         with torch.cuda.stream(half._stream):
-            half.flat_grads.zero_(); half.dZ.zero_(); half.acc.zero_()
+            half.grad_bucket.zero_(); half.dZ.zero_(); half.acc.zero_()
             half._enqueue_forward(True, True)
             half._enqueue_loss_and_backward(True, B)
             T.ops.elbo_finalize(half.acc[0:3], half.acc[3:6], half.acc[6:9], 3, half.lam_i, half.lam_t, 1.0, 1.0 / B,
