@@ -48,6 +48,17 @@ def executed_gemm_flops_per_sample(L: int = N_LATENTS) -> float:
     return 2.0 * (fwd + wgrad + dgrad)
 
 
+def fashion_gemm_flops_per_sample(L: int = N_LATENTS) -> float:
+    """2*MAC of the GEMMs the FashionMNIST-flavour trainer launches per sample (fwd + wgrad + dgrad)."""
+    enc_i = 196 * 64 * 16 + 49 * 128 * 1024 + 6272 * 512 + 512 * 2 * L
+    enc_t = 512 * 512 + 512 * 2 * L
+    dec_i = L * 512 + 512 * 6272 + 49 * 128 * 1024 + 196 * 64 * 16
+    dec_t = L * 512 + 512 * 512 * 2 + 512 * 10
+    fwd = enc_i + enc_t + 2 * (dec_i + dec_t)
+    dgrad = (enc_i - 196 * 64 * 16) + enc_t + 2 * (dec_i + dec_t)
+    return 2.0 * (2 * fwd + dgrad)
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -180,8 +191,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     b_local = BATCH // world if strong else BATCH
     b_global = b_local * world
     prec = ops.PREC_3XTF32 if args.precision == "3xtf32" else ops.PREC_TF32
-    tr = MnistMVAETrainer(N_LATENTS, b_local, device=dev, lr=1e-3, lambda_image=LAMBDA_IMAGE, lambda_text=LAMBDA_TEXT,
-                          precision=prec, world_size=world, rank=rank, seed=0, use_graph=not args.no_graph)
+    if args.workload == "fashion":
+        from multimodal_vae_public_b200.trainer_fashion import FashionMVAETrainer as Trainer
+    else:
+        Trainer = MnistMVAETrainer
+    tr = Trainer(N_LATENTS, b_local, device=dev, lr=1e-3, lambda_image=LAMBDA_IMAGE, lambda_text=LAMBDA_TEXT,
+                 precision=prec, world_size=world, rank=rank, seed=0, use_graph=not args.no_graph)
     host = synth_batches(POOL, b_local, seed=100 + rank)
     host = [(im.pin_memory(), tx.pin_memory()) for im, tx in host]
     pool = [(im.to(dev), tx.to(dev)) for im, tx in host]
@@ -261,9 +276,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "dtype": "fp32 (3xTF32 tensor-core split products, fp32 accumulate)" if prec == ops.PREC_3XTF32
                      else "tf32 (fp32 storage/accumulate)",
             "data": "synthetic",
-            "config": {"workload": f"MNIST MVAE (image 28x28x1 + label one-of-10), n_latents={N_LATENTS}, "
+            "config": {"workload": f"{'FashionMNIST (conv enc/dec)' if args.workload == 'fashion' else 'MNIST'} MVAE "
+                                   f"(image 28x28x1 + label one-of-10), n_latents={N_LATENTS}, "
                                    f"global batch {b_global} ({b_local}/GPU), full train step "
-                                   "(3 passes + ELBO + backward + Adam), BASELINE.json configs[1]",
+                                   "(3 passes + ELBO + backward + Adam), BASELINE.json "
+                                   f"{'configs[2]' if args.workload == 'fashion' else 'configs[1]'}",
                        "parallelism": f"dp{world}", "global_batch": b_global,
                        "l2": f"rotating pool of {POOL} distinct input batches ({POOL * b_local * 3144 / 1e6:.0f} MB) and a "
                              f"~{working_set_mb(b_local):.0f} MB per-step working set, both larger than the 126 MB L2",
@@ -343,7 +360,8 @@ def measure_rooflines(tr, dev, prec, args):
     gemm_ms = per.get("gemm_batch", 0.0) + per.get("linear_fwd", 0.0)
     gemm_launches = (cnt.get("gemm_batch", 0) + cnt.get("linear_fwd", 0)) // reps
     out = {"gemm": {"ms_per_step": gemm_ms, "launches": gemm_launches,
-                    "algorithmic_flops_per_step": executed_gemm_flops_per_sample(tr.L) * tr.B},
+                    "algorithmic_flops_per_step": (executed_gemm_flops_per_sample(tr.L) if args.workload == "mnist"
+                                           else fashion_gemm_flops_per_sample(tr.L)) * tr.B},
            "breakdown": {k: round(v, 5) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
     # HBM roofline of the fused reconstruction-loss kernel at roofline size (inputs >> L2), L2 not reusable
     R, D = 65536, 784
@@ -380,6 +398,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--workload", choices=["mnist", "fashion"], default="mnist",
+                    help="mnist = BASELINE.json configs[1] (default, the headline); fashion = conv flavour (configs[2])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

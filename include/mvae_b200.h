@@ -156,6 +156,17 @@ int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float* t, int64_t
 int mvae_ce_fwd_bwd(const float* x, int64_t ldx, const int64_t* target, int t_rows, float* dx, int64_t lddx, int R,
                     int K, float scale, double* loss_acc, int seg_rows, float* loss_rows, int64_t ldl, void* stream);
 
+/* 4x4 / stride 2 / pad 1 convolution data movement for the conv flavours (fashionmnist/model.py:79-82,112-114;
+ * celeba/model.py:77-87,117-126), NHWC activations; the contraction runs on mvae_gemm_batch.
+ *   im2col : x [B,H,W,C] -> cols [B*(H/2)*(W/2), 16*C] (row stride ld_cols), column (kh*4+kw)*C + c
+ *            = operand of Conv2d forward / ConvTranspose2d backward-data.
+ *   col2im : cols [B*IH*IW, 16*C] -> out [B,2IH,2IW,C] (gather-sum of the <= 4 contributing taps)
+ *            = ConvTranspose2d forward tail / Conv2d backward-data tail.  Optional fusions:
+ *            out_act = swish(out) (decoder forward), out *= swish'(aux) with aux [B,2IH,2IW,C] (encoder backward). */
+int mvae_im2col_k4s2p1(const float* x, float* cols, int64_t ld_cols, int B, int H, int W, int C, void* stream);
+int mvae_col2im_k4s2p1(const float* cols, int64_t ld_cols, float* out, float* out_act, const float* aux, int B, int IH,
+                       int IW, int C, void* stream);
+
 /* Fused flat Adam over one contiguous parameter bucket (torch.optim.Adam defaults, mnist/train.py:168,219):
  *   g is first multiplied by grad_scale (1/world_size after a sum-allreduce).
  *   lr_mult_dev: optional device float multiplying lr.

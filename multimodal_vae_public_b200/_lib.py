@@ -57,6 +57,8 @@ SIGNATURES = {
     "mvae_reparam_bwd": [_P, _P, _P, _P, _L, _P],
     "mvae_bce_logits_fwd_bwd": [_P, _L, _P, _L, _I, _P, _L, _I, _I, _F, _P, _I, _P, _L, _P],
     "mvae_ce_fwd_bwd": [_P, _L, _P, _I, _P, _L, _I, _I, _F, _P, _I, _P, _L, _P],
+    "mvae_im2col_k4s2p1": [_P, _P, _L, _I, _I, _I, _I, _P],
+    "mvae_col2im_k4s2p1": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvae_adam_flat": [_P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _F, _P, _P],
     "mvae_elbo_finalize": [_P, _P, _P, _I, _F, _F, _F, _P, _F, _P, _P],
 }

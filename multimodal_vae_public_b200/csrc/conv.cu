@@ -1,0 +1,140 @@
+// 4x4 / stride 2 / pad 1 convolution plumbing for the conv MVAE flavours (fashionmnist/model.py:79-82,112-114):
+// NHWC activations, the contraction itself runs on the tcgen05 GEMM (gemm_tcgen05.cu); these two bandwidth-bound
+// kernels move data between image layout and GEMM-operand layout.
+//
+//   Conv2d(Cin->Cout,4,2,1)           y = im2col(x) * W^T            cols [B*OH*OW, 16*Cin]  (k = (kh*4+kw)*Cin + ci)
+//   ConvTranspose2d(Cin->Cout,4,2,1)  cols = x * Wt^T ; y = col2im(cols)   cols [B*IH*IW, 16*Cout]
+//   and their adjoints: d/dx Conv = col2im(dcols), d/dcols ConvT = im2col(dy).
+// col2im is written as a GATHER (each output pixel sums its <= 4 contributing taps): no atomics, deterministic.
+// Optional fusions: Swish of the gathered sum (decoder forward) or multiplication by Swish'(aux) (encoder backward).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mvae_b200.h"
+#include "common.h"
+
+namespace mvae {
+namespace {
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// one thread = one float4 of channels (or one scalar when C < 4) of one (output pixel, tap)
+template <int VEC>
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ cols, int B, int H,
+                                                     int W, int C, int64_t ld_cols) {
+  const int OH = H / 2, OW = W / 2;
+  const int cv = C / VEC;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW * 16 * cv;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c = static_cast<int>(gid % cv) * VEC;
+  int64_t r = gid / cv;
+  const int tap = static_cast<int>(r % 16);
+  r /= 16;                       // output pixel index m = (b*OH + oh)*OW + ow
+  const int ow = static_cast<int>(r % OW);
+  const int64_t r2 = r / OW;
+  const int oh = static_cast<int>(r2 % OH);
+  const int b = static_cast<int>(r2 / OH);
+  const int kh = tap >> 2, kw = tap & 3;
+  const int ih = 2 * oh - 1 + kh, iw = 2 * ow - 1 + kw;
+  float* dst = cols + r * ld_cols + tap * C + c;
+  const bool in = (ih >= 0 && ih < H && iw >= 0 && iw < W);
+  const float* src = x + ((static_cast<int64_t>(b) * H + ih) * W + iw) * C + c;
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(dst) = in ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    *dst = in ? __ldg(src) : 0.f;
+  }
+}
+
+// out[b, oh, ow, c] = sum over taps (kh,kw) with oh = 2*ih - 1 + kh, ow = 2*iw - 1 + kw of cols[(b,ih,iw), (kh,kw,c)]
+template <int VEC>
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ cols, int64_t ld_cols, float* out,
+                                                     float* out_act, const float* __restrict__ aux, int B, int IH,
+                                                     int IW, int C) {
+  const int OH = 2 * IH, OW = 2 * IW;
+  const int cv = C / VEC;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW * cv;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int c = static_cast<int>(gid % cv) * VEC;
+  int64_t r = gid / cv;          // output pixel
+  const int ow = static_cast<int>(r % OW);
+  const int64_t r2 = r / OW;
+  const int oh = static_cast<int>(r2 % OH);
+  const int b = static_cast<int>(r2 / OH);
+  float acc[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+  const int kh0 = (oh + 1) & 1, kw0 = (ow + 1) & 1;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int kh = kh0 + 2 * a;
+    const int ih = (oh + 1 - kh) >> 1;          // exact: oh + 1 - kh is even
+    if (ih < 0 || ih >= IH) continue;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const int kw = kw0 + 2 * d;
+      const int iw = (ow + 1 - kw) >> 1;
+      if (iw < 0 || iw >= IW) continue;
+      const float* src = cols + ((static_cast<int64_t>(b) * IH + ih) * IW + iw) * ld_cols + (kh * 4 + kw) * C + c;
+      if constexpr (VEC == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      } else {
+        acc[0] += __ldg(src);
+      }
+    }
+  }
+  const int64_t o = r * C + c;
+  if (aux != nullptr) {  // backward through the Swish that produced this layer's input: multiply by Swish'(aux)
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      const float a = aux[o + q];
+      const float s = sigmoid_f(a);
+      acc[q] *= s * (1.0f + a * (1.0f - s));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) out[o + q] = acc[q];
+  if (out_act != nullptr) {
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) out_act[o + q] = acc[q] * sigmoid_f(acc[q]);
+  }
+}
+
+}  // namespace
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" int mvae_im2col_k4s2p1(const float* x, float* cols, int64_t ld_cols, int B, int H, int W, int C,
+                                  void* stream) {
+  if (!x || !cols || B < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 1 || ld_cols < 16 * C)
+    return set_error(MVAE_ERR_BAD_ARG, "im2col: bad arguments (even H, W required; ld_cols >= 16*C)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool v4 = (C % 4 == 0) && (ld_cols % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(cols)) & 15) == 0;
+  const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2) * 16 * (v4 ? C / 4 : C);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (v4) im2col_kernel<4><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols);
+  else    im2col_kernel<1><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols);
+  count_launch();
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  return MVAE_OK;
+}
+
+extern "C" int mvae_col2im_k4s2p1(const float* cols, int64_t ld_cols, float* out, float* out_act, const float* aux,
+                                  int B, int IH, int IW, int C, void* stream) {
+  if (!cols || !out || B < 1 || IH < 1 || IW < 1 || C < 1 || ld_cols < 16 * C)
+    return set_error(MVAE_ERR_BAD_ARG, "col2im: bad arguments (ld_cols >= 16*C)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool v4 = (C % 4 == 0) && (ld_cols % 4 == 0) && (reinterpret_cast<uintptr_t>(cols) & 15) == 0;
+  const int64_t total = static_cast<int64_t>(B) * (2 * IH) * (2 * IW) * (v4 ? C / 4 : C);
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (v4) col2im_kernel<4><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C);
+  else    col2im_kernel<1><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C);
+  count_launch();
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  return MVAE_OK;
+}

@@ -611,8 +611,8 @@ extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision
     GemmProblem& p = batch.p[i];
     if (d.M < 1 || d.N < 1 || d.K < 1 || !d.A || !d.B || !d.C)
       return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: bad shape/pointer (M=%d N=%d K=%d)", i, d.M, d.N, d.K);
-    if (d.epilogue == MVAE_EPI_BIAS_SWISH && (!d.out2 || !d.bias))
-      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: BIAS_SWISH needs bias and out2", i);
+    if (d.epilogue == MVAE_EPI_BIAS_SWISH && !d.out2)
+      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: BIAS_SWISH needs out2 (bias may be NULL: bias=False convs)", i);
     if (d.epilogue == MVAE_EPI_MUL_DSWISH && !d.aux)
       return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: MUL_DSWISH needs aux", i);
     if (d.epilogue < 0 || d.epilogue > MVAE_EPI_MUL_DSWISH)

@@ -164,6 +164,18 @@ def ce_fwd_bwd(x, target, dx, K, scale, loss_acc=None, seg_rows=0, loss_rows=Non
                                            _stream()), "mvae_ce_fwd_bwd")
 
 
+def im2col_k4s2p1(x, cols, B, H, W, Cch):
+    """x NHWC [B,H,W,C] (contiguous) -> cols [B*(H/2)*(W/2), 16*C]."""
+    _lib.check(_lib.load().mvae_im2col_k4s2p1(x.data_ptr(), cols.data_ptr(), cols.stride(0), B, H, W, Cch, _stream()),
+               "mvae_im2col_k4s2p1")
+
+
+def col2im_k4s2p1(cols, out, B, IH, IW, Cch, out_act=None, aux=None):
+    """cols [B*IH*IW, 16*C] -> out NHWC [B,2IH,2IW,C]; optional out_act = swish(out) or out *= swish'(aux)."""
+    _lib.check(_lib.load().mvae_col2im_k4s2p1(cols.data_ptr(), cols.stride(0), out.data_ptr(), _p(out_act), _p(aux), B,
+                                              IH, IW, Cch, _stream()), "mvae_col2im_k4s2p1")
+
+
 def adam_flat(p, g, m, v, step_count, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, lr_mult_dev=None):
     _lib.check(_lib.load().mvae_adam_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
                                           _p(lr_mult_dev), beta1, beta2, eps, grad_scale, step_count.data_ptr(),

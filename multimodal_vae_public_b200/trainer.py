@@ -112,7 +112,7 @@ class MnistMVAETrainer:
         self.world, self.rank, self.seed = world_size, rank, seed
         self.pg = process_group
         self.use_graph = use_graph
-        self.layout = mnist_layout(n_latents)
+        self.layout = self._make_layout(n_latents)
         self.arena = FlatArena(self.layout, self.dev, n_buffers=4, tail=4)  # params, grads(+loss tail), adam m, adam v
         self.params = {k: self.arena.view(0, k) for k, _ in self.layout}
         self.grads = {k: self.arena.view(1, k) for k, _ in self.layout}
@@ -126,21 +126,13 @@ class MnistMVAETrainer:
         self.x = f(B, 784)
         self.text = torch.zeros(B, dtype=torch.int64, device=dev)
         self.noise = f(3 * B, L)           # internal pass order
-        # encoders
-        self.ie_a1, self.ie_h1, self.ie_a2, self.ie_h2 = f(B, 512), f(B, 512), f(B, 512), f(B, 512)
-        self.te_h1, self.te_a2, self.te_h2 = f(B, 512), f(B, 512), f(B, 512)
         self.enc_i, self.enc_t = f(B, 2 * L), f(B, 2 * L)
+        self.d_enc_i, self.d_enc_t = f(B, 2 * L), f(B, 2 * L)
         self.Z = f(3 * B, L)
-        # decoders (2B rows each)
-        self.id_a = [f(2 * B, 512) for _ in range(3)]; self.id_h = [f(2 * B, 512) for _ in range(3)]
-        self.td_a = [f(2 * B, 512) for _ in range(3)]; self.td_h = [f(2 * B, 512) for _ in range(3)]
         self.logit_i = f(2 * B, 784)
         self.logit_t_buf = f(2 * B, 16)    # N = 10 padded to ld 16 for TMA
         self.logit_t = self.logit_t_buf[:, :10]
-        # backward scratch
-        self.id_dA = [f(2 * B, 512) for _ in range(2)]; self.td_dA = [f(2 * B, 512) for _ in range(2)]
-        self.ie_dA = [f(B, 512) for _ in range(2)]; self.te_dA = [f(B, 512) for _ in range(2)]
-        self.d_enc_i, self.d_enc_t = f(B, 2 * L), f(B, 2 * L)
+        self._alloc_activations(f)
         # one zero-initialised region per step: dZ + loss accumulators
         self.dZ = torch.zeros(3 * B, L, dtype=torch.float32, device=dev)
         self.acc = torch.zeros(9, dtype=torch.float64, device=dev)  # recon_img[3], recon_txt[3], kl[3]
@@ -153,6 +145,22 @@ class MnistMVAETrainer:
         self._stream = torch.cuda.Stream(device=dev)
         self.launches_per_step = 0
         self.init_parameters(seed)
+
+    # ------------------------------------------------------------------ flavour hooks
+    def _make_layout(self, n_latents: int):
+        return mnist_layout(n_latents)
+
+    def _alloc_activations(self, f) -> None:
+        B = self.B
+        # encoders
+        self.ie_a1, self.ie_h1, self.ie_a2, self.ie_h2 = f(B, 512), f(B, 512), f(B, 512), f(B, 512)
+        self.te_h1, self.te_a2, self.te_h2 = f(B, 512), f(B, 512), f(B, 512)
+        # decoders (2B rows each)
+        self.id_a = [f(2 * B, 512) for _ in range(3)]; self.id_h = [f(2 * B, 512) for _ in range(3)]
+        self.td_a = [f(2 * B, 512) for _ in range(3)]; self.td_h = [f(2 * B, 512) for _ in range(3)]
+        # backward scratch
+        self.id_dA = [f(2 * B, 512) for _ in range(2)]; self.td_dA = [f(2 * B, 512) for _ in range(2)]
+        self.ie_dA = [f(B, 512) for _ in range(2)]; self.te_dA = [f(B, 512) for _ in range(2)]
 
     # ------------------------------------------------------------------ parameters
     def init_parameters(self, seed: int = 0) -> None:

@@ -50,7 +50,8 @@ def mnist_param_shapes(n_latents: int) -> List[Tuple[str, Tuple[int, ...]]]:
 
 
 def make_params(shapes: Sequence[Tuple[str, Tuple[int, ...]]], seed: int = 0,
-                dtype=torch.float32, embedding_names: Sequence[str] = ("text_encoder.fc1.weight",)) -> Params:
+                dtype=torch.float32,
+                embedding_names: Sequence[str] = ("text_encoder.fc1.weight", "text_encoder.net.0.weight")) -> Params:
     """Deterministic parameters with PyTorch-default *scales* (U(+-1/sqrt(fan_in)) for
     Linear, N(0,1) for Embedding) drawn from numpy's frozen RandomState stream so
     the same values can be rebuilt on any box without the reference or torch's RNG."""
@@ -248,6 +249,105 @@ def mnist_step_grads(p: Params, image, text, n_latents, noises, lambda_image=1.0
     loss.backward()
     grads = {k: (v.grad.detach() if v.grad is not None else torch.zeros_like(v)) for k, v in q.items()}
     return loss.detach(), tuple(t.detach() for t in terms), grads, aux
+
+
+# ----------------------------------------------------------------------------
+# FashionMNIST MVAE (conv) forward -- fashionmnist/model.py
+# ----------------------------------------------------------------------------
+
+def fashion_param_shapes(n_latents: int) -> List[Tuple[str, Tuple[int, ...]]]:
+    """state_dict names/shapes of the FashionMNIST MVAE in the reference's registration order
+    (fashionmnist/model.py:24-31, 76-87, 104-116, 131-137, 153-161).  Convs have bias=False."""
+    L = n_latents
+    return [
+        ("image_encoder.features.0.weight", (64, 1, 4, 4)),
+        ("image_encoder.features.2.weight", (128, 64, 4, 4)),
+        ("image_encoder.classifier.0.weight", (512, 6272)), ("image_encoder.classifier.0.bias", (512,)),
+        ("image_encoder.classifier.2.weight", (2 * L, 512)), ("image_encoder.classifier.2.bias", (2 * L,)),
+        ("image_decoder.upsampler.0.weight", (512, L)), ("image_decoder.upsampler.0.bias", (512,)),
+        ("image_decoder.upsampler.2.weight", (6272, 512)), ("image_decoder.upsampler.2.bias", (6272,)),
+        ("image_decoder.hallucinate.0.weight", (128, 64, 4, 4)),   # ConvTranspose2d: [Cin, Cout, kh, kw]
+        ("image_decoder.hallucinate.2.weight", (64, 1, 4, 4)),
+        ("text_encoder.net.0.weight", (10, 512)),
+        ("text_encoder.net.2.weight", (512, 512)), ("text_encoder.net.2.bias", (512,)),
+        ("text_encoder.net.4.weight", (2 * L, 512)), ("text_encoder.net.4.bias", (2 * L,)),
+        ("text_decoder.net.0.weight", (512, L)), ("text_decoder.net.0.bias", (512,)),
+        ("text_decoder.net.2.weight", (512, 512)), ("text_decoder.net.2.bias", (512,)),
+        ("text_decoder.net.4.weight", (512, 512)), ("text_decoder.net.4.bias", (512,)),
+        ("text_decoder.net.6.weight", (10, 512)), ("text_decoder.net.6.bias", (10,)),
+    ]
+
+
+FASHION_EMBEDDINGS = ("text_encoder.net.0.weight",)
+
+
+def fashion_image_encoder(p: Params, x: Tensor, L: int):
+    """fashionmnist/model.py:89-94: conv(1->64) Swish conv(64->128) Swish, flatten (C,H,W), FC 6272->512 Swish, FC -> 2L."""
+    F = torch.nn.functional
+    h = swish(F.conv2d(x.reshape(-1, 1, 28, 28), p["image_encoder.features.0.weight"], None, 2, 1))
+    h = swish(F.conv2d(h, p["image_encoder.features.2.weight"], None, 2, 1))
+    h = swish(_lin(p, "image_encoder.classifier.0", h.reshape(h.size(0), -1)))
+    o = _lin(p, "image_encoder.classifier.2", h)
+    return o[:, :L], o[:, L:]
+
+
+def fashion_image_decoder(p: Params, z: Tensor):
+    """fashionmnist/model.py:117-121: FC L->512 Swish, FC 512->6272 Swish, view(128,7,7), convT(128->64) Swish,
+    convT(64->1) -> logits [B,1,28,28]."""
+    F = torch.nn.functional
+    h = swish(_lin(p, "image_decoder.upsampler.0", z))
+    h = swish(_lin(p, "image_decoder.upsampler.2", h)).reshape(-1, 128, 7, 7)
+    h = swish(F.conv_transpose2d(h, p["image_decoder.hallucinate.0.weight"], None, 2, 1))
+    return F.conv_transpose2d(h, p["image_decoder.hallucinate.2.weight"], None, 2, 1)
+
+
+def fashion_text_encoder(p: Params, y: Tensor, L: int):
+    """fashionmnist/model.py:139-143."""
+    h = swish(p["text_encoder.net.0.weight"][y])
+    h = swish(_lin(p, "text_encoder.net.2", h))
+    o = _lin(p, "text_encoder.net.4", h)
+    return o[:, :L], o[:, L:]
+
+
+def fashion_text_decoder(p: Params, z: Tensor):
+    """fashionmnist/model.py:163-165."""
+    h = swish(_lin(p, "text_decoder.net.0", z))
+    h = swish(_lin(p, "text_decoder.net.2", h))
+    h = swish(_lin(p, "text_decoder.net.4", h))
+    return _lin(p, "text_decoder.net.6", h)
+
+
+def fashion_forward(p: Params, image, text, L: int, noise: Optional[Tensor]):
+    """fashionmnist/model.py:41-67 (same control flow as mnist)."""
+    B = image.size(0) if image is not None else text.size(0)
+    dtype = p["image_encoder.features.0.weight"].dtype
+    mu, logvar = prior_expert((1, B, L), dtype)
+    if image is not None:
+        m, lv = fashion_image_encoder(p, image, L)
+        mu = torch.cat((mu, m.unsqueeze(0)), 0); logvar = torch.cat((logvar, lv.unsqueeze(0)), 0)
+    if text is not None:
+        m, lv = fashion_text_encoder(p, text, L)
+        mu = torch.cat((mu, m.unsqueeze(0)), 0); logvar = torch.cat((logvar, lv.unsqueeze(0)), 0)
+    mu, logvar = product_of_experts(mu, logvar, variant="A")
+    z = reparametrize(mu, logvar, noise)
+    return fashion_image_decoder(p, z), fashion_text_decoder(p, z), mu, logvar
+
+
+def fashion_step_grads(p: Params, image, text, L, noises, lambda_image=1.0, lambda_text=10.0, annealing=1.0):
+    """Three-pass objective + gradients of fashionmnist/train.py:196-218 (identical to mnist's)."""
+    q = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    r1 = fashion_forward(q, image, text, L, noises[0])
+    r2 = fashion_forward(q, image, None, L, noises[1])
+    r3 = fashion_forward(q, None, text, L, noises[2])
+    joint = elbo_loss_bimodal(r1[0], image, r1[1], text, r1[2], r1[3], lambda_image, lambda_text, annealing)
+    img = elbo_loss_bimodal(r2[0], image, None, None, r2[2], r2[3], lambda_image, lambda_text, annealing)
+    txt = elbo_loss_bimodal(None, None, r3[1], text, r3[2], r3[3], lambda_image, lambda_text, annealing)
+    loss = joint + img + txt
+    loss.backward()
+    grads = {k: (v.grad.detach() if v.grad is not None else torch.zeros_like(v)) for k, v in q.items()}
+    aux = {"mu": (r1[2], r2[2], r3[2]), "logvar": (r1[3], r2[3], r3[3]), "recon_image": (r1[0], r2[0], r3[0]),
+           "recon_text": (r1[1], r2[1], r3[1])}
+    return loss.detach(), (joint.detach(), img.detach(), txt.detach()), grads, aux
 
 
 # ----------------------------------------------------------------------------

@@ -113,6 +113,38 @@ def main():
         out[f"mnist_adam1_head/{k}"] = v.detach().reshape(-1)[:32].numpy().copy()
     np.savez_compressed(os.path.join(HERE, "mnist_golden.npz"), **out)
 
+    # ---------------------------------------------------------------- fashionmnist (conv enc/dec)
+    fds = types.ModuleType("datasets"); fds.FashionMNIST = object
+    ref_fm = load_ref("fashionmnist", "model", "ref_fashion_model")
+    Lf, Bf = 64, 4
+    fparams = O.make_params(O.fashion_param_shapes(Lf), seed=0)
+    fmodel = ref_fm.MVAE(Lf)
+    assert [k for k in fmodel.state_dict().keys()] == [k for k, _ in O.fashion_param_shapes(Lf)], list(fmodel.state_dict().keys())
+    fmodel.load_state_dict(fparams)
+    rs = np.random.RandomState(4321)
+    fimage = torch.from_numpy(rs.uniform(0, 1, size=(Bf, 1, 28, 28)).astype(np.float32))
+    ftext = torch.from_numpy(rs.randint(0, 10, size=(Bf,)).astype(np.int64))
+    fout = {}
+    torch.manual_seed(78)
+    fnoises = [torch.empty(Bf, Lf).normal_() for _ in range(3)]
+    fmodel.train(True); fmodel.zero_grad(); torch.manual_seed(78)
+    r1 = fmodel(fimage, ftext); r2 = fmodel(fimage); r3 = fmodel(text=ftext)
+    fj = ref_train.elbo_loss(r1[0], fimage, r1[1], ftext, r1[2], r1[3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    fi = ref_train.elbo_loss(r2[0], fimage, None, None, r2[2], r2[3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    ft = ref_train.elbo_loss(None, None, r3[1], ftext, r3[2], r3[3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    (fj + fi + ft).backward()
+    fout["image"] = fimage.numpy(); fout["text"] = ftext.numpy(); fout["noises"] = torch.stack(fnoises).numpy()
+    fout["terms"] = np.array([fj.item(), fi.item(), ft.item()], np.float64)
+    for pi, r in enumerate((r1, r2, r3)):
+        fout[f"mu{pi}"] = r[2].detach().numpy(); fout[f"logvar{pi}"] = r[3].detach().numpy()
+        fout[f"recon_text{pi}"] = r[1].detach().numpy(); fout[f"recon_image{pi}"] = r[0].detach().numpy()
+    for k, v in fmodel.named_parameters():
+        fout[f"grad_digest/{k}"] = tensor_digest(v.grad)
+        fout[f"grad_head/{k}"] = v.grad.detach().reshape(-1)[:64].numpy().copy()
+        if v.grad.numel() <= 2048:
+            fout[f"grad_full/{k}"] = v.grad.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "fashion_golden.npz"), **fout)
+
     # ------------------------------------------------------- element-wise KATs
     ew = {}
     poeA = ref_model.ProductOfExperts()

@@ -154,3 +154,21 @@ def test_recon_analytic_vs_autograd():
     xs = rs.standard_normal(100)
     txs = torch.tensor(xs, requires_grad=True); O.swish(txs).sum().backward()
     np.testing.assert_allclose(EN.swish_grad(xs), txs.grad.numpy(), rtol=1e-10)
+
+
+def test_fashion_step_matches_reference():
+    """Conv flavour (fashionmnist/model.py): oracle vs the unmodified reference on the B=4 fixture."""
+    fa = dict(np.load(os.path.join(G, "fashion_golden.npz")))
+    L = 64
+    p = O.make_params(O.fashion_param_shapes(L), seed=0)
+    image = torch.from_numpy(fa["image"]); text = torch.from_numpy(fa["text"])
+    noises = [torch.from_numpy(n) for n in fa["noises"]]
+    loss, terms, grads, aux = O.fashion_step_grads(p, image, text, L, noises, 1.0, 10.0, 0.5)
+    np.testing.assert_allclose([t.item() for t in terms], fa["terms"], rtol=3e-6)
+    for pi in range(3):
+        np.testing.assert_allclose(aux["mu"][pi].detach().numpy(), fa[f"mu{pi}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(aux["recon_image"][pi].detach().numpy(), fa[f"recon_image{pi}"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(aux["recon_text"][pi].detach().numpy(), fa[f"recon_text{pi}"], rtol=1e-4, atol=1e-6)
+    for k, g in grads.items():
+        np.testing.assert_allclose(g.reshape(-1)[:64].numpy(), fa[f"grad_head/{k}"], rtol=3e-4, atol=1e-7)
+        np.testing.assert_allclose(_digest(g)[1:], fa[f"grad_digest/{k}"][1:], rtol=1e-4)
