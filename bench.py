@@ -227,9 +227,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if args.verbose:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
+    e2e_losses = []
+
     def step_e2e(i):
+        # public host-fed API: pinned host batch -> (copy stream) -> device, step, loss read back on the host every
+        # call (one step lagged, as in any asynchronous training loop); flush() at the end of the timed region
         im, tx = host[i % POOL]
-        return tr.step(im, tx, annealing_factor=annealing(i), sync=True)   # loss is read on the host every step
+        v = tr.step_pipelined(im, tx, annealing_factor=annealing(i))
+        if v is not None:
+            e2e_losses.append(v)
 
     # warm-up (also captures the CUDA graph) -- long enough for the clocks to ramp
     log("warm-up / graph capture")
@@ -253,7 +259,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     log("timed region (end to end from pinned host memory)")
     for i in range(3):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    tr.flush()
+
+    def e2e_region(i):
+        step_e2e(i)
+        if i == args.steps - 1:
+            e2e_losses.append(tr.flush())
+    ms_e2e = timed(e2e_region, args.steps)
     e2e = b_global * args.steps / (ms_e2e * 1e-3)
     loss = float(tr.loss_host[0])
 
@@ -288,7 +300,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": b_local * (784 * 4 + 8) + 4, "d2h_bytes_per_step": 16,
-                    "note": "trainer.step(pinned host image, pinned host labels) with the loss read back every step"},
+                    "losses_read": len(e2e_losses),
+                    "note": "trainer.step_pipelined(pinned host image, pinned host labels): H2D of batch i+1 on a copy stream "
+                            "overlaps step i; the loss is copied D2H and read on the host every step (one step lagged)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 kind::tf32, all GEMM launches of a step)",
                          "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,

@@ -529,14 +529,21 @@ __global__ void __launch_bounds__(128) emb_swish_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* __restrict__ g, float* m, float* v, int64_t n,
                                                    float lr, const float* lr_mult_dev, float beta1, float beta2,
                                                    float eps, float grad_scale, const int32_t* step_count) {
+  // bias corrections: one double-precision pow per BLOCK (thread 0), broadcast through shared memory
+  __shared__ float s_step_size, s_inv_sqrt_bc2;
+  if (threadIdx.x == 0) {
+    const int t = *step_count + 1;
+    const float lr_eff = lr * (lr_mult_dev ? __ldg(lr_mult_dev) : 1.0f);
+    const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
+    s_step_size = static_cast<float>(lr_eff / bc1);
+    s_inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  }
+  __syncthreads();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
-  const int t = *step_count + 1;
-  const float lr_eff = lr * (lr_mult_dev ? __ldg(lr_mult_dev) : 1.0f);
-  const double bc1 = 1.0 - pow(static_cast<double>(beta1), t);
-  const double bc2 = 1.0 - pow(static_cast<double>(beta2), t);
-  const float step_size = static_cast<float>(lr_eff / bc1);
-  const float inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
+  const float step_size = s_step_size;
+  const float inv_sqrt_bc2 = s_inv_sqrt_bc2;
   if (i + 3 < n) {
     float4 P = *reinterpret_cast<float4*>(p + i);
     const float4 G = *reinterpret_cast<const float4*>(g + i);

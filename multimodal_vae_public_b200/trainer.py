@@ -410,6 +410,69 @@ class MnistMVAETrainer:
             return float(self.loss_host[0])
         return None
 
+    # ------------------------------------------------------------------ host-fed, double-buffered stepping
+    def _pipe_init(self) -> None:
+        B, dev = self.B, self.dev
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._pipe = []
+        for _ in range(2):
+            slot = {"img": torch.empty(B, 784, dtype=torch.float32, device=dev),
+                    "txt": torch.empty(B, dtype=torch.int64, device=dev),
+                    "beta": torch.ones(1, dtype=torch.float32).pin_memory(),
+                    "loss": torch.zeros(4, dtype=torch.float32).pin_memory(),
+                    "up": torch.cuda.Event(), "free": torch.cuda.Event(), "done": torch.cuda.Event(), "busy": False}
+            slot["free"].record(self._stream)
+            self._pipe.append(slot)
+        self._pipe_idx = 0
+
+    def step_pipelined(self, image: torch.Tensor, text: torch.Tensor, annealing_factor: float = 1.0,
+                       training: bool = True, update: bool = True) -> Optional[float]:
+        """Like ``step`` for HOST batches (pinned memory recommended), but the upload of this batch runs on a copy
+        stream while the previous step is still computing, and the loss that is read back (and returned) is the
+        PREVIOUS call's -- the usual one-step-lagged logging of an asynchronous training loop.  Returns None on the
+        first call; ``flush()`` returns the last loss.  Every call still moves one batch host->device and one loss
+        device->host."""
+        if not hasattr(self, "_pipe"):
+            self._pipe_init()
+        B = self.B
+        k = self._pipe_idx
+        self._pipe_idx ^= 1
+        cur, prev = self._pipe[k], self._pipe[k ^ 1]
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(cur["free"])            # the compute stream finished reading this staging slot
+            cur["img"].copy_(image.reshape(B, 784), non_blocking=True)
+            cur["txt"].copy_(text.reshape(B), non_blocking=True)
+            cur["up"].record(self._copy_stream)
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(cur["up"])
+            self.x.copy_(cur["img"], non_blocking=True)
+            self.text.copy_(cur["txt"], non_blocking=True)
+            cur["free"].record(self._stream)
+            cur["beta"][0] = float(annealing_factor)
+            self.beta_dev.copy_(cur["beta"], non_blocking=True)
+        self.run(training=training, noise_given=False, update=update)
+        with torch.cuda.stream(self._stream):
+            cur["loss"].copy_(self.loss_out, non_blocking=True)
+            cur["done"].record(self._stream)
+        cur["busy"] = True
+        if prev["busy"]:
+            prev["done"].synchronize()
+            prev["busy"] = False
+            return float(prev["loss"][0])
+        return None
+
+    def flush(self) -> Optional[float]:
+        """Wait for the in-flight pipelined step and return its loss."""
+        out = None
+        if hasattr(self, "_pipe"):
+            for slot in (self._pipe[self._pipe_idx], self._pipe[self._pipe_idx ^ 1]):
+                if slot["busy"]:
+                    slot["done"].synchronize()
+                    slot["busy"] = False
+                    out = float(slot["loss"][0])
+                    self.loss_host.copy_(slot["loss"])
+        return out
+
     def losses(self) -> Dict[str, float]:
         """(after a synchronised step) the reference's three ELBO terms and their sum."""
         v = self.loss_host

@@ -149,3 +149,25 @@ def test_full_size_properties():
     for k in full:
         err = (acc[k] - full[k]).abs().max().item() / max(full[k].abs().max().item(), 1e-12)
         assert err <= 2e-5, (k, err)
+
+
+def test_pipelined_host_fed_steps_equal_synchronous_steps():
+    B, L = 128, 64
+    rs = np.random.RandomState(2)
+    batches = [(torch.from_numpy(rs.uniform(0, 1, (B, 784)).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rs.randint(0, 10, B)).pin_memory()) for _ in range(5)]
+    a, b = _trainer(B, 1, graph=True), _trainer(B, 1, graph=True)
+    b.load_state_dict(a.state_dict())
+    # eval-mode steps (no noise) so both trainers see identical inputs; updates on
+    ref = [a.step(im, tx, annealing_factor=0.5, training=False) for im, tx in batches]
+    got = []
+    for im, tx in batches:
+        v = b.step_pipelined(im, tx, annealing_factor=0.5, training=False)
+        if v is not None:
+            got.append(v)
+    got.append(b.flush())
+    assert len(got) == len(ref)
+    for x, y in zip(ref, got):
+        assert abs(x - y) <= 2e-6 * abs(x)
+    for k in a.params:
+        assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-5, k
