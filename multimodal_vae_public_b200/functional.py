@@ -96,6 +96,122 @@ def linear_swish(x, w, b, precision: int = DEFAULT_PRECISION):
     return _LinearFn.apply(x, w, b, True, precision)
 
 
+def _conv_weight_cols(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [Cout,Cin,4,4] -> GEMM operand [Cout, (kh,kw,ci)]."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+def _convT_weight_cols(w: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d weight [Cin,Cout,4,4] -> GEMM operand [(kh,kw,co), Cin]."""
+    return w.permute(2, 3, 1, 0).reshape(-1, w.shape[0]).contiguous()
+
+
+class _Conv4x4s2Fn(Function):
+    """nn.Conv2d(Cin, Cout, 4, 2, 1, bias=False) on NCHW tensors (fashionmnist/model.py:79-82), optional fused Swish.
+    NHWC internally: im2col kernel + tcgen05 GEMM; backward = GEMM dgrad + col2im gather, GEMM wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w, act: bool, prec: int):
+        _need_cuda(x, w)
+        B, Cin, H, W = x.shape
+        Cout = w.shape[0]
+        xh = x.detach().to(torch.float32).permute(0, 2, 3, 1).contiguous()
+        OH, OW = H // 2, W // 2
+        cols = _padded(B * OH * OW, 16 * Cin, xh)
+        ops.im2col_k4s2p1(xh, cols, B, H, W, Cin)
+        wp = _as_operand(_conv_weight_cols(w.detach().to(torch.float32)))
+        a = _padded(B * OH * OW, Cout, xh)
+        h = _padded(B * OH * OW, Cout, xh) if act else None
+        ops.gemm_batch([ops.gemm_desc(cols, wp, a, B * OH * OW, Cout, 16 * Cin, out2=h,
+                                      epilogue=ops.EPI_BIAS_SWISH if act else ops.EPI_STORE)], prec)
+        ctx.save_for_backward(cols, wp, a if act else None)
+        ctx.meta = (B, Cin, H, W, Cout, act, prec)
+        out = h if act else a
+        return out.reshape(B, OH, OW, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, wp, a = ctx.saved_tensors
+        B, Cin, H, W, Cout, act, prec = ctx.meta
+        OH, OW = H // 2, W // 2
+        M = B * OH * OW
+        d = _as_operand(dy.to(torch.float32).permute(0, 2, 3, 1).reshape(M, Cout))
+        if act:
+            da = _padded(M, Cout, d)
+            if d.stride(0) == Cout and a.stride(0) == Cout:
+                ops.swish_bwd(a, d.contiguous(), da)
+            else:
+                s = torch.sigmoid(a)
+                da.copy_(d * s * (1 + a * (1 - s)))
+            d = da
+        dx = dw = None
+        if ctx.needs_input_grad[1]:
+            dwp = _padded(Cout, 16 * Cin, d, zero=True)
+            ops.gemm_batch([ops.gemm_desc(d, cols, dwp, Cout, 16 * Cin, M, a_mn=True, b_mn=True, split_k=_split_k(M),
+                                          accumulate=True)], prec)
+            dw = dwp.reshape(Cout, 4, 4, Cin).permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[0]:
+            dcols = _padded(M, 16 * Cin, d)
+            ops.gemm_batch([ops.gemm_desc(d, wp, dcols, M, 16 * Cin, Cout, b_mn=True)], prec)
+            dxh = torch.empty(B, H, W, Cin, dtype=torch.float32, device=d.device)
+            ops.col2im_k4s2p1(dcols, dxh, B, OH, OW, Cin)
+            dx = dxh.permute(0, 3, 1, 2)
+        return dx, dw, None, None
+
+
+class _ConvT4x4s2Fn(Function):
+    """nn.ConvTranspose2d(Cin, Cout, 4, 2, 1, bias=False) on NCHW tensors (fashionmnist/model.py:112-114), optional
+    fused Swish: tcgen05 GEMM + col2im gather; backward = im2col + GEMM dgrad / wgrad."""
+
+    @staticmethod
+    def forward(ctx, x, w, act: bool, prec: int):
+        _need_cuda(x, w)
+        B, Cin, IH, IW = x.shape
+        Cout = w.shape[1]
+        xh = _as_operand(x.detach().to(torch.float32).permute(0, 2, 3, 1).reshape(B * IH * IW, Cin))
+        wp = _as_operand(_convT_weight_cols(w.detach().to(torch.float32)))
+        cols = _padded(B * IH * IW, 16 * Cout, xh)
+        ops.gemm_batch([ops.gemm_desc(xh, wp, cols, B * IH * IW, 16 * Cout, Cin)], prec)
+        a = torch.empty(B, 2 * IH, 2 * IW, Cout, dtype=torch.float32, device=xh.device)
+        h = torch.empty_like(a) if act else None
+        ops.col2im_k4s2p1(cols, a, B, IH, IW, Cout, out_act=h)
+        ctx.save_for_backward(xh, wp, a if act else None)
+        ctx.meta = (B, Cin, IH, IW, Cout, act, prec)
+        return (h if act else a).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, wp, a = ctx.saved_tensors
+        B, Cin, IH, IW, Cout, act, prec = ctx.meta
+        M = B * IH * IW
+        d = dy.to(torch.float32).permute(0, 2, 3, 1).contiguous()
+        if act:
+            da = torch.empty_like(d)
+            ops.swish_bwd(a, d, da)
+            d = da
+        dcols = _padded(M, 16 * Cout, d)
+        ops.im2col_k4s2p1(d, dcols, B, 2 * IH, 2 * IW, Cout)
+        dx = dw = None
+        if ctx.needs_input_grad[1]:
+            dwp = _padded(16 * Cout, Cin, d, zero=True)
+            ops.gemm_batch([ops.gemm_desc(dcols, xh, dwp, 16 * Cout, Cin, M, a_mn=True, b_mn=True, split_k=_split_k(M),
+                                          accumulate=True)], prec)
+            dw = dwp.reshape(4, 4, Cout, Cin).permute(3, 2, 0, 1)
+        if ctx.needs_input_grad[0]:
+            dxh = _padded(M, Cin, d)
+            ops.gemm_batch([ops.gemm_desc(dcols, wp, dxh, M, Cin, 16 * Cout, b_mn=True)], prec)
+            dx = dxh.reshape(B, IH, IW, Cin).permute(0, 3, 1, 2)
+        return dx, dw, None, None
+
+
+def conv4x4s2(x, w, swish_act: bool = False, precision: int = DEFAULT_PRECISION):
+    return _Conv4x4s2Fn.apply(x, w, swish_act, precision)
+
+
+def conv_transpose4x4s2(x, w, swish_act: bool = False, precision: int = DEFAULT_PRECISION):
+    return _ConvT4x4s2Fn.apply(x, w, swish_act, precision)
+
+
 class _SwishFn(Function):
     """x * sigmoid(x)  (Swish, mnist/model.py:166-169)."""
 

@@ -119,3 +119,32 @@ def test_elementwise_loss_functions_match_oracle():
     rce = O.cross_entropy_rows(lr, tg.cpu()); rce.sum(dim=1).mean().backward()
     np.testing.assert_allclose(ce.detach().cpu().numpy(), rce.detach().numpy(), rtol=2e-6, atol=1e-7)
     np.testing.assert_allclose(lg.grad.cpu().numpy(), lr.grad.numpy(), rtol=2e-5, atol=1e-7)
+
+
+def test_fashion_modules_match_oracle():
+    """Drop-in fashionmnist/model.py surface: state_dict keys, eval forward of the three passes, ELBO, every gradient."""
+    from multimodal_vae_public_b200.fashionmnist import model as FM, train as FT
+    L, B = 64, 12
+    m = FM.MVAE(L)
+    assert list(m.state_dict().keys()) == [k for k, _ in O.fashion_param_shapes(L)]
+    p32 = O.make_params(O.fashion_param_shapes(L), seed=4)
+    m.load_state_dict(p32)
+    m = m.cuda().eval()
+    rs = np.random.RandomState(8)
+    image = torch.from_numpy(rs.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32)); text = torch.from_numpy(rs.randint(0, 10, B))
+    ic, tc = image.cuda(), text.cuda()
+    outs = [m(ic, tc), m(ic), m(text=tc)]
+    j = FT.elbo_loss(outs[0][0], ic, outs[0][1], tc, outs[0][2], outs[0][3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    i = FT.elbo_loss(outs[1][0], ic, None, None, outs[1][2], outs[1][3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    t = FT.elbo_loss(None, None, outs[2][1], tc, outs[2][2], outs[2][3], lambda_image=1.0, lambda_text=10.0, annealing_factor=0.5)
+    (j + i + t).backward()
+    ref, terms, grads, aux = O.fashion_step_grads({k: v.double() for k, v in p32.items()}, image.double(), text, L,
+                                                  [None] * 3, 1.0, 10.0, 0.5)
+    assert abs((j + i + t).item() - ref.item()) <= 5e-6 * abs(ref.item())
+    assert outs[0][0].shape == (B, 1, 28, 28)
+    np.testing.assert_allclose(outs[0][0].detach().cpu().numpy(), aux["recon_image"][0].detach().numpy(), rtol=1e-3, atol=1e-4)
+    for k, v in m.named_parameters():
+        g = grads[k]
+        err = (v.grad.cpu().double() - g).abs().max().item() / max(g.abs().max().item(), 1e-12)
+        assert err < 5e-4, (k, err)
+    assert FT.annealing_factor(1, 0, 600, 200) == pytest.approx(601.0 / (200 * 600))
