@@ -166,6 +166,41 @@ int mvae_ce_fwd_bwd(const float* x, int64_t ldx, const int64_t* target, int t_ro
 int mvae_im2col_k4s2p1(const float* x, float* cols, int64_t ld_cols, int B, int H, int W, int C, void* stream);
 int mvae_col2im_k4s2p1(const float* cols, int64_t ld_cols, float* out, float* out_act, const float* aux, int B, int IH,
                        int IW, int C, void* stream);
+/* General 4x4 variants (stride, pad): CelebA also uses k4 s1 p0 (8x8 <-> 5x5, celeba/model.py:85,117).
+ *   im2col: OH = (H + 2 pad - 4)/stride + 1 ;  col2im: OH = (IH - 1) stride - 2 pad + 4.                     */
+int mvae_im2col_k4(const float* x, float* cols, int64_t ld_cols, int B, int H, int W, int C, int stride, int pad,
+                   void* stream);
+int mvae_col2im_k4(const float* cols, int64_t ld_cols, float* out, float* out_act, const float* aux, int B, int IH, int IW,
+                   int C, int stride, int pad, void* stream);
+
+/* Train-mode BatchNorm2d/1d (+ Swish) over [rows, C] activations split into S equal row segments (one per stacked
+ * model() call), celeba/model.py:80,83,86,118,121,124,149,152,176,179,182.  eps = 1e-5, momentum = 0.1 (nn defaults).
+ *   bn_stats    : acc[S][C][2] (double) = per-segment sum / sum of squares (zeroed by the call)
+ *   bn_finalize : mean/invstd [S][C]; running stats updated once per entry of update_order (segment indices in the
+ *                 reference's call order; a segment may appear twice when the reference evaluates a net twice)
+ *   bn_eval_stats: mean/invstd from the running statistics (model.eval())
+ *   bn_apply    : h = [swish](gamma * (x - mean) * invstd + beta)
+ *   bn_bwd      : for the live segments [seg0, seg0+nseg): dx (through Swish and BN), dgamma += , dbeta +=           */
+int mvae_bn_stats(const float* x, int64_t ldx, int S, int seg_rows, int C, double* acc, void* stream);
+int mvae_bn_finalize(const double* acc, int S, int seg_rows, int C, float eps, float momentum, float* mean, float* invstd,
+                     float* running_mean, float* running_var, const int32_t* update_order, int n_updates, void* stream);
+int mvae_bn_eval_stats(const float* running_mean, const float* running_var, int S, int C, float eps, float* mean,
+                       float* invstd, void* stream);
+int mvae_bn_apply(const float* x, int64_t ldx, float* h, int64_t ldh, int rows, int seg_rows, int C, const float* mean,
+                  const float* invstd, const float* gamma, const float* beta, int swish_act, void* stream);
+int mvae_bn_bwd(const float* x, int64_t ldx, const float* dh, int64_t lddh, float* dx, int64_t lddx, int S, int seg_rows,
+                int C, int seg0, int nseg, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                int swish_act, double* acc2, float* dgamma, float* dbeta, void* stream);
+
+/* nn.Dropout(p) (celeba/model.py:91) on `copies` stacked calls over the same input x [x_rows, D]:
+ *   y[k*x_rows + r] = x[r] * mask / (1 - p), fresh mask per copy (hash of (index, seed, *step_dev)) or mask_in.
+ *   backward: dx[r] = sum_k dy[k*x_rows + r] * mask / (1 - p).                                                      */
+int mvae_dropout_fwd(const float* x, int x_rows, float* y, float* mask_out, const float* mask_in, int copies, int D,
+                     float p, uint64_t seed, const int32_t* step_dev, void* stream);
+int mvae_dropout_bwd(const float* dy, const float* mask, float* dx, int x_rows, int copies, int D, float p, void* stream);
+
+/* NCHW -> NHWC staging of the input image batch (the kernels work on NHWC). */
+int mvae_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW, void* stream);
 
 /* Fused flat Adam over one contiguous parameter bucket (torch.optim.Adam defaults, mnist/train.py:168,219):
  *   g is first multiplied by grad_scale (1/world_size after a sum-allreduce).

@@ -59,6 +59,16 @@ SIGNATURES = {
     "mvae_ce_fwd_bwd": [_P, _L, _P, _I, _P, _L, _I, _I, _F, _P, _I, _P, _L, _P],
     "mvae_im2col_k4s2p1": [_P, _P, _L, _I, _I, _I, _I, _P],
     "mvae_col2im_k4s2p1": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _P],
+    "mvae_im2col_k4": [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
+    "mvae_col2im_k4": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mvae_bn_stats": [_P, _L, _I, _I, _I, _P, _P],
+    "mvae_bn_finalize": [_P, _I, _I, _I, _F, _F, _P, _P, _P, _P, C.POINTER(C.c_int32), _I, _P],
+    "mvae_bn_eval_stats": [_P, _P, _I, _I, _F, _P, _P, _P],
+    "mvae_bn_apply": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _P],
+    "mvae_bn_bwd": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    "mvae_dropout_fwd": [_P, _I, _P, _P, _P, _I, _I, _F, _U64, _P, _P],
+    "mvae_dropout_bwd": [_P, _P, _P, _I, _I, _I, _F, _P],
+    "mvae_nchw_to_nhwc": [_P, _P, _I, _I, _I, _P],
     "mvae_adam_flat": [_P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _F, _P, _P],
     "mvae_elbo_finalize": [_P, _P, _P, _I, _F, _F, _F, _P, _F, _P, _P],
 }

@@ -21,8 +21,8 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf
 // one thread = one float4 of channels (or one scalar when C < 4) of one (output pixel, tap)
 template <int VEC>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ cols, int B, int H,
-                                                     int W, int C, int64_t ld_cols) {
-  const int OH = H / 2, OW = W / 2;
+                                                     int W, int C, int64_t ld_cols, int stride, int pad) {
+  const int OH = (H + 2 * pad - 4) / stride + 1, OW = (W + 2 * pad - 4) / stride + 1;
   const int cv = C / VEC;
   const int64_t total = static_cast<int64_t>(B) * OH * OW * 16 * cv;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
   const int oh = static_cast<int>(r2 % OH);
   const int b = static_cast<int>(r2 / OH);
   const int kh = tap >> 2, kw = tap & 3;
-  const int ih = 2 * oh - 1 + kh, iw = 2 * ow - 1 + kw;
+  const int ih = stride * oh - pad + kh, iw = stride * ow - pad + kw;
   float* dst = cols + r * ld_cols + tap * C + c;
   const bool in = (ih >= 0 && ih < H && iw >= 0 && iw < W);
   const float* src = x + ((static_cast<int64_t>(b) * H + ih) * W + iw) * C + c;
@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
 template <int VEC>
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ cols, int64_t ld_cols, float* out,
                                                      float* out_act, const float* __restrict__ aux, int B, int IH,
-                                                     int IW, int C) {
-  const int OH = 2 * IH, OW = 2 * IW;
+                                                     int IW, int C, int stride, int pad) {
+  const int OH = (IH - 1) * stride - 2 * pad + 4, OW = (IW - 1) * stride - 2 * pad + 4;
   const int cv = C / VEC;
   const int64_t total = static_cast<int64_t>(B) * OH * OW * cv;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -66,17 +66,18 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ c
   float acc[VEC];
 #pragma unroll
   for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
-  const int kh0 = (oh + 1) & 1, kw0 = (ow + 1) & 1;
 #pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    const int kh = kh0 + 2 * a;
-    const int ih = (oh + 1 - kh) >> 1;          // exact: oh + 1 - kh is even
-    if (ih < 0 || ih >= IH) continue;
+  for (int kh = 0; kh < 4; ++kh) {
+    const int th = oh + pad - kh;               // = stride * ih
+    if (th < 0 || th % stride != 0) continue;
+    const int ih = th / stride;
+    if (ih >= IH) continue;
 #pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const int kw = kw0 + 2 * d;
-      const int iw = (ow + 1 - kw) >> 1;
-      if (iw < 0 || iw >= IW) continue;
+    for (int kw = 0; kw < 4; ++kw) {
+      const int tw = ow + pad - kw;
+      if (tw < 0 || tw % stride != 0) continue;
+      const int iw = tw / stride;
+      if (iw >= IW) continue;
       const float* src = cols + ((static_cast<int64_t>(b) * IH + ih) * IW + iw) * ld_cols + (kh * 4 + kw) * C + c;
       if constexpr (VEC == 4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(src));
@@ -108,33 +109,45 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ c
 
 using namespace mvae;
 
-extern "C" int mvae_im2col_k4s2p1(const float* x, float* cols, int64_t ld_cols, int B, int H, int W, int C,
-                                  void* stream) {
-  if (!x || !cols || B < 1 || H < 2 || W < 2 || (H & 1) || (W & 1) || C < 1 || ld_cols < 16 * C)
-    return set_error(MVAE_ERR_BAD_ARG, "im2col: bad arguments (even H, W required; ld_cols >= 16*C)");
+extern "C" int mvae_im2col_k4(const float* x, float* cols, int64_t ld_cols, int B, int H, int W, int C, int stride,
+                              int pad, void* stream) {
+  if (!x || !cols || B < 1 || H < 1 || W < 1 || C < 1 || ld_cols < 16 * C || stride < 1 || pad < 0 ||
+      H + 2 * pad < 4 || W + 2 * pad < 4)
+    return set_error(MVAE_ERR_BAD_ARG, "im2col: bad arguments (ld_cols >= 16*C)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool v4 = (C % 4 == 0) && (ld_cols % 4 == 0) &&
                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(cols)) & 15) == 0;
-  const int64_t total = static_cast<int64_t>(B) * (H / 2) * (W / 2) * 16 * (v4 ? C / 4 : C);
+  const int OH = (H + 2 * pad - 4) / stride + 1, OW = (W + 2 * pad - 4) / stride + 1;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW * 16 * (v4 ? C / 4 : C);
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (v4) im2col_kernel<4><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols);
-  else    im2col_kernel<1><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols);
+  if (v4) im2col_kernel<4><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols, stride, pad);
+  else    im2col_kernel<1><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols, stride, pad);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
 }
+extern "C" int mvae_im2col_k4s2p1(const float* x, float* cols, int64_t ld_cols, int B, int H, int W, int C,
+                                  void* stream) {
+  if ((H & 1) || (W & 1)) return set_error(MVAE_ERR_BAD_ARG, "im2col_k4s2p1: even H, W required");
+  return mvae_im2col_k4(x, cols, ld_cols, B, H, W, C, 2, 1, stream);
+}
 
-extern "C" int mvae_col2im_k4s2p1(const float* cols, int64_t ld_cols, float* out, float* out_act, const float* aux,
-                                  int B, int IH, int IW, int C, void* stream) {
-  if (!cols || !out || B < 1 || IH < 1 || IW < 1 || C < 1 || ld_cols < 16 * C)
+extern "C" int mvae_col2im_k4(const float* cols, int64_t ld_cols, float* out, float* out_act, const float* aux, int B,
+                              int IH, int IW, int C, int stride, int pad, void* stream) {
+  if (!cols || !out || B < 1 || IH < 1 || IW < 1 || C < 1 || ld_cols < 16 * C || stride < 1 || pad < 0)
     return set_error(MVAE_ERR_BAD_ARG, "col2im: bad arguments (ld_cols >= 16*C)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool v4 = (C % 4 == 0) && (ld_cols % 4 == 0) && (reinterpret_cast<uintptr_t>(cols) & 15) == 0;
-  const int64_t total = static_cast<int64_t>(B) * (2 * IH) * (2 * IW) * (v4 ? C / 4 : C);
+  const int OH = (IH - 1) * stride - 2 * pad + 4, OW = (IW - 1) * stride - 2 * pad + 4;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW * (v4 ? C / 4 : C);
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-  if (v4) col2im_kernel<4><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C);
-  else    col2im_kernel<1><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C);
+  if (v4) col2im_kernel<4><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C, stride, pad);
+  else    col2im_kernel<1><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C, stride, pad);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
+}
+extern "C" int mvae_col2im_k4s2p1(const float* cols, int64_t ld_cols, float* out, float* out_act, const float* aux,
+                                  int B, int IH, int IW, int C, void* stream) {
+  return mvae_col2im_k4(cols, ld_cols, out, out_act, aux, B, IH, IW, C, 2, 1, stream);
 }

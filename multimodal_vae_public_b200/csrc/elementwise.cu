@@ -410,6 +410,31 @@ __global__ void __launch_bounds__(256, 4) bce_kernel(const float* __restrict__ x
   if (loss_acc != nullptr) block_atomic_add_seg(acc, cur_seg < 0 ? 0 : cur_seg, loss_acc, scratch, &seg_smem);
 }
 
+// BCE for narrow rows (D not a multiple of 4, e.g. the 18 CelebA attributes): one thread per row.
+__global__ void __launch_bounds__(256) bce_rows_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ t,
+                                                       int64_t ldt, int t_rows, float* dx, int64_t lddx, int R, int D,
+                                                       float scale, double* loss_acc, int seg_rows, float* loss_elem,
+                                                       int64_t ldl) {
+  __shared__ double scratch[32];
+  __shared__ int seg_smem;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  double loss = 0.0;
+  if (r < R) {
+    const float* xr = x + static_cast<int64_t>(r) * ldx;
+    const float* tr = t + static_cast<int64_t>(r % t_rows) * ldt;
+    for (int k = 0; k < D; ++k) {
+      const float xq = xr[k], tq = tr[k];
+      const float e = expf(-fabsf(xq));
+      const float inv = 1.0f / (1.0f + e);
+      const float le = fmaxf(xq, 0.f) - xq * tq + logf(1.0f + e);
+      loss += static_cast<double>(le);
+      if (loss_elem) loss_elem[static_cast<int64_t>(r) * ldl + k] = le;
+      if (dx) dx[static_cast<int64_t>(r) * lddx + k] = scale * ((xq >= 0.f ? inv : e * inv) - tq);
+    }
+  }
+  if (loss_acc != nullptr) block_atomic_add_seg(loss, (r < R ? r : R - 1) / seg_rows, loss_acc, scratch, &seg_smem);
+}
+
 // ---------------------------------------------------------------- cross entropy (K small): one thread per row
 __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ x, int64_t ldx, const int64_t* __restrict__ target,
                                                  int t_rows, float* dx, int64_t lddx, int R, int K, float scale,
@@ -722,8 +747,14 @@ extern "C" int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float*
   if (seg_rows < 1) seg_rows = R;
   auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if ((D & 3) || (ldx & 3) || (ldt & 3) || (dx && (lddx & 3)) || !al(x) || !al(t) || !al(dx) ||
-      (loss_elem && ((ldl & 3) || !al(loss_elem))))
-    return set_error(MVAE_ERR_UNSUPPORTED, "bce: D and leading dims must be multiples of 4 and pointers 16B aligned");
+      (loss_elem && ((ldl & 3) || !al(loss_elem)))) {
+    if (D > 4096) return set_error(MVAE_ERR_UNSUPPORTED, "bce: wide rows need D, ld multiples of 4 and 16B aligned pointers");
+    bce_rows_kernel<<<(R + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, ldx, t, ldt, t_rows, dx, lddx, R, D, scale, loss_acc, seg_rows, loss_elem, ldl);
+    count_launch();
+    MVAE_CUDA_CHECK(cudaGetLastError());
+    return MVAE_OK;
+  }
   const int64_t n4 = static_cast<int64_t>(R) * (D / 4);
   if (n4 >= (int64_t(1) << 31) || ldx >= (int64_t(1) << 31) || ldt >= (int64_t(1) << 31) || lddx >= (int64_t(1) << 31) ||
       ldl >= (int64_t(1) << 31))

@@ -176,6 +176,59 @@ def col2im_k4s2p1(cols, out, B, IH, IW, Cch, out_act=None, aux=None):
                                               IH, IW, Cch, _stream()), "mvae_col2im_k4s2p1")
 
 
+def im2col_k4(x, cols, B, H, W, Cch, stride, pad):
+    _lib.check(_lib.load().mvae_im2col_k4(x.data_ptr(), cols.data_ptr(), cols.stride(0), B, H, W, Cch, stride, pad,
+                                          _stream()), "mvae_im2col_k4")
+
+
+def col2im_k4(cols, out, B, IH, IW, Cch, stride, pad, out_act=None, aux=None):
+    _lib.check(_lib.load().mvae_col2im_k4(cols.data_ptr(), cols.stride(0), out.data_ptr(), _p(out_act), _p(aux), B, IH, IW,
+                                          Cch, stride, pad, _stream()), "mvae_col2im_k4")
+
+
+def bn_forward(x, h, S, seg_rows, gamma, beta, mean, invstd, acc, running_mean=None, running_var=None, update_order=(),
+               training=True, act=True, eps=1e-5, momentum=0.1):
+    """Train/eval BatchNorm (+Swish) over x [S*seg_rows, C] -> h; fills mean/invstd [S, C]."""
+    lib = _lib.load()
+    Cch = x.shape[1]
+    if training:
+        _lib.check(lib.mvae_bn_stats(x.data_ptr(), x.stride(0), S, seg_rows, Cch, acc.data_ptr(), _stream()), "mvae_bn_stats")
+        order = (C.c_int32 * max(len(update_order), 1))(*update_order)
+        _lib.check(lib.mvae_bn_finalize(acc.data_ptr(), S, seg_rows, Cch, eps, momentum, mean.data_ptr(), invstd.data_ptr(),
+                                        _p(running_mean), _p(running_var), order, len(update_order), _stream()),
+                   "mvae_bn_finalize")
+    else:
+        _lib.check(lib.mvae_bn_eval_stats(running_mean.data_ptr(), running_var.data_ptr(), S, Cch, eps, mean.data_ptr(),
+                                          invstd.data_ptr(), _stream()), "mvae_bn_eval_stats")
+    _lib.check(lib.mvae_bn_apply(x.data_ptr(), x.stride(0), h.data_ptr(), h.stride(0), S * seg_rows, seg_rows, Cch,
+                                 mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(), int(act), _stream()),
+               "mvae_bn_apply")
+
+
+def bn_backward(x, dh, dx, S, seg_rows, seg0, nseg, gamma, beta, mean, invstd, acc2, dgamma, dbeta, act=True):
+    Cch = x.shape[1]
+    _lib.check(_lib.load().mvae_bn_bwd(x.data_ptr(), x.stride(0), dh.data_ptr(), dh.stride(0), dx.data_ptr(), dx.stride(0), S,
+                                       seg_rows, Cch, seg0, nseg, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
+                                       beta.data_ptr(), int(act), acc2.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                       _stream()), "mvae_bn_bwd")
+
+
+def dropout_fwd(x, y, copies, p, mask_out=None, mask_in=None, seed=0, step_dev=None):
+    x_rows, D = x.shape
+    _lib.check(_lib.load().mvae_dropout_fwd(x.data_ptr(), x_rows, y.data_ptr(), _p(mask_out), _p(mask_in), copies, D, p, seed,
+                                            _p(step_dev), _stream()), "mvae_dropout_fwd")
+
+
+def dropout_bwd(dy, mask, dx, copies, p):
+    x_rows, D = dx.shape
+    _lib.check(_lib.load().mvae_dropout_bwd(dy.data_ptr(), mask.data_ptr(), dx.data_ptr(), x_rows, copies, D, p, _stream()),
+               "mvae_dropout_bwd")
+
+
+def nchw_to_nhwc(x, y, B, Cch, HW):
+    _lib.check(_lib.load().mvae_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), B, Cch, HW, _stream()), "mvae_nchw_to_nhwc")
+
+
 def adam_flat(p, g, m, v, step_count, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, lr_mult_dev=None):
     _lib.check(_lib.load().mvae_adam_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
                                           _p(lr_mult_dev), beta1, beta2, eps, grad_scale, step_count.data_ptr(),
