@@ -145,6 +145,54 @@ def main():
             fout[f"grad_full/{k}"] = v.grad.detach().numpy().copy()
     np.savez_compressed(os.path.join(HERE, "fashion_golden.npz"), **fout)
 
+    # ---------------------------------------------------------------- celeba (conv + BatchNorm + Dropout, PoE variant B)
+    from oracle import celeba_oracle as CO
+    cds = types.ModuleType("datasets"); cds.N_ATTRS = 18; cds.CelebAttributes = object
+    tqm = types.ModuleType("tqdm"); tqm.tqdm = lambda x=None, **k: x
+    ref_cm = load_ref("celeba", "model", "ref_celeba_model2", {"datasets": cds})
+    ref_ct = load_ref("celeba", "train", "ref_celeba_train2", {"datasets": cds, "model": ref_cm, "tqdm": sys.modules.get("tqdm", tqm)})
+    Lc, Bc = 100, 4
+    cstate = CO.make_celeba_state(Lc, seed=0)
+    cmodel = ref_cm.MVAE(Lc)
+    assert list(cmodel.state_dict().keys()) == [k for k, _ in CO.celeba_state_shapes(Lc)]
+    cmodel.load_state_dict(cstate)
+    rs = np.random.RandomState(2468)
+    cimage = torch.from_numpy(rs.uniform(0, 1, size=(Bc, 3, 64, 64)).astype(np.float32))
+    cattrs = torch.from_numpy(rs.randint(0, 2, size=(Bc, 18)).astype(np.float32))
+    cout = {"image": cimage.numpy(), "attrs": cattrs.numpy()}
+    # replay of the reference's RNG draws of one train-mode step: dropout mask then noise per model() call
+    torch.manual_seed(79)
+    m1 = torch.empty(Bc, 512).bernoulli_(0.9); n1 = torch.empty(Bc, Lc).normal_()
+    m2 = torch.empty(Bc, 512).bernoulli_(0.9); n2 = torch.empty(Bc, Lc).normal_()
+    n3 = torch.empty(Bc, Lc).normal_()
+    captured = []
+    hook = cmodel.image_encoder.classifier[2].register_forward_hook(lambda mod, inp, out: captured.append((out != 0).float()))
+    for mode, tag in ((True, "train"), (False, "eval")):
+        cmodel.load_state_dict(cstate)
+        cmodel.train(mode); cmodel.zero_grad(); torch.manual_seed(79); captured.clear()
+        r1 = cmodel(cimage, cattrs); r2 = cmodel(cimage); r3 = cmodel(attrs=cattrs)
+        cj = ref_ct.elbo_loss(r1[0], cimage, r1[1], cattrs, r1[2], r1[3], lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+        ci = ref_ct.elbo_loss(r2[0], cimage, None, None, r2[2], r2[3], lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+        ca = ref_ct.elbo_loss(None, None, r3[1], cattrs, r3[2], r3[3], lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+        (cj + ci + ca).backward()
+        if mode:
+            assert torch.equal(captured[0], m1) and torch.equal(captured[1], m2), "dropout RNG replay does not match the reference"
+        cout[f"{tag}_terms"] = np.array([cj.item(), ci.item(), ca.item()], np.float64)
+        for pi, r in enumerate((r1, r2, r3)):
+            cout[f"{tag}_mu{pi}"] = r[2].detach().numpy(); cout[f"{tag}_logvar{pi}"] = r[3].detach().numpy()
+            cout[f"{tag}_recon_attrs{pi}"] = r[1].detach().numpy()
+            cout[f"{tag}_recon_image{pi}_digest"] = tensor_digest(r[0]); cout[f"{tag}_recon_image{pi}_head"] = r[0].detach().reshape(-1)[:256].numpy().copy()
+        for k, v in cmodel.named_parameters():
+            cout[f"{tag}_grad_digest/{k}"] = tensor_digest(v.grad)
+            cout[f"{tag}_grad_head/{k}"] = v.grad.detach().reshape(-1)[:64].numpy().copy()
+        if mode:
+            for k, v in cmodel.state_dict().items():
+                if k.endswith("running_mean") or k.endswith("running_var"):
+                    cout[f"train_buffer/{k}"] = v.numpy().copy()
+    hook.remove()
+    cout["noises"] = torch.stack([n1, n2, n3]).numpy(); cout["drop_masks"] = torch.stack([m1, m2]).numpy()
+    np.savez_compressed(os.path.join(HERE, "celeba_golden.npz"), **cout)
+
     # ------------------------------------------------------- element-wise KATs
     ew = {}
     poeA = ref_model.ProductOfExperts()

@@ -172,3 +172,28 @@ def test_fashion_step_matches_reference():
     for k, g in grads.items():
         np.testing.assert_allclose(g.reshape(-1)[:64].numpy(), fa[f"grad_head/{k}"], rtol=3e-4, atol=1e-7)
         np.testing.assert_allclose(_digest(g)[1:], fa[f"grad_digest/{k}"][1:], rtol=1e-4)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_celeba_step_matches_reference(mode):
+    """CelebA flavour (conv + BatchNorm + Dropout, PoE variant B): oracle vs the unmodified reference, B=4 fixture;
+    dropout masks / noise are the reference's own RNG draws (replayed by make_golden.py)."""
+    from oracle import celeba_oracle as CO
+    ce = dict(np.load(os.path.join(G, "celeba_golden.npz")))
+    L = 100
+    st = CO.make_celeba_state(L, seed=0)
+    image = torch.from_numpy(ce["image"]); attrs = torch.from_numpy(ce["attrs"])
+    noises = [torch.from_numpy(n) for n in ce["noises"]]; masks = [torch.from_numpy(m) for m in ce["drop_masks"]]
+    loss, terms, grads, bufs, aux = CO.step_grads(st, image, attrs, L, noises, masks, 1.0, 10.0, 0.5, training=(mode == "train"))
+    np.testing.assert_allclose([t.item() for t in terms], ce[f"{mode}_terms"], rtol=5e-6)
+    for pi in range(3):
+        np.testing.assert_allclose(aux["mu"][pi].detach().numpy(), ce[f"{mode}_mu{pi}"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(aux["recon_attrs"][pi].detach().numpy(), ce[f"{mode}_recon_attrs{pi}"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(aux["recon_image"][pi].detach().reshape(-1)[:256].numpy(), ce[f"{mode}_recon_image{pi}_head"], rtol=1e-4, atol=1e-5)
+    for k, g in grads.items():
+        np.testing.assert_allclose(g.reshape(-1)[:64].numpy(), ce[f"{mode}_grad_head/{k}"], rtol=2e-3, atol=2e-6)
+        # biases feeding a BatchNorm have a mathematically zero gradient (pure rounding noise ~1e-7): absolute floor
+        np.testing.assert_allclose(_digest(g)[2], ce[f"{mode}_grad_digest/{k}"][2], rtol=5e-4, atol=2e-6)
+    if mode == "train":
+        for k, v in bufs.items():
+            np.testing.assert_allclose(v.numpy(), ce[f"train_buffer/{k}"], rtol=1e-5, atol=1e-6)
