@@ -180,7 +180,8 @@ int mvae_col2im_k4(const float* cols, int64_t ld_cols, float* out, float* out_ac
  *                 reference's call order; a segment may appear twice when the reference evaluates a net twice)
  *   bn_eval_stats: mean/invstd from the running statistics (model.eval())
  *   bn_apply    : h = [swish](gamma * (x - mean) * invstd + beta)
- *   bn_bwd      : for the live segments [seg0, seg0+nseg): dx (through Swish and BN), dgamma += , dbeta +=           */
+ *   bn_bwd      : for the live segments [seg0, seg0+nseg): dx (through Swish and BN), dgamma += , dbeta += ;
+ *                 batch_stats = 0 differentiates the eval-mode (fixed statistics, affine) BatchNorm instead       */
 int mvae_bn_stats(const float* x, int64_t ldx, int S, int seg_rows, int C, double* acc, void* stream);
 int mvae_bn_finalize(const double* acc, int S, int seg_rows, int C, float eps, float momentum, float* mean, float* invstd,
                      float* running_mean, float* running_var, const int32_t* update_order, int n_updates, void* stream);
@@ -190,7 +191,7 @@ int mvae_bn_apply(const float* x, int64_t ldx, float* h, int64_t ldh, int rows, 
                   const float* invstd, const float* gamma, const float* beta, int swish_act, void* stream);
 int mvae_bn_bwd(const float* x, int64_t ldx, const float* dh, int64_t lddh, float* dx, int64_t lddx, int S, int seg_rows,
                 int C, int seg0, int nseg, const float* mean, const float* invstd, const float* gamma, const float* beta,
-                int swish_act, double* acc2, float* dgamma, float* dbeta, void* stream);
+                int swish_act, int batch_stats, double* acc2, float* dgamma, float* dbeta, void* stream);
 
 /* nn.Dropout(p) (celeba/model.py:91) on `copies` stacked calls over the same input x [x_rows, D]:
  *   y[k*x_rows + r] = x[r] * mask / (1 - p), fresh mask per copy (hash of (index, seed, *step_dev)) or mask_in.

@@ -65,7 +65,7 @@ SIGNATURES = {
     "mvae_bn_finalize": [_P, _I, _I, _I, _F, _F, _P, _P, _P, _P, C.POINTER(C.c_int32), _I, _P],
     "mvae_bn_eval_stats": [_P, _P, _I, _I, _F, _P, _P, _P],
     "mvae_bn_apply": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _P],
-    "mvae_bn_bwd": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    "mvae_bn_bwd": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P],
     "mvae_dropout_fwd": [_P, _I, _P, _P, _P, _I, _I, _F, _U64, _P, _P],
     "mvae_dropout_bwd": [_P, _P, _P, _I, _I, _I, _F, _P],
     "mvae_nchw_to_nhwc": [_P, _P, _I, _I, _I, _P],

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            int64_t lddx, int row_begin, int rows, int seg_rows, int C4,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           int act, const double* __restrict__ acc2) {
+                                                           int act, const double* __restrict__ acc2, int batch_stats) {
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<int64_t>(rows) * C4) return;
   const int r = row_begin + static_cast<int>(gid / C4);
@@ -197,9 +197,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
       const float sg = sigmoid_f(a);
       d *= sg * (1.0f + a * (1.0f - sg));
     }
-    const float m1 = static_cast<float>(acc2[(static_cast<int64_t>(s) * C + c + q) * 2]) * inv_n;
-    const float m2 = static_cast<float>(acc2[(static_cast<int64_t>(s) * C + c + q) * 2 + 1]) * inv_n;
-    out[q] = g * is * (d - m1 - xh * m2);
+    if (batch_stats) {
+      const float m1 = static_cast<float>(acc2[(static_cast<int64_t>(s) * C + c + q) * 2]) * inv_n;
+      const float m2 = static_cast<float>(acc2[(static_cast<int64_t>(s) * C + c + q) * 2 + 1]) * inv_n;
+      out[q] = g * is * (d - m1 - xh * m2);
+    } else {  // eval mode: fixed (running) statistics -> BatchNorm is an affine map
+      out[q] = g * is * d;
+    }
   }
   *reinterpret_cast<float4*>(dx + static_cast<int64_t>(r) * lddx + c) = make_float4(out[0], out[1], out[2], out[3]);
 }
@@ -309,8 +313,8 @@ extern "C" int mvae_bn_apply(const float* x, int64_t ldx, float* h, int64_t ldh,
 
 extern "C" int mvae_bn_bwd(const float* x, int64_t ldx, const float* dh, int64_t lddh, float* dx, int64_t lddx, int S,
                            int seg_rows, int C, int seg0, int nseg, const float* mean, const float* invstd,
-                           const float* gamma, const float* beta, int swish_act, double* acc2, float* dgamma, float* dbeta,
-                           void* stream) {
+                           const float* gamma, const float* beta, int swish_act, int batch_stats, double* acc2,
+                           float* dgamma, float* dbeta, void* stream) {
   if (!x || !dh || !dx || !acc2 || !dgamma || !dbeta || S < 1 || S > kMaxSeg || seg0 < 0 || nseg < 1 || seg0 + nseg > S ||
       (C & 3) || (ldx & 3) || (lddh & 3) || (lddx & 3))
     return set_error(MVAE_ERR_BAD_ARG, "bn_bwd: bad args");
@@ -323,7 +327,8 @@ extern "C" int mvae_bn_bwd(const float* x, int64_t ldx, const float* dh, int64_t
   const int rows = nseg * seg_rows;
   const int64_t n = static_cast<int64_t>(rows) * (C / 4);
   bn_bwd_apply_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ST(stream)>>>(
-      x, ldx, dh, lddh, dx, lddx, seg0 * seg_rows, rows, seg_rows, C / 4, mean, invstd, gamma, beta, swish_act, acc2);
+      x, ldx, dh, lddh, dx, lddx, seg0 * seg_rows, rows, seg_rows, C / 4, mean, invstd, gamma, beta, swish_act, acc2,
+      batch_stats);
   count_launch(3);
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;

@@ -205,11 +205,13 @@ def bn_forward(x, h, S, seg_rows, gamma, beta, mean, invstd, acc, running_mean=N
                "mvae_bn_apply")
 
 
-def bn_backward(x, dh, dx, S, seg_rows, seg0, nseg, gamma, beta, mean, invstd, acc2, dgamma, dbeta, act=True):
+def bn_backward(x, dh, dx, S, seg_rows, seg0, nseg, gamma, beta, mean, invstd, acc2, dgamma, dbeta, act=True,
+                training=True):
     Cch = x.shape[1]
     _lib.check(_lib.load().mvae_bn_bwd(x.data_ptr(), x.stride(0), dh.data_ptr(), dh.stride(0), dx.data_ptr(), dx.stride(0), S,
                                        seg_rows, Cch, seg0, nseg, mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                       beta.data_ptr(), int(act), acc2.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                       beta.data_ptr(), int(act), int(training), acc2.data_ptr(), dgamma.data_ptr(),
+                                       dbeta.data_ptr(),
                                        _stream()), "mvae_bn_bwd")
 
 

@@ -1,0 +1,85 @@
+"""GPU parity of the fused CelebA-flavour trainer (conv + BatchNorm + Dropout, PoE variant B) against the golden fixture
+produced by the unmodified reference (celeba/model.py, celeba/train.py) and the fp64 oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import celeba_oracle as CO
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+L = 100
+
+
+def _trainer(B, prec=1, **kw):
+    from multimodal_vae_public_b200.trainer_celeba import CelebAMVAETrainer
+    return CelebAMVAETrainer(n_latents=L, batch_size=B, precision=prec, use_graph=False, **kw)
+
+
+def test_names_and_state_dict_round_trip():
+    from multimodal_vae_public_b200 import trainer_celeba as TC
+    assert TC.celeba_param_shapes(L) == CO.celeba_param_shapes(L)
+    tr = _trainer(4)
+    st = CO.make_celeba_state(L, seed=5)
+    tr.load_state_dict(st)
+    sd = tr.state_dict()
+    assert list(sd.keys()) == [k for k, _ in CO.celeba_state_shapes(L)]
+    for k, v in st.items():
+        assert torch.equal(sd[k].cpu(), v), k
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_celeba_step_matches_reference_golden(mode):
+    ce = dict(np.load(os.path.join(G, "celeba_golden.npz")))
+    tr = _trainer(4)
+    tr.load_state_dict(CO.make_celeba_state(L, seed=0))
+    image = torch.from_numpy(ce["image"]); attrs = torch.from_numpy(ce["attrs"])
+    noise = torch.from_numpy(ce["noises"]); masks = torch.from_numpy(ce["drop_masks"])
+    train = mode == "train"
+    tr.step(image, attrs, annealing_factor=0.5, noise=noise if train else None, drop_masks=masks if train else None,
+            training=train, update=False)
+    ls = tr.losses()
+    for name, ref in zip(("joint", "image", "attrs"), ce[f"{mode}_terms"]):
+        assert abs(ls[name] - ref) <= 1e-5 * abs(ref) + 1e-4, (name, ls[name], ref)
+    grads = tr.export_grads()
+    for k, g in grads.items():
+        g = g.cpu()
+        head = ce[f"{mode}_grad_head/{k}"]
+        scale = max(np.abs(head).max(), ce[f"{mode}_grad_digest/{k}"][2] / np.sqrt(g.numel()), 1e-5)
+        # biases that feed a BatchNorm have a mathematically zero gradient: both sides hold ~1e-5 rounding noise there,
+        # hence the absolute floors (typical gradient norms are 1e-2 .. 1e+1)
+        assert np.abs(g.reshape(-1)[:64].numpy() - head).max() <= 2e-3 * scale + 1e-5, k
+        d = ce[f"{mode}_grad_digest/{k}"]
+        assert abs(g.double().norm().item() - d[2]) <= 5e-3 * d[2] + 5e-5, k
+    if train:
+        sd = tr.state_dict()
+        for k in sd:
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                np.testing.assert_allclose(sd[k].cpu().numpy(), ce[f"train_buffer/{k}"], rtol=2e-4, atol=2e-5)
+
+
+def test_celeba_step_matches_oracle_fp64():
+    B = 24
+    rs = np.random.RandomState(3)
+    image = torch.from_numpy(rs.uniform(0, 1, (B, 3, 64, 64)).astype(np.float32))
+    attrs = torch.from_numpy(rs.randint(0, 2, (B, 18)).astype(np.float32))
+    noise = torch.from_numpy(rs.standard_normal((3, B, L)).astype(np.float32))
+    masks = torch.from_numpy((rs.uniform(0, 1, (2, B, 512)) > 0.1).astype(np.float32))
+    st = CO.make_celeba_state(L, seed=2)
+    st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in st.items()}
+    loss, terms, grads, bufs, _ = CO.step_grads(st64, image.double(), attrs.double(), L, [n.double() for n in noise],
+                                                [m.double() for m in masks], 1.0, 10.0, 0.5, training=True)
+    tr = _trainer(B)
+    tr.load_state_dict(st)
+    got = tr.step(image, attrs, annealing_factor=0.5, noise=noise, drop_masks=masks, update=False)
+    assert abs(got - loss.item()) <= 5e-6 * abs(loss.item())
+    mine = tr.export_grads()
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for k, gref in grads.items():
+        err = (mine[k].cpu().double() - gref).abs().max().item() / max(gref.abs().max().item(), 1e-4 * gmax)
+        assert err <= 2e-3, (k, err)
+    sd = tr.state_dict()
+    for k, v in bufs.items():
+        np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=1e-4, atol=1e-5)
