@@ -59,6 +59,19 @@ def fashion_gemm_flops_per_sample(L: int = N_LATENTS) -> float:
     return 2.0 * (2 * fwd + dgrad)
 
 
+def celeba_gemm_flops_per_sample(L: int = 100) -> float:
+    """2*MAC of the GEMMs the CelebA-flavour trainer launches per sample: encoders once, decoders forward on the three
+    passes, backward on the two live passes of each decoder."""
+    enc_conv = 1024 * 32 * 48 + 256 * 64 * 512 + 64 * 128 * 1024 + 25 * 256 * 2048
+    enc_i = enc_conv + 6400 * 512 + 2 * 512 * 2 * L
+    enc_a = 20 * 512 + 512 * 512 + 512 * 2 * L
+    dec_i = L * 6400 + 25 * 2048 * 256 + 64 * 1024 * 128 + 256 * 512 * 64 + 1024 * 48 * 32
+    dec_a = L * 512 + 2 * 512 * 512 + 512 * 18
+    fwd = enc_i + enc_a + 3 * (dec_i + dec_a)
+    bwd = 2 * (enc_i + enc_a) - 1024 * 32 * 48 - 20 * 512 + 2 * 2 * (dec_i + dec_a)
+    return 2.0 * (fwd + bwd)
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -188,16 +201,28 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         else:
             dist.init_process_group(backend, timeout=datetime.timedelta(seconds=90))
     strong = args.scaling == "strong"
-    b_local = BATCH // world if strong else BATCH
+    batch = 1024 if args.workload == "celeba" else BATCH
+    b_local = batch // world if strong else batch
     b_global = b_local * world
     prec = ops.PREC_3XTF32 if args.precision == "3xtf32" else ops.PREC_TF32
+    celeba = args.workload == "celeba"
     if args.workload == "fashion":
         from multimodal_vae_public_b200.trainer_fashion import FashionMVAETrainer as Trainer
+    elif celeba:
+        from multimodal_vae_public_b200.trainer_celeba import CelebAMVAETrainer as Trainer
     else:
         Trainer = MnistMVAETrainer
-    tr = Trainer(N_LATENTS, b_local, device=dev, lr=1e-3, lambda_image=LAMBDA_IMAGE, lambda_text=LAMBDA_TEXT,
-                 precision=prec, world_size=world, rank=rank, seed=0, use_graph=not args.no_graph)
-    host = synth_batches(POOL, b_local, seed=100 + rank)
+    if celeba:
+        tr = Trainer(100, b_local, device=dev, lr=1e-4, lambda_image=1.0, lambda_attrs=10.0, precision=prec,
+                     world_size=world, rank=rank, seed=0, use_graph=not args.no_graph)
+        g = torch.Generator().manual_seed(100 + rank)
+        host = [(torch.rand(b_local, 3, 64, 64, generator=g), torch.randint(0, 2, (b_local, 18), generator=g).float())
+                for _ in range(4)]
+    else:
+        tr = Trainer(N_LATENTS, b_local, device=dev, lr=1e-3, lambda_image=LAMBDA_IMAGE, lambda_text=LAMBDA_TEXT,
+                     precision=prec, world_size=world, rank=rank, seed=0, use_graph=not args.no_graph)
+        host = synth_batches(POOL, b_local, seed=100 + rank)
+    npool = len(host)
     host = [(im.pin_memory(), tx.pin_memory()) for im, tx in host]
     pool = [(im.to(dev), tx.to(dev)) for im, tx in host]
 
@@ -220,7 +245,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         return ms.item()
 
     def step_resident(i):
-        im, tx = pool[i % POOL]
+        im, tx = pool[i % npool]
         tr.step(im, tx, annealing_factor=annealing(i), sync=False)
 
     def log(msg):
@@ -232,7 +257,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     def step_e2e(i):
         # public host-fed API: pinned host batch -> (copy stream) -> device, step, loss read back on the host every
         # call (one step lagged, as in any asynchronous training loop); flush() at the end of the timed region
-        im, tx = host[i % POOL]
+        im, tx = host[i % npool]
+        if celeba:   # the double-buffered host path is implemented for the MNIST-shape trainers only
+            e2e_losses.append(tr.step(im, tx, annealing_factor=annealing(i), sync=True))
+            return
         v = tr.step_pipelined(im, tx, annealing_factor=annealing(i))
         if v is not None:
             e2e_losses.append(v)
@@ -288,21 +316,28 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "dtype": "fp32 (3xTF32 tensor-core split products, fp32 accumulate)" if prec == ops.PREC_3XTF32
                      else "tf32 (fp32 storage/accumulate)",
             "data": "synthetic",
-            "config": {"workload": f"{'FashionMNIST (conv enc/dec)' if args.workload == 'fashion' else 'MNIST'} MVAE "
-                                   f"(image 28x28x1 + label one-of-10), n_latents={N_LATENTS}, "
+            "config": {"workload": (f"CelebA MVAE (image 64x64x3 + 18 attrs, conv+BatchNorm+Dropout), n_latents=100, "
+                                    if celeba else
+                                    f"{'FashionMNIST (conv enc/dec)' if args.workload == 'fashion' else 'MNIST'} MVAE "
+                                    f"(image 28x28x1 + label one-of-10), n_latents={N_LATENTS}, ") +
                                    f"global batch {b_global} ({b_local}/GPU), full train step "
                                    "(3 passes + ELBO + backward + Adam), BASELINE.json "
-                                   f"{'configs[2]' if args.workload == 'fashion' else 'configs[1]'}",
+                                   f"{ {'fashion': 'configs[2]', 'celeba': 'configs[3]'}.get(args.workload, 'configs[1]') }",
                        "parallelism": f"dp{world}", "global_batch": b_global,
-                       "l2": f"rotating pool of {POOL} distinct input batches ({POOL * b_local * 3144 / 1e6:.0f} MB) and a "
-                             f"~{working_set_mb(b_local):.0f} MB per-step working set, both larger than the 126 MB L2",
+                       "l2": (f"rotating pool of {npool} distinct input batches and a multi-GB per-step working set "
+                              "(im2col matrices), larger than the 126 MB L2" if args.workload != "mnist" else
+                              f"rotating pool of {POOL} distinct input batches ({POOL * b_local * 3144 / 1e6:.0f} MB) and a "
+                              f"~{working_set_mb(b_local):.0f} MB per-step working set, both larger than the 126 MB L2"),
                        "cuda_graph": tr.use_graph, "loss_last": loss},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": b_local * (784 * 4 + 8) + 4, "d2h_bytes_per_step": 16,
+                    "h2d_bytes_per_step": (b_local * (12288 + 18) * 4 + 4) if celeba else (b_local * (784 * 4 + 8) + 4),
+                    "d2h_bytes_per_step": 16,
                     "losses_read": len(e2e_losses),
-                    "note": "trainer.step_pipelined(pinned host image, pinned host labels): H2D of batch i+1 on a copy stream "
-                            "overlaps step i; the loss is copied D2H and read on the host every step (one step lagged)"},
+                    "note": ("trainer.step(pinned host image NCHW, pinned host attrs): H2D + NCHW->NHWC staging + step + loss "
+                             "read back synchronously every step" if celeba else
+                             "trainer.step_pipelined(pinned host image, pinned host labels): H2D of batch i+1 on a copy stream "
+                             "overlaps step i; the loss is copied D2H and read on the host every step (one step lagged)")},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 kind::tf32, all GEMM launches of a step)",
                          "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
@@ -344,7 +379,8 @@ def measure_rooflines(tr, dev, prec, args):
     from multimodal_vae_public_b200 import ops
     st = tr._stream
     names = ["gemm_batch", "linear_fwd", "bce_logits_fwd_bwd", "ce_fwd_bwd", "poe_fwd", "poe_bwd", "colsum_accumulate",
-             "embedding_swish_fwd", "embedding_swish_bwd", "adam_flat", "elbo_finalize"]
+             "embedding_swish_fwd", "embedding_swish_bwd", "adam_flat", "elbo_finalize", "im2col_k4s2p1", "col2im_k4s2p1",
+             "im2col_k4", "col2im_k4", "bn_forward", "bn_backward", "dropout_fwd", "dropout_bwd", "nchw_to_nhwc", "swish_bwd"]
     records = []
     orig = {n: getattr(ops, n) for n in names}
 
@@ -374,8 +410,8 @@ def measure_rooflines(tr, dev, prec, args):
     gemm_ms = per.get("gemm_batch", 0.0) + per.get("linear_fwd", 0.0)
     gemm_launches = (cnt.get("gemm_batch", 0) + cnt.get("linear_fwd", 0)) // reps
     out = {"gemm": {"ms_per_step": gemm_ms, "launches": gemm_launches,
-                    "algorithmic_flops_per_step": (executed_gemm_flops_per_sample(tr.L) if args.workload == "mnist"
-                                           else fashion_gemm_flops_per_sample(tr.L)) * tr.B},
+                    "algorithmic_flops_per_step": {"mnist": executed_gemm_flops_per_sample, "fashion": fashion_gemm_flops_per_sample,
+                                           "celeba": celeba_gemm_flops_per_sample}[args.workload](tr.L) * tr.B},
            "breakdown": {k: round(v, 5) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
     # HBM roofline of the fused reconstruction-loss kernel at roofline size (inputs >> L2), L2 not reusable
     R, D = 65536, 784
@@ -412,8 +448,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
-    ap.add_argument("--workload", choices=["mnist", "fashion"], default="mnist",
-                    help="mnist = BASELINE.json configs[1] (default, the headline); fashion = conv flavour (configs[2])")
+    ap.add_argument("--workload", choices=["mnist", "fashion", "celeba"], default="mnist",
+                    help="mnist = BASELINE.json configs[1] (default, the headline); fashion = conv flavour (configs[2]); "
+                         "celeba = conv+BatchNorm flavour, global batch 1024 (configs[3])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/mvae_b200.h"
 #include "common.h"
@@ -347,8 +348,8 @@ __global__ void __launch_bounds__(256) kl_kernel(const float* __restrict__ mu, c
 // in a register and issues ONE double atomic per (block, segment): with one slab per block the same-address
 // atomics serialised in L2 and capped the kernel at 43 % of HBM bandwidth at roofline size.  32-bit index math
 // keeps the kernel at 4 blocks/SM.
-constexpr int kBceUnroll = 4;
-__global__ void __launch_bounds__(256, 4) bce_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ t,
+template <int kBceUnroll>
+__global__ void __launch_bounds__(256, kBceUnroll == 4 ? 4 : 2) bce_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ t,
                                                      int ldt, int t_rows, float* dx, int lddx, int R, int D4,
                                                      float scale, double* loss_acc, int seg_rows, float* loss_elem,
                                                      int ldl, int slabs) {
@@ -759,15 +760,21 @@ extern "C" int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float*
   if (n4 >= (int64_t(1) << 31) || ldx >= (int64_t(1) << 31) || ldt >= (int64_t(1) << 31) || lddx >= (int64_t(1) << 31) ||
       ldl >= (int64_t(1) << 31))
     return set_error(MVAE_ERR_UNSUPPORTED, "bce: tensor too large for 32-bit indexing");
-  const int per_block = 256 * kBceUnroll;
+  static const int unroll = getenv("MVAE_BCE_UNROLL") ? atoi(getenv("MVAE_BCE_UNROLL")) : 4;
+  const int per_block = 256 * (unroll == 8 ? 8 : 4);
   const int64_t nslabs = (n4 + per_block - 1) / per_block;
   const int sms = mvae_device_sm_count() > 0 ? mvae_device_sm_count() : 148;
   int slabs = static_cast<int>(nslabs / (static_cast<int64_t>(sms) * 8));   // aim for >= 8 blocks per SM
   slabs = slabs < 1 ? 1 : (slabs > 16 ? 16 : slabs);
   const int64_t blocks = (nslabs + slabs - 1) / slabs;
-  bce_kernel<<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<int>(ldx), t, static_cast<int>(ldt), t_rows, dx, static_cast<int>(lddx), R, D / 4, scale, loss_acc,
-      seg_rows, loss_elem, static_cast<int>(ldl), slabs);
+  if (unroll == 8)
+    bce_kernel<8><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<int>(ldx), t, static_cast<int>(ldt), t_rows, dx, static_cast<int>(lddx), R, D / 4, scale, loss_acc,
+        seg_rows, loss_elem, static_cast<int>(ldl), slabs);
+  else
+    bce_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<int>(ldx), t, static_cast<int>(ldt), t_rows, dx, static_cast<int>(lddx), R, D / 4, scale, loss_acc,
+        seg_rows, loss_elem, static_cast<int>(ldl), slabs);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
