@@ -111,31 +111,35 @@ class _Conv4x4s2Fn(Function):
     NHWC internally: im2col kernel + tcgen05 GEMM; backward = GEMM dgrad + col2im gather, GEMM wgrad."""
 
     @staticmethod
-    def forward(ctx, x, w, act: bool, prec: int):
+    def forward(ctx, x, w, act: bool, prec: int, stride: int = 2, pad: int = 1, nhwc: bool = False):
         _need_cuda(x, w)
-        B, Cin, H, W = x.shape
+        if nhwc:
+            B, H, W, Cin = x.shape
+            xh = x.detach().to(torch.float32).contiguous()
+        else:
+            B, Cin, H, W = x.shape
+            xh = x.detach().to(torch.float32).permute(0, 2, 3, 1).contiguous()
         Cout = w.shape[0]
-        xh = x.detach().to(torch.float32).permute(0, 2, 3, 1).contiguous()
-        OH, OW = H // 2, W // 2
+        OH, OW = (H + 2 * pad - 4) // stride + 1, (W + 2 * pad - 4) // stride + 1
         cols = _padded(B * OH * OW, 16 * Cin, xh)
-        ops.im2col_k4s2p1(xh, cols, B, H, W, Cin)
+        ops.im2col_k4(xh, cols, B, H, W, Cin, stride, pad)
         wp = _as_operand(_conv_weight_cols(w.detach().to(torch.float32)))
         a = _padded(B * OH * OW, Cout, xh)
         h = _padded(B * OH * OW, Cout, xh) if act else None
         ops.gemm_batch([ops.gemm_desc(cols, wp, a, B * OH * OW, Cout, 16 * Cin, out2=h,
                                       epilogue=ops.EPI_BIAS_SWISH if act else ops.EPI_STORE)], prec)
         ctx.save_for_backward(cols, wp, a if act else None)
-        ctx.meta = (B, Cin, H, W, Cout, act, prec)
-        out = h if act else a
-        return out.reshape(B, OH, OW, Cout).permute(0, 3, 1, 2)
+        ctx.meta = (B, Cin, H, W, Cout, act, prec, stride, pad, nhwc, OH, OW)
+        out = (h if act else a).reshape(B, OH, OW, Cout)
+        return out if nhwc else out.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
         cols, wp, a = ctx.saved_tensors
-        B, Cin, H, W, Cout, act, prec = ctx.meta
-        OH, OW = H // 2, W // 2
+        B, Cin, H, W, Cout, act, prec, stride, pad, nhwc, OH, OW = ctx.meta
         M = B * OH * OW
-        d = _as_operand(dy.to(torch.float32).permute(0, 2, 3, 1).reshape(M, Cout))
+        dyh = dy.to(torch.float32) if nhwc else dy.to(torch.float32).permute(0, 2, 3, 1)
+        d = _as_operand(dyh.reshape(M, Cout))
         if act:
             da = _padded(M, Cout, d)
             if d.stride(0) == Cout and a.stride(0) == Cout:
@@ -154,9 +158,9 @@ class _Conv4x4s2Fn(Function):
             dcols = _padded(M, 16 * Cin, d)
             ops.gemm_batch([ops.gemm_desc(d, wp, dcols, M, 16 * Cin, Cout, b_mn=True)], prec)
             dxh = torch.empty(B, H, W, Cin, dtype=torch.float32, device=d.device)
-            ops.col2im_k4s2p1(dcols, dxh, B, OH, OW, Cin)
-            dx = dxh.permute(0, 3, 1, 2)
-        return dx, dw, None, None
+            ops.col2im_k4(dcols, dxh, B, OH, OW, Cin, stride, pad)
+            dx = dxh if nhwc else dxh.permute(0, 3, 1, 2)
+        return dx, dw, None, None, None, None, None
 
 
 class _ConvT4x4s2Fn(Function):
@@ -164,33 +168,39 @@ class _ConvT4x4s2Fn(Function):
     fused Swish: tcgen05 GEMM + col2im gather; backward = im2col + GEMM dgrad / wgrad."""
 
     @staticmethod
-    def forward(ctx, x, w, act: bool, prec: int):
+    def forward(ctx, x, w, act: bool, prec: int, stride: int = 2, pad: int = 1, nhwc: bool = False):
         _need_cuda(x, w)
-        B, Cin, IH, IW = x.shape
+        if nhwc:
+            B, IH, IW, Cin = x.shape
+            xh = _as_operand(x.detach().to(torch.float32).reshape(B * IH * IW, Cin))
+        else:
+            B, Cin, IH, IW = x.shape
+            xh = _as_operand(x.detach().to(torch.float32).permute(0, 2, 3, 1).reshape(B * IH * IW, Cin))
         Cout = w.shape[1]
-        xh = _as_operand(x.detach().to(torch.float32).permute(0, 2, 3, 1).reshape(B * IH * IW, Cin))
+        OH, OW = (IH - 1) * stride - 2 * pad + 4, (IW - 1) * stride - 2 * pad + 4
         wp = _as_operand(_convT_weight_cols(w.detach().to(torch.float32)))
         cols = _padded(B * IH * IW, 16 * Cout, xh)
         ops.gemm_batch([ops.gemm_desc(xh, wp, cols, B * IH * IW, 16 * Cout, Cin)], prec)
-        a = torch.empty(B, 2 * IH, 2 * IW, Cout, dtype=torch.float32, device=xh.device)
+        a = torch.empty(B, OH, OW, Cout, dtype=torch.float32, device=xh.device)
         h = torch.empty_like(a) if act else None
-        ops.col2im_k4s2p1(cols, a, B, IH, IW, Cout, out_act=h)
+        ops.col2im_k4(cols, a, B, IH, IW, Cout, stride, pad, out_act=h)
         ctx.save_for_backward(xh, wp, a if act else None)
-        ctx.meta = (B, Cin, IH, IW, Cout, act, prec)
-        return (h if act else a).permute(0, 3, 1, 2)
+        ctx.meta = (B, Cin, IH, IW, Cout, act, prec, stride, pad, nhwc, OH, OW)
+        out = h if act else a
+        return out if nhwc else out.permute(0, 3, 1, 2)
 
     @staticmethod
     def backward(ctx, dy):
         xh, wp, a = ctx.saved_tensors
-        B, Cin, IH, IW, Cout, act, prec = ctx.meta
+        B, Cin, IH, IW, Cout, act, prec, stride, pad, nhwc, OH, OW = ctx.meta
         M = B * IH * IW
-        d = dy.to(torch.float32).permute(0, 2, 3, 1).contiguous()
+        d = (dy.to(torch.float32) if nhwc else dy.to(torch.float32).permute(0, 2, 3, 1)).contiguous()
         if act:
             da = torch.empty_like(d)
             ops.swish_bwd(a, d, da)
             d = da
         dcols = _padded(M, 16 * Cout, d)
-        ops.im2col_k4s2p1(d, dcols, B, 2 * IH, 2 * IW, Cout)
+        ops.im2col_k4(d, dcols, B, OH, OW, Cout, stride, pad)
         dx = dw = None
         if ctx.needs_input_grad[1]:
             dwp = _padded(16 * Cout, Cin, d, zero=True)
@@ -200,8 +210,9 @@ class _ConvT4x4s2Fn(Function):
         if ctx.needs_input_grad[0]:
             dxh = _padded(M, Cin, d)
             ops.gemm_batch([ops.gemm_desc(dcols, wp, dxh, M, Cin, 16 * Cout, b_mn=True)], prec)
-            dx = dxh.reshape(B, IH, IW, Cin).permute(0, 3, 1, 2)
-        return dx, dw, None, None
+            dx = dxh.reshape(B, IH, IW, Cin)
+            dx = dx if nhwc else dx.permute(0, 3, 1, 2)
+        return dx, dw, None, None, None, None, None
 
 
 def conv4x4s2(x, w, swish_act: bool = False, precision: int = DEFAULT_PRECISION):
@@ -210,6 +221,87 @@ def conv4x4s2(x, w, swish_act: bool = False, precision: int = DEFAULT_PRECISION)
 
 def conv_transpose4x4s2(x, w, swish_act: bool = False, precision: int = DEFAULT_PRECISION):
     return _ConvT4x4s2Fn.apply(x, w, swish_act, precision)
+
+
+def conv4x4(x, w, stride: int, pad: int, swish_act: bool = False, nhwc: bool = False, precision: int = DEFAULT_PRECISION):
+    """nn.Conv2d(Cin, Cout, 4, stride, pad, bias=False); NCHW in/out, or NHWC in/out with ``nhwc=True``."""
+    return _Conv4x4s2Fn.apply(x, w, swish_act, precision, stride, pad, nhwc)
+
+
+def conv_transpose4x4(x, w, stride: int, pad: int, swish_act: bool = False, nhwc: bool = False,
+                      precision: int = DEFAULT_PRECISION):
+    """nn.ConvTranspose2d(Cin, Cout, 4, stride, pad, bias=False); NCHW in/out, or NHWC in/out with ``nhwc=True``."""
+    return _ConvT4x4s2Fn.apply(x, w, swish_act, precision, stride, pad, nhwc)
+
+
+class _BatchNormActFn(Function):
+    """BatchNorm{1,2}d (train: batch statistics + running-stat update, eval: running statistics) + optional Swish over
+    channels-last activations [..., C] (celeba/model.py:80,149, ...)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, training: bool, act: bool):
+        _need_cuda(x, weight, bias)
+        Cc = x.shape[-1]
+        x2 = x.detach().to(torch.float32).reshape(-1, Cc).contiguous()
+        R = x2.shape[0]
+        h = torch.empty_like(x2)
+        mean = torch.empty(1, Cc, dtype=torch.float32, device=x2.device); invstd = torch.empty_like(mean)
+        acc = torch.empty(2 * Cc, dtype=torch.float64, device=x2.device)
+        ops.bn_forward(x2, h, 1, R, weight.detach(), bias.detach(), mean, invstd, acc, running_mean, running_var,
+                       update_order=(0,), training=training, act=act)
+        ctx.save_for_backward(x2, weight.detach(), bias.detach(), mean, invstd)
+        ctx.meta = (x.shape, act, training)
+        return h.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dh):
+        x2, w, b, mean, invstd = ctx.saved_tensors
+        shape, act, training = ctx.meta
+        Cc = x2.shape[1]
+        d = dh.to(torch.float32).reshape(-1, Cc).contiguous()
+        dx = torch.empty_like(x2)
+        dg = torch.zeros(Cc, dtype=torch.float32, device=x2.device); db = torch.zeros_like(dg)
+        acc = torch.empty(2 * Cc, dtype=torch.float64, device=x2.device)
+        ops.bn_backward(x2, d, dx, 1, x2.shape[0], 0, 1, w, b, mean, invstd, acc, dg, db, act=act, training=training)
+        return dx.reshape(shape), dg, db, None, None, None, None
+
+
+def batch_norm_act(x, weight, bias, running_mean, running_var, training: bool, swish_act: bool = True):
+    """x channels-last [..., C]."""
+    return _BatchNormActFn.apply(x, weight, bias, running_mean, running_var, training, swish_act)
+
+
+class _DropoutFn(Function):
+    """nn.Dropout(p) in training mode (celeba/model.py:91)."""
+
+    @staticmethod
+    def forward(ctx, x, p: float, seed: int):
+        _need_cuda(x)
+        x2 = x.detach().to(torch.float32).reshape(x.shape[0], -1).contiguous()
+        y = torch.empty_like(x2); mask = torch.empty_like(x2)
+        ops.dropout_fwd(x2, y, 1, p, mask_out=mask, seed=seed)
+        ctx.save_for_backward(mask)
+        ctx.p = p
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        d = dy.to(torch.float32).reshape(mask.shape).contiguous()
+        dx = torch.empty_like(d)
+        ops.dropout_bwd(d, mask, dx, 1, ctx.p)
+        return dx.reshape(dy.shape), None, None
+
+
+_dropout_counter = [0]
+
+
+def dropout(x, p: float, training: bool):
+    if not training or p == 0.0:
+        return x
+    _dropout_counter[0] += 1
+    seed = (int(torch.initial_seed()) * 1000003 + _dropout_counter[0]) & 0x7FFFFFFF
+    return _DropoutFn.apply(x, p, seed)
 
 
 class _SwishFn(Function):
@@ -350,9 +442,6 @@ class _BceSumFn(Function):
             raise ValueError("Target size ({}) must be the same as input size ({})".format(t.size(), x.size()))
         x2 = _as_operand(x.detach().reshape(x.shape[0], -1) if x.dim() > 1 else x.detach().reshape(1, -1))
         t2 = _as_operand(t.detach().reshape(x2.shape))
-        D = x2.shape[1]
-        if D % 4:
-            raise _lib.MvaeError("bce: inner size must be a multiple of 4")
         acc = torch.zeros(1, dtype=torch.float64, device=x.device)
         dx = torch.empty(x2.shape, dtype=torch.float32, device=x.device)
         ops.bce_logits_fwd_bwd(x2, t2, dx, 1.0, acc)

@@ -148,3 +148,51 @@ def test_fashion_modules_match_oracle():
         err = (v.grad.cpu().double() - g).abs().max().item() / max(g.abs().max().item(), 1e-12)
         assert err < 5e-4, (k, err)
     assert FT.annealing_factor(1, 0, 600, 200) == pytest.approx(601.0 / (200 * 600))
+
+
+def test_celeba_modules_match_oracle():
+    """Drop-in celeba/model.py surface: eval-mode three-pass objective + gradients, and the train-mode BatchNorm path
+    (batch statistics, running-stat updates) of the encoders, against the oracle."""
+    from oracle import celeba_oracle as CO
+    from multimodal_vae_public_b200.celeba import model as CM, train as CT
+    L, B = 100, 6
+    st = CO.make_celeba_state(L, seed=6)
+    m = CM.MVAE(L)
+    assert list(m.state_dict().keys()) == [k for k, _ in CO.celeba_state_shapes(L)]
+    m.load_state_dict(st)
+    m = m.cuda().eval()
+    rs = np.random.RandomState(10)
+    image = torch.from_numpy(rs.uniform(0, 1, (B, 3, 64, 64)).astype(np.float32))
+    attrs = torch.from_numpy(rs.randint(0, 2, (B, 18)).astype(np.float32))
+    ic, ac = image.cuda(), attrs.cuda()
+    outs = [m(ic, ac), m(ic), m(attrs=ac)]
+    assert outs[0][0].shape == (B, 3, 64, 64) and outs[0][1].shape == (B, 18)
+    j = CT.elbo_loss(outs[0][0], ic, outs[0][1], ac, outs[0][2], outs[0][3], lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+    i = CT.elbo_loss(outs[1][0], ic, None, None, outs[1][2], outs[1][3], lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+    a = CT.elbo_loss(None, None, outs[2][1], ac, outs[2][2], outs[2][3], lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+    (j + i + a).backward()
+    st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in st.items()}
+    ref, terms, grads, _, aux = CO.step_grads(st64, image.double(), attrs.double(), L, [None] * 3, [None] * 2, 1.0, 10.0, 0.5,
+                                              training=False)
+    assert abs((j + i + a).item() - ref.item()) <= 1e-5 * abs(ref.item())
+    np.testing.assert_allclose(outs[0][0].detach().cpu().numpy(), aux["recon_image"][0].detach().numpy(), rtol=2e-3, atol=2e-4)
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for k, v in m.named_parameters():
+        g = grads[k]
+        err = (v.grad.cpu().double() - g).abs().max().item() / max(g.abs().max().item(), 1e-4 * gmax)
+        assert err < 2e-3, (k, err)
+    # ---- train mode: BatchNorm batch statistics + running-stat update (Dropout disabled: p = 0)
+    m.zero_grad(); m.train()
+    m.image_encoder.classifier[2].p = 0.0
+    mu_i, lv_i = m.image_encoder(ic)
+    mu_a, lv_a = m.attrs_encoder(ac)
+    st_ref = {k: (v.double().clone() if v.dtype.is_floating_point else v.clone()) for k, v in st.items()}
+    keep = torch.full((B, 512), 0.9, dtype=torch.float64)          # h * 0.9 / 0.9 == h in the oracle
+    rmu_i, rlv_i = CO.image_encoder(st_ref, image.double(), L, True, keep)
+    rmu_a, rlv_a = CO.attrs_encoder(st_ref, attrs.double(), L, True)
+    np.testing.assert_allclose(mu_i.detach().cpu().numpy(), rmu_i.numpy(), rtol=2e-3, atol=2e-4)
+    np.testing.assert_allclose(lv_a.detach().cpu().numpy(), rlv_a.numpy(), rtol=2e-3, atol=2e-4)
+    sd = m.state_dict()
+    for k in ("image_encoder.features.6.running_mean", "image_encoder.features.9.running_var", "attrs_encoder.net.4.running_var"):
+        np.testing.assert_allclose(sd[k].cpu().numpy(), st_ref[k].numpy(), rtol=1e-4, atol=1e-5)
+    assert int(sd["image_encoder.features.3.num_batches_tracked"]) == 1
