@@ -193,6 +193,58 @@ def main():
     cout["noises"] = torch.stack([n1, n2, n3]).numpy(); cout["drop_masks"] = torch.stack([m1, m2]).numpy()
     np.savez_compressed(os.path.join(HERE, "celeba_golden.npz"), **cout)
 
+    # ---------------------------------------------------------------- celeba19 (19 experts, sampled ELBO terms)
+    from oracle import celeba19_oracle as O19
+    import tqdm as _tq, torchvision as _tv  # noqa: F401  (real modules must be imported before the stubs below)
+    ref19_m = load_ref("celeba19", "model", "ref_celeba19_model", {"datasets": cds})
+    ref19_t = load_ref("celeba19", "train", "ref_celeba19_train", {"datasets": cds, "model": ref19_m})
+    L9, B9 = 100, 3
+    st9 = O19.make_celeba19_state(L9, seed=0)
+    m9 = ref19_m.MVAE(L9)
+    assert list(m9.state_dict().keys()) == [k for k, _ in O19.celeba19_state_shapes(L9)]
+    m9.load_state_dict(st9)
+    rs = np.random.RandomState(1357)
+    image9 = torch.from_numpy(rs.uniform(0, 1, size=(B9, 3, 64, 64)).astype(np.float32))
+    attrs9 = torch.from_numpy(rs.randint(0, 2, size=(B9, 18)).astype(np.float32))
+    combos = np.zeros((2, 19), dtype=bool); combos[0, [0, 3, 6, 12]] = True; combos[1, [1, 8]] = True
+    passes = O19.pass_list(combos)
+    torch.manual_seed(80)
+    noises9, masks9 = [], []
+    for present, _ in passes:
+        if present[0]:
+            masks9.append(torch.empty(B9, 512).bernoulli_(0.9))
+        noises9.append(torch.empty(B9, L9).normal_())
+    m9.train(True); m9.zero_grad(); torch.manual_seed(80)
+    alist = ref19_t.tensor_2d_to_list(attrs9)
+    total = 0; terms9 = []
+    recon_image, recon_attrs, mu, logvar = m9(image9, alist)
+    t = ref19_t.elbo_loss([recon_image] + recon_attrs, [image9] + alist, mu, logvar, lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+    total = total + t; terms9.append(t.item())
+    recon_image, _, mu, logvar = m9(image=image9)
+    t = ref19_t.elbo_loss([recon_image], [image9], mu, logvar, lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+    total = total + t; terms9.append(t.item())
+    for ix in range(18):
+        _, recon_attrs, mu, logvar = m9(attrs=[alist[k] if k == ix else None for k in range(18)])
+        t = ref19_t.elbo_loss([recon_attrs[ix]], [alist[ix]], mu, logvar, annealing_factor=0.5)
+        total = total + t; terms9.append(t.item())
+    for combo in combos:
+        ac = combo[1:]
+        recon_image, recon_attrs, mu, logvar = m9(image=image9 if combo[0] else None, attrs=[alist[ix] if ac[ix] else None for ix in range(18)])
+        if combo[0]:
+            t = ref19_t.elbo_loss([recon_image] + [recon_attrs[ix] for ix in range(18) if ac[ix]], [image9] + [alist[ix] for ix in range(18) if ac[ix]], mu, logvar, annealing_factor=0.5)
+        else:
+            t = ref19_t.elbo_loss([recon_attrs[ix] for ix in range(18) if ac[ix]], [alist[ix] for ix in range(18) if ac[ix]], mu, logvar, annealing_factor=0.5)
+        total = total + t; terms9.append(t.item())
+    total.backward()
+    o9 = {"image": image9.numpy(), "attrs": attrs9.numpy(), "combos": combos, "noises": torch.stack(noises9).numpy(),
+          "drop_masks": torch.stack(masks9).numpy(), "terms": np.array(terms9, np.float64), "total": np.float64(total.item())}
+    for k, v in m9.named_parameters():
+        o9[f"grad_digest/{k}"] = tensor_digest(v.grad); o9[f"grad_head/{k}"] = v.grad.detach().reshape(-1)[:32].numpy().copy()
+    for k, v in m9.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            o9[f"buffer/{k}"] = v.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "celeba19_golden.npz"), **o9)
+
     # ------------------------------------------------------- element-wise KATs
     ew = {}
     poeA = ref_model.ProductOfExperts()

@@ -197,3 +197,35 @@ def test_celeba_step_matches_reference(mode):
     if mode == "train":
         for k, v in bufs.items():
             np.testing.assert_allclose(v.numpy(), ce[f"train_buffer/{k}"], rtol=1e-5, atol=1e-6)
+
+
+def test_celeba19_step_matches_reference():
+    """CelebA-19 (19 experts, 22 ELBO terms incl. two sampled combinations): oracle vs the unmodified reference."""
+    from oracle import celeba19_oracle as O19
+    c9 = dict(np.load(os.path.join(G, "celeba19_golden.npz")))
+    L = 100
+    st = O19.make_celeba19_state(L, seed=0)
+    image = torch.from_numpy(c9["image"]); attrs = torch.from_numpy(c9["attrs"])
+    noises = [torch.from_numpy(n) for n in c9["noises"]]; masks = [torch.from_numpy(m) for m in c9["drop_masks"]]
+    total, terms, grads, bufs = O19.step_grads(st, image, attrs, L, noises, masks, c9["combos"], 1.0, 10.0, 0.5, training=True)
+    np.testing.assert_allclose([t.item() for t in terms], c9["terms"], rtol=5e-6)
+    assert abs(total.item() - c9["total"]) <= 5e-6 * abs(c9["total"])
+    for k, g in grads.items():
+        np.testing.assert_allclose(g.reshape(-1)[:32].numpy(), c9[f"grad_head/{k}"], rtol=3e-3, atol=3e-6)
+        np.testing.assert_allclose(_digest(g)[2], c9[f"grad_digest/{k}"][2], rtol=1e-3, atol=1e-5)
+    for k, v in bufs.items():
+        np.testing.assert_allclose(v.numpy(), c9[f"buffer/{k}"], rtol=1e-5, atol=1e-6)
+
+
+def test_celeba19_sampler_distribution_and_unranking():
+    from itertools import combinations
+    from oracle import celeba19_oracle as O19
+    for n, k in ((6, 3), (19, 2), (7, 6)):
+        all_c = list(combinations(range(n), k))
+        for idx in (0, 1, len(all_c) // 2, len(all_c) - 1):
+            assert tuple(O19.unrank_combination(n, k, idx)) == all_c[idx]
+    rng = np.random.RandomState(0)
+    rows = O19.sample_combinations_fast(19, 64, rng)
+    assert rows.shape == (64, 19) and rows.dtype == bool
+    sizes = rows.sum(1)
+    assert sizes.min() >= 2 and sizes.max() <= 18
