@@ -96,7 +96,7 @@ int mvae_embedding_swish_bwd(const float* table, const int64_t* idx, const float
 
 /* Fused ProductOfExperts + reparametrize + KL for P "passes" (modality subsets) over E encoder
  * experts; the N(0,1) prior expert (prior_expert(), mnist/model.py:172-185) is implicit.
- *   mu_e[e], lv_e[e] : [B, L] with row stride ld_e  (e < E <= 20)
+ *   mu_e[e], lv_e[e] : [B, L] with row stride ld_e  (e < E <= 24)
  *   pass_masks[p]    : bit e set => expert e present in pass p      (p < P <= 32)
  *   z                : [P*B, L] row stride ldz, pass p at rows [p*B, (p+1)*B)
  *   noise            : [P*B, L] N(0,1) draws or NULL.  NULL with training=1 => Philox(seed, offset)

@@ -17,7 +17,7 @@
 namespace mvae {
 namespace {
 
-constexpr int kMaxExperts = 20;
+constexpr int kMaxExperts = 24;
 constexpr int kMaxPasses = 32;
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -17,7 +17,7 @@ namespace mvae {
 namespace {
 
 constexpr int kRowsPerBlock = 128;
-constexpr int kMaxSeg = 8;
+constexpr int kMaxSeg = 32;
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
