@@ -196,3 +196,49 @@ def test_celeba_modules_match_oracle():
     for k in ("image_encoder.features.6.running_mean", "image_encoder.features.9.running_var", "attrs_encoder.net.4.running_var"):
         np.testing.assert_allclose(sd[k].cpu().numpy(), st_ref[k].numpy(), rtol=1e-4, atol=1e-5)
     assert int(sd["image_encoder.features.3.num_batches_tracked"]) == 1
+
+
+def test_celeba19_modules_match_oracle():
+    """Drop-in celeba19/model.py + train.py surface: eval-mode objective of the full 22-term step (joint, image-only,
+    18 singles, 2 sampled subsets) built from MVAE.forward + the list-based elbo_loss, and its gradients, vs the oracle."""
+    from oracle import celeba19_oracle as O19
+    from multimodal_vae_public_b200.celeba19 import model as M19, train as T19
+    L, B = 100, 4
+    st = O19.make_celeba19_state(L, seed=3)
+    m = M19.MVAE(L)
+    assert list(m.state_dict().keys()) == [k for k, _ in O19.celeba19_state_shapes(L)]
+    m.load_state_dict(st)
+    m = m.cuda().eval()
+    rs = np.random.RandomState(12)
+    image = torch.from_numpy(rs.uniform(0, 1, (B, 3, 64, 64)).astype(np.float32))
+    attrs = torch.from_numpy(rs.randint(0, 2, (B, 18)).astype(np.float32))
+    combos = np.zeros((2, 19), dtype=bool); combos[0, [0, 2, 17]] = True; combos[1, [4, 5, 6]] = True
+    ic = image.cuda(); alist = T19.tensor_2d_to_list(attrs.cuda())
+    total = 0
+    ri, ra, mu, lv = m(ic, alist)
+    assert ri.shape == (B, 3, 64, 64) and len(ra) == 18 and ra[0].shape == (B,)
+    total = total + T19.elbo_loss([ri] + ra, [ic] + alist, mu, lv, lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+    ri, _, mu, lv = m(image=ic)
+    total = total + T19.elbo_loss([ri], [ic], mu, lv, lambda_image=1.0, lambda_attrs=10.0, annealing_factor=0.5)
+    for i in range(18):
+        _, ra, mu, lv = m(attrs=[alist[k] if k == i else None for k in range(18)])
+        total = total + T19.elbo_loss([ra[i]], [alist[i]], mu, lv, annealing_factor=0.5)
+    for c in combos:
+        ri, ra, mu, lv = m(image=ic if c[0] else None, attrs=[alist[k] if c[1 + k] else None for k in range(18)])
+        rec = ([ri] if c[0] else []) + [ra[k] for k in range(18) if c[1 + k]]
+        dat = ([ic] if c[0] else []) + [alist[k] for k in range(18) if c[1 + k]]
+        total = total + T19.elbo_loss(rec, dat, mu, lv, annealing_factor=0.5)
+    total.backward()
+    st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in st.items()}
+    ref, terms, grads, _ = O19.step_grads(st64, image.double(), attrs.double(), L, [None] * 22, [], combos, 1.0, 10.0, 0.5,
+                                          training=False)
+    assert abs(total.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for k, v in m.named_parameters():
+        g = grads[k]
+        err = (v.grad.cpu().double() - g).abs().max().item() / max(g.abs().max().item(), 1e-4 * gmax)
+        assert err < 2e-3, (k, err)
+    # the subset sampler consumes numpy's global RNG like the reference's pool-based one
+    np.random.seed(21); a = T19.sample_combinations(T19.enumerate_combinations(19), 3)
+    np.random.seed(21); b = O19.sample_combinations_fast(19, 3, np.random)
+    assert np.array_equal(a, b)
