@@ -201,18 +201,29 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         else:
             dist.init_process_group(backend, timeout=datetime.timedelta(seconds=90))
     strong = args.scaling == "strong"
-    batch = 1024 if args.workload == "celeba" else BATCH
+    batch = {"celeba": 1024, "celeba19": 512}.get(args.workload, BATCH)
     b_local = batch // world if strong else batch
     b_global = b_local * world
     prec = ops.PREC_3XTF32 if args.precision == "3xtf32" else ops.PREC_TF32
-    celeba = args.workload == "celeba"
+    celeba = args.workload in ("celeba", "celeba19")
+    c19 = args.workload == "celeba19"
     if args.workload == "fashion":
         from multimodal_vae_public_b200.trainer_fashion import FashionMVAETrainer as Trainer
+    elif c19:
+        from multimodal_vae_public_b200.trainer_celeba19 import CelebA19MVAETrainer as Trainer
     elif celeba:
         from multimodal_vae_public_b200.trainer_celeba import CelebAMVAETrainer as Trainer
     else:
         Trainer = MnistMVAETrainer
-    if celeba:
+    if c19:
+        import numpy as np
+        np.random.seed(1234)             # the modality subsets of every step come from numpy's global RNG (as in the reference)
+        tr = Trainer(100, b_local, approx_m=1, device=dev, lr=1e-4, lambda_image=1.0, lambda_attrs=10.0, precision=prec,
+                     world_size=world, rank=rank, seed=0)
+        g = torch.Generator().manual_seed(100 + rank)
+        host = [(torch.rand(b_local, 3, 64, 64, generator=g), torch.randint(0, 2, (b_local, 18), generator=g).float())
+                for _ in range(4)]
+    elif celeba:
         tr = Trainer(100, b_local, device=dev, lr=1e-4, lambda_image=1.0, lambda_attrs=10.0, precision=prec,
                      world_size=world, rank=rank, seed=0, use_graph=not args.no_graph)
         g = torch.Generator().manual_seed(100 + rank)
@@ -295,7 +306,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             e2e_losses.append(tr.flush())
     ms_e2e = timed(e2e_region, args.steps)
     e2e = b_global * args.steps / (ms_e2e * 1e-3)
-    loss = float(tr.loss_host[0])
+    loss = float(tr.loss19.item()) if c19 else float(tr.loss_host[0])
 
     # ---- per-kernel roofline, measured live with CUDA events on the launching stream (eager pass, same buffers)
     log("per-kernel roofline pass")
@@ -316,13 +327,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "dtype": "fp32 (3xTF32 tensor-core split products, fp32 accumulate)" if prec == ops.PREC_3XTF32
                      else "tf32 (fp32 storage/accumulate)",
             "data": "synthetic",
-            "config": {"workload": (f"CelebA MVAE (image 64x64x3 + 18 attrs, conv+BatchNorm+Dropout), n_latents=100, "
+            "config": {"workload": ("CelebA-19 MVAE (image 64x64x3 + 18 single-attribute experts, 20 + approx_m=1 ELBO terms "
+                                    "per step, subsets re-sampled every step), n_latents=100, " if c19 else
+                                    "CelebA MVAE (image 64x64x3 + 18 attrs, conv+BatchNorm+Dropout), n_latents=100, "
                                     if celeba else
                                     f"{'FashionMNIST (conv enc/dec)' if args.workload == 'fashion' else 'MNIST'} MVAE "
                                     f"(image 28x28x1 + label one-of-10), n_latents={N_LATENTS}, ") +
                                    f"global batch {b_global} ({b_local}/GPU), full train step "
-                                   "(3 passes + ELBO + backward + Adam), BASELINE.json "
-                                   f"{ {'fashion': 'configs[2]', 'celeba': 'configs[3]'}.get(args.workload, 'configs[1]') }",
+                                   f"({'21' if c19 else '3'} passes + ELBO + backward + Adam), BASELINE.json "
+                                   f"{ {'fashion': 'configs[2]', 'celeba': 'configs[3]', 'celeba19': 'configs[4]'}.get(args.workload, 'configs[1]') }",
                        "parallelism": f"dp{world}", "global_batch": b_global,
                        "l2": (f"rotating pool of {npool} distinct input batches and a multi-GB per-step working set "
                               "(im2col matrices), larger than the 126 MB L2" if args.workload != "mnist" else
@@ -411,7 +424,8 @@ def measure_rooflines(tr, dev, prec, args):
     gemm_launches = (cnt.get("gemm_batch", 0) + cnt.get("linear_fwd", 0)) // reps
     out = {"gemm": {"ms_per_step": gemm_ms, "launches": gemm_launches,
                     "algorithmic_flops_per_step": {"mnist": executed_gemm_flops_per_sample, "fashion": fashion_gemm_flops_per_sample,
-                                           "celeba": celeba_gemm_flops_per_sample}[args.workload](tr.L) * tr.B},
+                                           "celeba": celeba_gemm_flops_per_sample,
+                                           "celeba19": lambda L: tr.gemm_flops_last_step() / tr.B}[args.workload](tr.L) * tr.B},
            "breakdown": {k: round(v, 5) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}}
     # HBM roofline of the fused reconstruction-loss kernel at roofline size (inputs >> L2), L2 not reusable
     R, D = 65536, 784
@@ -448,9 +462,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
-    ap.add_argument("--workload", choices=["mnist", "fashion", "celeba"], default="mnist",
+    ap.add_argument("--workload", choices=["mnist", "fashion", "celeba", "celeba19"], default="mnist",
                     help="mnist = BASELINE.json configs[1] (default, the headline); fashion = conv flavour (configs[2]); "
-                         "celeba = conv+BatchNorm flavour, global batch 1024 (configs[3])")
+                         "celeba = conv+BatchNorm flavour, global batch 1024 (configs[3]); celeba19 = 19 experts, "
+                         "approx_m=1, global batch 512 (configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -126,9 +126,9 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         self.colsT1 = f(P * B * 25, 2048); self.t1_x, self.t1_h = f(P * B * 64, 128), f(P * B * 64, 128)
         self.colsT2 = f(P * B * 64, 1024); self.t2_x, self.t2_h = f(P * B * 256, 64), f(P * B * 256, 64)
         self.colsT3 = f(P * B * 256, 512); self.t3_x, self.t3_h = f(P * B * 1024, 32), f(P * B * 1024, 32)
-        self.colsT4 = f(P * B * 1024, 48)
-        self.logit_i = f(P * B, 12288)
         R = NI * B
+        self.colsT4 = f(R * 1024, 48)          # the last ConvTranspose2d has no BatchNorm after it: live image passes only
+        self.logit_i = f(R, 12288)
         self.dcolsT4 = f(R * 1024, 48); self.d_t3h, self.d_t3x = f(R * 1024, 32), f(R * 1024, 32)
         self.dcolsT3 = f(R * 256, 512); self.d_t2h, self.d_t2x = f(R * 256, 64), f(R * 256, 64)
         self.dcolsT2 = f(R * 64, 1024); self.d_t1h, self.d_t1x = f(R * 64, 128), f(R * 64, 128)
@@ -241,6 +241,11 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         B, L = self.B, self.L
         if combos is None:
             combos = sample_combinations(19, self.approx_m) if self.approx_m > 0 else np.zeros((0, 19), dtype=bool)
+            if self.world > 1 and self.approx_m > 0:     # one global batch = one set of subsets: rank 0's draw wins
+                import torch.distributed as dist
+                t = torch.from_numpy(np.ascontiguousarray(combos).astype(np.uint8)).to(self.dev)
+                dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+                combos = t.cpu().numpy().astype(bool)
         combos = np.asarray(combos, dtype=bool).reshape(-1, 19)
         if len(combos) != self.approx_m:
             raise _lib.MvaeError(f"expected {self.approx_m} sampled combinations, got {len(combos)}")
@@ -276,6 +281,23 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         plan = self._last_plan
         t = self._terms.cpu().tolist()
         return {"total": float(sum(t)), "terms": [t[plan["inv"][r]] for r in range(plan["P"])]}
+
+    def _enqueue_step(self, training: bool, use_noise_input: bool, update: bool) -> None:
+        """Re-enqueue the last step's pass structure (bench.py's per-kernel timing pass)."""
+        self._enqueue(self._last_plan, training, use_noise_input, False, 1.0, update)
+
+    def gemm_flops_last_step(self) -> float:
+        """2*MAC of the GEMMs of the last step (depends on how many sampled subsets contained the image)."""
+        B, L, plan = self.B, self.L, self._last_plan
+        P, NI = plan["P"], plan["n_img"]
+        enc_conv = 1024 * 32 * 48 + 256 * 64 * 512 + 64 * 128 * 1024 + 25 * 256 * 2048
+        enc_i_f = enc_conv + 6400 * 512 + NI * 512 * 2 * L
+        enc_i_b = 2 * enc_i_f - 1024 * 32 * 48
+        enc_a = 3 * N_ATTRS * (512 * 512 + 512 * 2 * L)
+        dec_i_bn = L * 6400 + 25 * 2048 * 256 + 64 * 1024 * 128 + 256 * 512 * 64
+        dec_i = P * dec_i_bn + NI * 1024 * 48 * 32 + 2 * NI * (dec_i_bn + 1024 * 48 * 32)
+        dec_a = 3 * sum(len(lp) for lp in plan["dec_passes"]) * (L * 512 + 2 * 512 * 512 + 512)
+        return 2.0 * B * (enc_i_f + enc_i_b + enc_a + dec_i + dec_a)
 
     # ------------------------------------------------------------------ the launches of one step
     def _enqueue(self, plan, training: bool, noise_given: bool, masks_given: bool, beta: float, update: bool) -> None:
@@ -349,8 +371,9 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         G([D(self.t2_h[: P * B * 256], p[f"{d}.6.weight"], self.colsT3[: P * B * 256], P * B * 256, 512, 64)], Pp)
         ops.col2im_k4(self.colsT3, self.t3_x, P * B, 16, 16, 32, 2, 1)
         self._bn_f(self.t3_x[: P * B * 1024], self.t3_h[: P * B * 1024], P, B * 1024, f"{d}.7", bo, training)
-        G([D(self.t3_h[: P * B * 1024], p[f"{d}.9.weight"], self.colsT4[: P * B * 1024], P * B * 1024, 48, 32)], Pp)
-        ops.col2im_k4(self.colsT4, self.logit_i, P * B, 32, 32, 3, 2, 1)
+        R = NI * B                                     # image logits: only the passes whose loss has an image term
+        G([D(self.t3_h[: R * 1024], p[f"{d}.9.weight"], self.colsT4[: R * 1024], R * 1024, 48, 32)], Pp)
+        ops.col2im_k4(self.colsT4, self.logit_i, R, 32, 32, 3, 2, 1)
         # ---- attribute decoders on their live passes (rows gathered from Z)
         nrows = [len(lp) * B for lp in plan["dec_passes"]]
         torch.index_select(Z, 0, plan["rowidx_dev"], out=self.ad_z.view(-1, L))
@@ -365,7 +388,6 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
                    bias=p[f"attr_decoders.{i}.net.6.bias"]) for i in range(N_ATTRS)])
 
         # ================================================================ losses (+ dlogits)
-        R = NI * B
         li = self.logit_i[:R]
         acc_img = self.acc19[P:P + self.n_img_max]
         ops.bce_logits_fwd_bwd(li[: 2 * B], self.x, li[: 2 * B], self.lam_i / b_global, acc_img[:2], seg_rows=B)

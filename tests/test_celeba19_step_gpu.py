@@ -118,3 +118,28 @@ def test_celeba19_training_decreases_loss_and_samples_combos():
     assert np.isfinite(first) and np.isfinite(last) and last < first
     sd = tr.state_dict()
     assert int(sd["image_decoder.hallucinate.1.num_batches_tracked"]) == 16 * 22
+
+
+def test_celeba19_eval_mode_matches_oracle_fp64():
+    """training=False: z = mu, Dropout off, BatchNorm uses running statistics (which therefore must not change)."""
+    B = 8
+    rs = np.random.RandomState(6)
+    combos = np.zeros((1, 19), dtype=bool); combos[0, [0, 4, 11]] = True
+    image = torch.from_numpy(rs.uniform(0, 1, (B, 3, 64, 64)).astype(np.float32))
+    attrs = torch.from_numpy(rs.randint(0, 2, (B, 18)).astype(np.float32))
+    st = O19.make_celeba19_state(L, seed=8)
+    st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in st.items()}
+    total, terms, grads, bufs = O19.step_grads(st64, image.double(), attrs.double(), L, [None] * 21, [], combos, 1.0, 10.0,
+                                               0.25, training=False)
+    tr = _trainer(B, 1)
+    tr.load_state_dict(st)
+    got = tr.step(image, attrs, annealing_factor=0.25, combos=combos, training=False, update=False)
+    assert abs(got - total.item()) <= 5e-6 * abs(total.item())
+    mine = tr.export_grads()
+    gmax = max(g.abs().max().item() for g in grads.values())
+    for k, gref in grads.items():
+        err = (mine[k].cpu().double() - gref).abs().max().item() / max(gref.abs().max().item(), 1e-4 * gmax)
+        assert err <= 2e-3, (k, err)
+    sd = tr.state_dict()
+    for k, v in bufs.items():
+        assert torch.equal(sd[k].cpu(), st[k]), k
