@@ -442,7 +442,7 @@ def measure_rooflines(tr, dev, prec, args):
     st.synchronize()
     ms = s.elapsed_time(e) / 10
     peaks = load_peaks()
-    alg = (2 * R * D + R * D // 1) * 4.0   # read x, write dx, read t once per row (t re-read by the 2nd pass) = 12 B/elem
+    alg = (2 * R * D + (R // 2) * D) * 4.0   # read x once, write dx once, read the shared target once = 10 B per logit
     out["hbm"] = {"bound": "hbm", "kernel": "bce_kernel (fused BCE-with-logits loss + gradient), roofline-size run "
                                             f"R={R} D={D}", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                   "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,

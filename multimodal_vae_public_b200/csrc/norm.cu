@@ -21,13 +21,13 @@ constexpr int kMaxSeg = 32;
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// grid = (ceil(C/32), S * chunks_per_seg); block = 32 columns x 8 row lanes
+// grid = (S * chunks_per_seg, ceil(C/32)); block = 32 columns x 8 row lanes
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int64_t ld, int seg_rows, int C,
                                                        int chunks_per_seg, double* __restrict__ acc /*[S][C][2]*/) {
   __shared__ float s1[8][33], s2[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
-  const int seg = blockIdx.y / chunks_per_seg, chunk = blockIdx.y % chunks_per_seg;
+  const int seg = blockIdx.x / chunks_per_seg, chunk = blockIdx.x % chunks_per_seg;
   const int r0 = chunk * kRowsPerBlock, r1 = min(seg_rows, r0 + kRowsPerBlock);
   float a = 0.f, b = 0.f;
   if (c < C) {
@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int act, double* __restrict__ acc2 /*[S][C][2]*/) {
   __shared__ float s1[8][33], s2[8][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
-  const int seg = seg0 + blockIdx.y / chunks_per_seg, chunk = blockIdx.y % chunks_per_seg;
+  const int seg = seg0 + blockIdx.x / chunks_per_seg, chunk = blockIdx.x % chunks_per_seg;
   const int r0 = chunk * kRowsPerBlock, r1 = min(seg_rows, r0 + kRowsPerBlock);
   float a1 = 0.f, a2 = 0.f;
   if (c < C) {
@@ -264,7 +264,7 @@ extern "C" int mvae_bn_stats(const float* x, int64_t ldx, int S, int seg_rows, i
   if (!x || !acc || S < 1 || S > kMaxSeg || seg_rows < 1 || C < 1) return set_error(MVAE_ERR_BAD_ARG, "bn_stats: bad args");
   const int chunks = (seg_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   MVAE_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * S * C, ST(stream)));
-  dim3 grid((C + 31) / 32, S * chunks);
+  dim3 grid(S * chunks, (C + 31) / 32);
   bn_stats_kernel<<<grid, 256, 0, ST(stream)>>>(x, ldx, seg_rows, C, chunks, acc);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
@@ -320,7 +320,7 @@ extern "C" int mvae_bn_bwd(const float* x, int64_t ldx, const float* dh, int64_t
     return set_error(MVAE_ERR_BAD_ARG, "bn_bwd: bad args");
   const int chunks = (seg_rows + kRowsPerBlock - 1) / kRowsPerBlock;
   MVAE_CUDA_CHECK(cudaMemsetAsync(acc2, 0, sizeof(double) * 2 * S * C, ST(stream)));
-  dim3 grid((C + 31) / 32, nseg * chunks);
+  dim3 grid(nseg * chunks, (C + 31) / 32);
   bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(x, ldx, dh, lddh, seg_rows, C, chunks, seg0, mean, invstd, gamma, beta,
                                                      swish_act, acc2);
   bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(acc2, C, seg0, nseg, dgamma, dbeta);
