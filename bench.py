@@ -201,7 +201,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         else:
             dist.init_process_group(backend, timeout=datetime.timedelta(seconds=90))
     strong = args.scaling == "strong"
-    batch = {"celeba": 1024, "celeba19": 512}.get(args.workload, BATCH)
+    batch = args.global_batch or {"celeba": 1024, "celeba19": 512}.get(args.workload, BATCH)
     b_local = batch // world if strong else batch
     b_global = b_local * world
     prec = ops.PREC_3XTF32 if args.precision == "3xtf32" else ops.PREC_TF32
@@ -320,6 +320,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         gemm = roof["gemm"]
         ach = gemm["algorithmic_flops_per_step"] / (gemm["ms_per_step"] * 1e-3) / 1e12
         cpu = cpu_baseline(BATCH, budget_s=15.0) if world == 1 and not args.no_cpu_baseline else None
+        if args.workload == "mnist":
+            line_chain = {"gemm_chain": bool(tr.chain)}
+        else:
+            line_chain = {}
         line = {
             "metric": "mvae_train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -341,7 +345,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                               "(im2col matrices), larger than the 126 MB L2" if args.workload != "mnist" else
                               f"rotating pool of {POOL} distinct input batches ({POOL * b_local * 3144 / 1e6:.0f} MB) and a "
                               f"~{working_set_mb(b_local):.0f} MB per-step working set, both larger than the 126 MB L2"),
-                       "cuda_graph": tr.use_graph, "loss_last": loss},
+                       "cuda_graph": tr.use_graph, "loss_last": loss, **line_chain},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (b_local * (12288 + 18) * 4 + 4) if celeba else (b_local * (784 * 4 + 8) + 4),
@@ -459,6 +463,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--precision", choices=["3xtf32", "tf32"], default="3xtf32")
     ap.add_argument("--scaling", choices=["strong", "weak"], default="strong")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="override the global batch (experiments only; the default is the BASELINE.json configuration)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")

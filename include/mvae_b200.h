@@ -69,6 +69,26 @@ typedef struct {
 #define MVAE_GEMM_MAX_BATCH 4
 int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision, void* stream);
 
+/* Launch up to MVAE_GEMM_MAX_CHAIN problems in ONE persistent kernel where problem i may consume, as its A operand,
+ * the C (or out2) matrix written by an earlier problem deps[i] < i of the same launch (deps[i] = -1: independent).
+ * This is how a whole Linear+Swish stack -- mnist/model.py:81-84 (encoder), :101-105 (decoder) -- or its autograd chain
+ * runs as one launch: tiles are scheduled problem after problem, a tile's TMA producer waits until the row blocks of A
+ * it reads have been stored (per-row-block completion counters, release/acquire at gpu scope), so the tail of layer l
+ * overlaps the head of layer l+1 and no launch boundary separates them.
+ *   K-major A  : rows [m0, m0+128) of A  <- the producer's row block(s) holding those rows
+ *   MN-major A : (wgrad) the k range of the tile <- the producer's row blocks covering that range
+ * A must start at a multiple of 128 rows inside the producer's output and share its leading dimension.  Only the A
+ * operand may be produced inside the chain, and an output that a later problem of the chain still reads must not be
+ * overwritten by another problem of the same chain (no launch boundary orders those accesses any more).
+ *   ws : int32 workspace of ws_ints >= MVAE_GEMM_CHAIN_WS_HEADER + sum_i ceil(M_i/128) elements, zero-initialised ONCE
+ *        by the caller; the kernel leaves the counters zeroed.  ws[1] is a sticky error flag: non-zero after a
+ *        dependency wait timed out (~0.5 s; results are then invalid).
+ * The launch uses one CTA per SM (all CTAs co-resident), which the wait-for-producer scheme relies on. */
+#define MVAE_GEMM_MAX_CHAIN 16
+#define MVAE_GEMM_CHAIN_WS_HEADER 2
+int mvae_gemm_chain(const mvae_gemm_desc* descs, const int32_t* deps, int n, int32_t* ws, int64_t ws_ints,
+                    int precision, void* stream);
+
 /* y = x W^T + b (optionally also h = swish(y)):  nn.Linear.forward + Swish, mnist/model.py:81-84. */
 int mvae_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
                     int64_t ldy, float* h, int64_t ldh, int M, int N, int K, int precision, void* stream);

@@ -15,6 +15,8 @@ PREC_TF32 = 0
 PREC_3XTF32 = 1
 EPI_STORE, EPI_BIAS_SWISH, EPI_MUL_DSWISH = 0, 1, 2
 GEMM_MAX_BATCH = 4
+GEMM_MAX_CHAIN = 16
+GEMM_CHAIN_WS_HEADER = 2
 
 
 class MvaeError(RuntimeError):
@@ -40,6 +42,7 @@ _P, _I, _L, _F, _U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 # name -> argtypes ; every function returns int status unless listed in _SPECIAL_RESTYPE
 SIGNATURES = {
     "mvae_gemm_batch": [C.POINTER(GemmDesc), _I, _I, _P],
+    "mvae_gemm_chain": [C.POINTER(GemmDesc), C.POINTER(C.c_int32), _I, _P, _L, _I, _P],
     "mvae_linear_fwd": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P],
     "mvae_linear_dgrad": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P],
     "mvae_linear_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P],

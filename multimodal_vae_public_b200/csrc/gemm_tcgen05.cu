@@ -41,6 +41,12 @@ constexpr int A_STAGE_COLS = 64;                            // 3xTF32: A operand
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_SPLIT_WARPS = 4;
 constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;  // one swizzled 32x32 fp32 staging tile per epilogue warp
+constexpr int MAX_PROBLEMS = MVAE_GEMM_MAX_CHAIN;             // problem slots of one launch (batch uses the first 4)
+// Chain workspace (int32, caller-owned, zero-initialised once; the kernel leaves the counters zeroed again):
+//   ws[0] = CTAs that finished, ws[1] = sticky error flag (a dependency wait timed out), ws[2 + i] = completion
+//   counter of row block i (all problems of the chain, concatenated).
+constexpr int WS_DONE = 0, WS_ERR = 1, WS_CTR0 = MVAE_GEMM_CHAIN_WS_HEADER;
+constexpr long long DEP_TIMEOUT_CYCLES = 1LL << 30;           // ~0.5 s: a broken chain fails loudly instead of hanging
 
 template <bool kSplit>
 struct Cfg {
@@ -75,12 +81,19 @@ struct alignas(64) GemmProblem {
   uint32_t b_lbo, b_sbo, b_kstep, b_layout;
   int epilogue;
   int atomic;             // accumulate with red.add instead of st
+  // ---- chain mode (mvae_gemm_chain): the A operand of this problem is the C/out2 of problem `dep` of the same launch
+  int dep;                // producer problem index or -1
+  int dep_ctr_base;       // first counter of the producer's row blocks (+ the row-block offset of A inside it)
+  int dep_target;         // counter value of a complete producer row block: 8 epilogue warps x tiles_n x split_k
+  int ctr_base;           // first counter of this problem's row blocks
 };
 
 struct GemmBatch {
-  GemmProblem p[MVAE_GEMM_MAX_BATCH];
+  GemmProblem p[MAX_PROBLEMS];
   int num_problems;
   int total_tiles;
+  int* ws;          // chain workspace or nullptr (independent problems: no signalling, no waiting)
+  int num_ctrs;
   long long* dbg;   // optional timeline buffer (MVAE_DBG_TIMELINE): [block < 8][role < 4][64] clock64 stamps
   int dbg_flags;    // MVAE_DBG_EPI: 1 = skip global stores, 2 = skip sigmoid math, 4 = skip smem transpose
 };
@@ -100,7 +113,7 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmBatch& b, int t) {
   TileInfo ti;
   int pi = 0;
 #pragma unroll
-  for (int i = 1; i < MVAE_GEMM_MAX_BATCH; ++i)
+  for (int i = 1; i < MAX_PROBLEMS; ++i)
     if (i < b.num_problems && t >= b.p[i].tile_begin) pi = i;
   const GemmProblem& p = b.p[pi];
   int local = t - p.tile_begin;
@@ -132,6 +145,33 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(layout & 7) << 61;
   return d;
+}
+
+// ---- chain mode: row-block completion counters in global memory (release/acquire at gpu scope)
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// Wait until row block counter `ctr` reaches `target` (the producer tiles covering those rows have stored their
+// results).  Bounded: after DEP_TIMEOUT_CYCLES the sticky error flag is raised and every later wait returns at once,
+// so a scheduling bug shows up as a wrong result + error status, never as a hung GPU.
+__device__ __forceinline__ void wait_row_block(const int* ctr, int target, int* ws) {
+  if (ld_acquire_gpu(ctr) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_gpu(ctr) < target) {
+    __nanosleep(64);
+    if (*reinterpret_cast<volatile int*>(ws + WS_ERR) != 0) return;
+    if (clock64() - t0 > DEP_TIMEOUT_CYCLES) {
+      atomicExch(ws + WS_ERR, 1);
+      return;
+    }
+  }
 }
 
 // Epilogue sigmoid: ex2.approx + rcp.approx (5 instructions; max relative error ~ (2 + |x|) * 2^-23).  The epilogue
@@ -315,6 +355,18 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
         const int n0 = ti.n_blk * block_n;
         const uint32_t a_bytes = OPERAND_BYTES;
         const uint32_t b_bytes = static_cast<uint32_t>(block_n) * BLOCK_K * 4;
+        if (batch.ws != nullptr && p.dep >= 0) {
+          // chain mode: the rows of A this tile reads are produced by earlier tiles of this same launch
+          int rb0 = ti.m_blk, rb1 = ti.m_blk;                       // K-major A: my row block
+          if (a_mn) {                                               // MN-major A (wgrad): my k range = producer rows
+            const int k_end = ti.kb_end * BLOCK_K < p.K ? ti.kb_end * BLOCK_K : p.K;
+            rb0 = (ti.kb_begin * BLOCK_K) / BLOCK_M;
+            rb1 = (k_end - 1) / BLOCK_M;
+          }
+          const int* ctr = batch.ws + WS_CTR0 + p.dep_ctr_base;
+          for (int rb = rb0; rb <= rb1; ++rb) wait_row_block(ctr + rb, p.dep_target, batch.ws);
+          fence_proxy_async_all();   // the acquired generic-proxy stores -> visible to this thread's TMA (async proxy) reads
+        }
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
@@ -435,10 +487,12 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       if (ew == 0 && lane == 0) dbg_stamp(batch, 2, dn);
+      int* const my_ctr = batch.ws != nullptr ? batch.ws + WS_CTR0 + p.ctr_base + ti.m_blk : nullptr;
       if (half >= nchunks) {  // nothing to do for this warp on a narrow tile: release immediately
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        if (my_ctr != nullptr && lane == 0) red_release_gpu_add(my_ctr, 1);
         continue;
       }
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N_MAX;
@@ -460,6 +514,16 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
         if (ew == 0 && lane == 0) dbg_stamp(batch, 3, dn3);
         epilogue_chunk(e, stage_buf, r, ncols, lane, row_base, n0 + c0, bv, a0, batch.dbg_flags);
         if (ew == 0 && lane == 0) dbg_stamp(batch, 3, dn3);
+      }
+      if (my_ctr != nullptr) {
+        // chain mode: publish this warp's share of the tile.  Every lane orders its own stores against the async
+        // proxy (consumers read them through TMA), the warp converges, lane 0 releases at gpu scope.
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          red_release_gpu_add(my_ctr, 1);
+        }
       }
       if (ew == 0 && lane == 0) dbg_stamp(batch, 2, dn);
     }
@@ -539,6 +603,20 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
+  if (batch.ws != nullptr) {
+    // the last CTA to get here zeroes the counters, so the workspace is ready for the next launch on this stream
+    __shared__ int is_last;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      is_last = atomicAdd(batch.ws + WS_DONE, 1) == static_cast<int>(gridDim.x) - 1;
+      __threadfence();
+    }
+    __syncthreads();
+    if (is_last) {
+      for (int i = threadIdx.x; i < batch.num_ctrs; i += blockDim.x) batch.ws[WS_CTR0 + i] = 0;
+      if (threadIdx.x == 0) batch.ws[WS_DONE] = 0;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -598,31 +676,37 @@ MnEncoding mn_encoding() {
 
 using namespace mvae;
 
-extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision, void* stream) {
-  if (descs == nullptr || n < 1 || n > MVAE_GEMM_MAX_BATCH)
-    return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch: n must be in [1,%d]", MVAE_GEMM_MAX_BATCH);
+namespace mvae {
+namespace {
+
+// Shared host path of mvae_gemm_batch (independent problems) and mvae_gemm_chain (problems whose A operand is produced
+// by an earlier problem of the same launch; deps != nullptr, ws != nullptr).
+int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t* deps, int n, int max_n, int32_t* ws,
+                    int64_t ws_ints, int precision, void* stream) {
+  if (descs == nullptr || n < 1 || n > max_n) return set_error(MVAE_ERR_BAD_ARG, "%s: n must be in [1,%d]", who, max_n);
   if (precision != MVAE_PREC_TF32 && precision != MVAE_PREC_3XTF32)
-    return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch: unknown precision %d", precision);
-  GemmBatch batch;
+    return set_error(MVAE_ERR_BAD_ARG, "%s: unknown precision %d", who, precision);
+  GemmBatch batch;   // ~7 KiB of launch parameters (copied by value at launch)
   memset(&batch, 0, sizeof(batch));
-  int tiles = 0;
+  int tiles = 0, ctrs = 0;
+  const MnEncoding mn = mn_encoding();
   for (int i = 0; i < n; ++i) {
     const mvae_gemm_desc& d = descs[i];
     GemmProblem& p = batch.p[i];
     if (d.M < 1 || d.N < 1 || d.K < 1 || !d.A || !d.B || !d.C)
-      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: bad shape/pointer (M=%d N=%d K=%d)", i, d.M, d.N, d.K);
+      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: bad shape/pointer (M=%d N=%d K=%d)", who, i, d.M, d.N, d.K);
     if (d.epilogue == MVAE_EPI_BIAS_SWISH && !d.out2)
-      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: BIAS_SWISH needs out2 (bias may be NULL: bias=False convs)", i);
+      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: BIAS_SWISH needs out2 (bias may be NULL: bias=False convs)", who, i);
     if (d.epilogue == MVAE_EPI_MUL_DSWISH && !d.aux)
-      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: MUL_DSWISH needs aux", i);
+      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: MUL_DSWISH needs aux", who, i);
     if (d.epilogue < 0 || d.epilogue > MVAE_EPI_MUL_DSWISH)
-      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: unknown epilogue %d", i, d.epilogue);
+      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: unknown epilogue %d", who, i, d.epilogue);
     const int split = d.split_k < 1 ? 1 : d.split_k;
     const bool atomic = split > 1 || d.accumulate;
     if (atomic && (d.bias || d.epilogue != MVAE_EPI_STORE || d.colsum))
-      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: split_k/accumulate only with plain STORE epilogue", i);
+      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: split_k/accumulate only with plain STORE epilogue", who, i);
     if ((d.ldc & 3) || (reinterpret_cast<uintptr_t>(d.C) & 15))
-      return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_batch[%d]: C must be 16B aligned with ldc %% 4 == 0", i);
+      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: C must be 16B aligned with ldc %% 4 == 0", who, i);
     // MMA N: multiple of 16; MN-major B is fetched in 32-wide boxes.
     int block_n = d.N >= BLOCK_N_MAX ? BLOCK_N_MAX : round_up(d.N, d.b_mn_major ? 32 : 16);
     p.block_n = block_n;
@@ -636,17 +720,42 @@ extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision
     p.split_k = s;
     p.tile_begin = tiles;
     tiles += p.tiles_m * p.tiles_n * s;
+    p.ctr_base = ctrs;
+    ctrs += p.tiles_m;
     p.a_mn = d.a_mn_major ? 1 : 0;
     p.b_mn = d.b_mn_major ? 1 : 0;
     p.epilogue = d.epilogue;
     p.atomic = atomic ? 1 : 0;
     p.C = d.C; p.bias = d.bias; p.aux = d.aux; p.out2 = d.out2; p.colsum = d.colsum;
     p.ldc = d.ldc; p.ldaux = d.ldaux; p.ldout2 = d.ldout2;
-    const MnEncoding mn = mn_encoding();
     p.a_lbo = p.a_mn ? mn.lbo : 16u;  p.a_sbo = p.a_mn ? mn.sbo : 1024u;
     p.a_kstep = p.a_mn ? mn.kstep : 32u;  p.a_layout = p.a_mn ? mn.layout : 2u;
     p.b_lbo = p.b_mn ? mn.lbo : 16u;  p.b_sbo = p.b_mn ? mn.sbo : 1024u;
     p.b_kstep = p.b_mn ? mn.kstep : 32u;  p.b_layout = p.b_mn ? mn.layout : 2u;
+    p.dep = -1;
+    if (deps != nullptr && deps[i] >= 0) {
+      // A must be (a row-block aligned slice of) the C or out2 matrix of an EARLIER problem of this chain: stored rows
+      // of A are rows of the producer for K-major A, and the reduction index for MN-major A (wgrad).
+      const int q = deps[i];
+      if (q >= i) return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: dependency %d must be an earlier problem", who, i, q);
+      const mvae_gemm_desc& dq = descs[q];
+      const GemmProblem& pq = batch.p[q];
+      int64_t row_off = -1;
+      const float* bases[2] = {dq.C, dq.out2};
+      const int64_t lds[2] = {dq.ldc, dq.ldout2};
+      for (int b = 0; b < 2 && row_off < 0; ++b) {
+        if (bases[b] == nullptr || lds[b] != d.lda || d.A < bases[b]) continue;
+        const int64_t delta = d.A - bases[b];
+        if (delta % lds[b] == 0 && delta / lds[b] < dq.M) row_off = delta / lds[b];
+      }
+      const int a_rows = p.a_mn ? d.K : d.M;   // stored rows of A
+      if (row_off < 0 || row_off % BLOCK_M != 0 || row_off + a_rows > dq.M)
+        return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: A is not a %d-row aligned slice of the output of problem %d", who, i,
+                         BLOCK_M, q);
+      p.dep = q;
+      p.dep_ctr_base = pq.ctr_base + static_cast<int>(row_off / BLOCK_M);
+      p.dep_target = NUM_EPI_WARPS * pq.tiles_n * pq.split_k;
+    }
     int rc;
     if (!p.a_mn) rc = make_map(&p.map_a, d.A, d.K, d.M, d.lda, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
     else         rc = make_map(&p.map_a, d.A, d.M, d.K, d.lda, 32, BLOCK_K, mn.swizzle);
@@ -657,10 +766,18 @@ extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision
   }
   batch.num_problems = n;
   batch.total_tiles = tiles;
+  if (ws != nullptr) {
+    if (static_cast<int64_t>(WS_CTR0) + ctrs > ws_ints)
+      return set_error(MVAE_ERR_BAD_ARG, "%s: workspace too small (%lld ints, need %d)", who, (long long)ws_ints,
+                       WS_CTR0 + ctrs);
+    batch.ws = ws;
+    batch.num_ctrs = ctrs;
+  }
   if (const char* v = getenv("MVAE_DBG_TIMELINE")) batch.dbg = reinterpret_cast<long long*>(strtoull(v, nullptr, 0));
   if (const char* v = getenv("MVAE_DBG_EPI")) batch.dbg_flags = atoi(v);
   const int sms = mvae_device_sm_count();
   if (sms <= 0) return set_error(MVAE_ERR_CUDA, "no CUDA device");
+  // chain mode needs every CTA resident at once (a waiting tile's producers must be running): one CTA per SM
   const int grid = tiles < sms ? tiles : sms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static bool attr_set[2] = {false, false};
@@ -682,6 +799,20 @@ extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
+}
+
+}  // namespace
+}  // namespace mvae
+
+extern "C" int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision, void* stream) {
+  return launch_problems("mvae_gemm_batch", descs, nullptr, n, MVAE_GEMM_MAX_BATCH, nullptr, 0, precision, stream);
+}
+
+extern "C" int mvae_gemm_chain(const mvae_gemm_desc* descs, const int32_t* deps, int n, int32_t* ws, int64_t ws_ints,
+                               int precision, void* stream) {
+  if (deps == nullptr || ws == nullptr)
+    return set_error(MVAE_ERR_BAD_ARG, "mvae_gemm_chain: deps and ws must be non-NULL");
+  return launch_problems("mvae_gemm_chain", descs, deps, n, MVAE_GEMM_MAX_CHAIN, ws, ws_ints, precision, stream);
 }
 
 extern "C" int mvae_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,

@@ -48,6 +48,23 @@ def gemm_batch(descs: Sequence[GemmDesc], precision: int = PREC_3XTF32) -> None:
     _lib.check(_lib.load().mvae_gemm_batch(arr, len(descs), precision, _stream()), "mvae_gemm_batch")
 
 
+def gemm_chain(descs: Sequence[GemmDesc], deps: Sequence[int], ws: torch.Tensor, precision: int = PREC_3XTF32) -> None:
+    """Up to 16 problems in one launch; problem i reads, as its A operand, the output of problem deps[i] < i (or -1).
+    ``ws``: int32 CUDA workspace, zero-initialised once by the caller (see mvae_gemm_chain in include/mvae_b200.h)."""
+    if len(deps) != len(descs):
+        raise _lib.MvaeError("gemm_chain: one dependency entry per problem")
+    if ws.dtype != torch.int32 or not ws.is_cuda or not ws.is_contiguous():
+        raise _lib.MvaeError("gemm_chain: ws must be a contiguous CUDA int32 tensor")
+    arr = (GemmDesc * len(descs))(*descs)
+    dep = (C.c_int32 * len(deps))(*[int(d) for d in deps])
+    _lib.check(_lib.load().mvae_gemm_chain(arr, dep, len(descs), ws.data_ptr(), ws.numel(), precision, _stream()),
+               "mvae_gemm_chain")
+
+
+def chain_workspace(device, ints: int = 16384) -> torch.Tensor:
+    return torch.zeros(ints, dtype=torch.int32, device=device)
+
+
 def linear_fwd(x, w, bias, y, h=None, precision=PREC_3XTF32):
     """y = x @ w.T + bias ; optionally h = swish(y)."""
     _chk2d(x, "x"); _chk2d(w, "w"); _chk2d(y, "y")

@@ -22,6 +22,7 @@ Layout in HBM (fp32, row-major; B = per-rank batch, L = n_latents):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -99,7 +100,7 @@ class MnistMVAETrainer:
     def __init__(self, n_latents: int = 64, batch_size: int = 4096, device="cuda", lr: float = 1e-3,
                  lambda_image: float = 1.0, lambda_text: float = 10.0, precision: int = PREC_3XTF32,
                  world_size: int = 1, seed: int = 0, rank: int = 0, use_graph: bool = True,
-                 process_group=None):
+                 process_group=None, chain: Optional[bool] = None):
         _lib.load()  # fail loudly if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _lib.MvaeError("MnistMVAETrainer needs a CUDA device (no CPU fallback)")
@@ -112,6 +113,10 @@ class MnistMVAETrainer:
         self.world, self.rank, self.seed = world_size, rank, seed
         self.pg = process_group
         self.use_graph = use_graph
+        # chain mode: each Linear stack (and its autograd chain) is ONE persistent launch whose tiles wait on row-block
+        # completion counters instead of launch boundaries (mvae_gemm_chain); MVAE_CHAIN=0 restores one launch per layer
+        self.chain = os.environ.get("MVAE_CHAIN", "1") != "0" if chain is None else bool(chain)
+        self.chain_ws = ops.chain_workspace(torch.device(device))
         self.layout = self._make_layout(n_latents)
         self.arena = FlatArena(self.layout, self.dev, n_buffers=4, tail=4)  # params, grads(+loss tail), adam m, adam v
         self.params = {k: self.arena.view(0, k) for k, _ in self.layout}
@@ -159,7 +164,9 @@ class MnistMVAETrainer:
         self.id_a = [f(2 * B, 512) for _ in range(3)]; self.id_h = [f(2 * B, 512) for _ in range(3)]
         self.td_a = [f(2 * B, 512) for _ in range(3)]; self.td_h = [f(2 * B, 512) for _ in range(3)]
         # backward scratch
-        self.id_dA = [f(2 * B, 512) for _ in range(2)]; self.td_dA = [f(2 * B, 512) for _ in range(2)]
+        # one dA buffer per hidden layer: inside a chained launch no buffer may be rewritten while another problem of the
+        # same launch (the wgrad of the layer above) still reads it
+        self.id_dA = [f(2 * B, 512) for _ in range(3)]; self.td_dA = [f(2 * B, 512) for _ in range(3)]
         self.ie_dA = [f(B, 512) for _ in range(2)]; self.te_dA = [f(B, 512) for _ in range(2)]
 
     # ------------------------------------------------------------------ parameters
@@ -199,20 +206,28 @@ class MnistMVAETrainer:
     def _enqueue_forward(self, training: bool, use_noise_input: bool) -> None:
         B, L, P = self.B, self.L, self.prec
         p = self.params
-        # image encoder fc1 (+ text embedding in parallel on the same stream)
-        ops.linear_fwd(self.x, p["image_encoder.fc1.weight"], p["image_encoder.fc1.bias"], self.ie_a1, self.ie_h1, P)
-        ops.embedding_swish_fwd(p["text_encoder.fc1.weight"], self.text, None, self.te_h1)
-        ops.gemm_batch([
-            ops.gemm_desc(self.ie_h1, p["image_encoder.fc2.weight"], self.ie_a2, B, 512, 512,
-                          bias=p["image_encoder.fc2.bias"], out2=self.ie_h2, epilogue=ops.EPI_BIAS_SWISH),
-            ops.gemm_desc(self.te_h1, p["text_encoder.fc2.weight"], self.te_a2, B, 512, 512,
-                          bias=p["text_encoder.fc2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)], P)
         wi = self.arena.span(0, "image_encoder.fc31.weight", "image_encoder.fc32.weight").view(2 * L, 512)
         bi = self.arena.span(0, "image_encoder.fc31.bias", "image_encoder.fc32.bias")
         wt = self.arena.span(0, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512)
         bt = self.arena.span(0, "text_encoder.fc31.bias", "text_encoder.fc32.bias")
-        ops.gemm_batch([ops.gemm_desc(self.ie_h2, wi, self.enc_i, B, 2 * L, 512, bias=bi),
-                        ops.gemm_desc(self.te_h2, wt, self.enc_t, B, 2 * L, 512, bias=bt)], P)
+        D = ops.gemm_desc
+        fc1_i = D(self.x, p["image_encoder.fc1.weight"], self.ie_a1, B, 512, 784, bias=p["image_encoder.fc1.bias"],
+                  out2=self.ie_h1, epilogue=ops.EPI_BIAS_SWISH)
+        fc2_i = D(self.ie_h1, p["image_encoder.fc2.weight"], self.ie_a2, B, 512, 512,
+                  bias=p["image_encoder.fc2.bias"], out2=self.ie_h2, epilogue=ops.EPI_BIAS_SWISH)
+        fc2_t = D(self.te_h1, p["text_encoder.fc2.weight"], self.te_a2, B, 512, 512,
+                  bias=p["text_encoder.fc2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)
+        heads_i = D(self.ie_h2, wi, self.enc_i, B, 2 * L, 512, bias=bi)
+        heads_t = D(self.te_h2, wt, self.enc_t, B, 2 * L, 512, bias=bt)
+        ops.embedding_swish_fwd(p["text_encoder.fc1.weight"], self.text, None, self.te_h1)
+        if self.chain:
+            # both encoders in ONE launch: the two independent first layers fill the machine together, then the
+            # dependent layers follow tile by tile
+            ops.gemm_chain([fc1_i, fc2_t, fc2_i, heads_t, heads_i], [-1, -1, 0, 1, 2], self.chain_ws, P)
+        else:
+            ops.gemm_batch([fc1_i], P)
+            ops.gemm_batch([fc2_i, fc2_t], P)
+            ops.gemm_batch([heads_i, heads_t], P)
         # PoE + reparametrise + KL for the three passes
         mu_e = [self.enc_i[:, :L], self.enc_t[:, :L]]
         lv_e = [self.enc_i[:, L:], self.enc_t[:, L:]]
@@ -224,17 +239,23 @@ class MnistMVAETrainer:
         # decoders: image decoder on rows [0,2B) (image-only, joint), text decoder on rows [B,3B) (joint, text-only)
         zi, zt = self.Z[: 2 * B], self.Z[B:]
         xin_i, xin_t = zi, zt
+        layers = []
         for l in range(3):
             K = L if l == 0 else 512
-            ops.gemm_batch([
-                ops.gemm_desc(xin_i, p[f"image_decoder.fc{l + 1}.weight"], self.id_a[l], 2 * B, 512, K,
-                              bias=p[f"image_decoder.fc{l + 1}.bias"], out2=self.id_h[l], epilogue=ops.EPI_BIAS_SWISH),
-                ops.gemm_desc(xin_t, p[f"text_decoder.fc{l + 1}.weight"], self.td_a[l], 2 * B, 512, K,
-                              bias=p[f"text_decoder.fc{l + 1}.bias"], out2=self.td_h[l], epilogue=ops.EPI_BIAS_SWISH)], P)
+            layers.append([
+                D(xin_i, p[f"image_decoder.fc{l + 1}.weight"], self.id_a[l], 2 * B, 512, K,
+                  bias=p[f"image_decoder.fc{l + 1}.bias"], out2=self.id_h[l], epilogue=ops.EPI_BIAS_SWISH),
+                D(xin_t, p[f"text_decoder.fc{l + 1}.weight"], self.td_a[l], 2 * B, 512, K,
+                  bias=p[f"text_decoder.fc{l + 1}.bias"], out2=self.td_h[l], epilogue=ops.EPI_BIAS_SWISH)])
             xin_i, xin_t = self.id_h[l], self.td_h[l]
-        ops.gemm_batch([
-            ops.gemm_desc(xin_i, p["image_decoder.fc4.weight"], self.logit_i, 2 * B, 784, 512, bias=p["image_decoder.fc4.bias"]),
-            ops.gemm_desc(xin_t, p["text_decoder.fc4.weight"], self.logit_t, 2 * B, 10, 512, bias=p["text_decoder.fc4.bias"])], P)
+        layers.append([
+            D(xin_i, p["image_decoder.fc4.weight"], self.logit_i, 2 * B, 784, 512, bias=p["image_decoder.fc4.bias"]),
+            D(xin_t, p["text_decoder.fc4.weight"], self.logit_t, 2 * B, 10, 512, bias=p["text_decoder.fc4.bias"])])
+        if self.chain:   # both decoders, all four layers: one launch (problem 2l+d reads the output of problem 2(l-1)+d)
+            ops.gemm_chain([d for pair in layers for d in pair], [-1, -1, 0, 1, 2, 3, 4, 5], self.chain_ws, P)
+        else:
+            for pair in layers:
+                ops.gemm_batch(pair, P)
 
     def _enqueue_loss_and_backward(self, training: bool, b_global: int) -> None:
         B, L, P = self.B, self.L, self.prec
@@ -247,34 +268,44 @@ class MnistMVAETrainer:
         nk = max(1, (2 * B) // 32)  # k-blocks of a decoder wgrad
         ops.colsum_accumulate(dyi, g["image_decoder.fc4.bias"])
         ops.colsum_accumulate(dyt, g["text_decoder.fc4.bias"])
+        D = ops.gemm_desc
+        split = max(1, min(nk // 16, 32))   # ~16 k-blocks per wgrad tile, like the dgrad tiles of the same launch
+        chain_descs, chain_deps = [], []
         for l in (4, 3, 2, 1):
             n_i = 784 if l == 4 else 512
             n_t = 10 if l == 4 else 512
             K = L if l == 1 else 512
             x_i = self.Z[: 2 * B] if l == 1 else self.id_h[l - 2]
             x_t = self.Z[B:] if l == 1 else self.td_h[l - 2]
-            split = max(1, min(nk // 16, 32))   # ~16 k-blocks per wgrad tile, like the dgrad tiles of the same launch
-            descs = [
-                ops.gemm_desc(dyi, x_i, g[f"image_decoder.fc{l}.weight"], n_i, K, 2 * B, a_mn=True, b_mn=True,
-                              split_k=split, accumulate=True),
-                ops.gemm_desc(dyt, x_t, g[f"text_decoder.fc{l}.weight"], n_t, K, 2 * B, a_mn=True, b_mn=True,
-                              split_k=split, accumulate=True)]
+            wgrads = [
+                D(dyi, x_i, g[f"image_decoder.fc{l}.weight"], n_i, K, 2 * B, a_mn=True, b_mn=True,
+                  split_k=split, accumulate=True),
+                D(dyt, x_t, g[f"text_decoder.fc{l}.weight"], n_t, K, 2 * B, a_mn=True, b_mn=True,
+                  split_k=split, accumulate=True)]
             if l > 1:  # dA_{l-1} = (dy W_l) * swish'(a_{l-1}); its column sums are the bias gradient of layer l-1
-                dxi, dxt = self.id_dA[l % 2], self.td_dA[l % 2]
-                descs += [
-                    ops.gemm_desc(dyi, p[f"image_decoder.fc{l}.weight"], dxi, 2 * B, K, n_i, b_mn=True,
-                                  aux=self.id_a[l - 2], epilogue=ops.EPI_MUL_DSWISH,
-                                  colsum=g[f"image_decoder.fc{l - 1}.bias"]),
-                    ops.gemm_desc(dyt, p[f"text_decoder.fc{l}.weight"], dxt, 2 * B, K, n_t, b_mn=True,
-                                  aux=self.td_a[l - 2], epilogue=ops.EPI_MUL_DSWISH,
-                                  colsum=g[f"text_decoder.fc{l - 1}.bias"])]
+                dxi, dxt = self.id_dA[l - 2], self.td_dA[l - 2]
+                dgrads = [
+                    D(dyi, p[f"image_decoder.fc{l}.weight"], dxi, 2 * B, K, n_i, b_mn=True,
+                      aux=self.id_a[l - 2], epilogue=ops.EPI_MUL_DSWISH, colsum=g[f"image_decoder.fc{l - 1}.bias"]),
+                    D(dyt, p[f"text_decoder.fc{l}.weight"], dxt, 2 * B, K, n_t, b_mn=True,
+                      aux=self.td_a[l - 2], epilogue=ops.EPI_MUL_DSWISH, colsum=g[f"text_decoder.fc{l - 1}.bias"])]
             else:  # dZ is zero-initialised; both decoders add into it (the joint rows get both)
                 dxi, dxt = self.dZ[: 2 * B], self.dZ[B:]
-                descs += [
-                    ops.gemm_desc(dyi, p["image_decoder.fc1.weight"], dxi, 2 * B, K, n_i, b_mn=True, accumulate=True),
-                    ops.gemm_desc(dyt, p["text_decoder.fc1.weight"], dxt, 2 * B, K, n_t, b_mn=True, accumulate=True)]
-            ops.gemm_batch(descs, P)
+                dgrads = [
+                    D(dyi, p["image_decoder.fc1.weight"], dxi, 2 * B, K, n_i, b_mn=True, accumulate=True),
+                    D(dyt, p["text_decoder.fc1.weight"], dxt, 2 * B, K, n_t, b_mn=True, accumulate=True)]
+            if self.chain:
+                # per layer: [dgrad_i, dgrad_t, wgrad_i, wgrad_t]; dy of layer l is the dgrad output of layer l+1, four
+                # problems back (the dgrads come first so the dependent chain advances ahead of the filler wgrads)
+                base = len(chain_descs)
+                dep_i, dep_t = (-1, -1) if l == 4 else (base - 4, base - 3)
+                chain_descs += dgrads + wgrads
+                chain_deps += [dep_i, dep_t, dep_i, dep_t]
+            else:
+                ops.gemm_batch(wgrads + dgrads, P)
             dyi, dyt = dxi, dxt
+        if self.chain:   # the whole decoder backward (16 problems) is one launch
+            ops.gemm_chain(chain_descs, chain_deps, self.chain_ws, P)
         # ---- PoE / reparam / KL backward -> gradients of both encoders' outputs (summed over passes)
         mu_e = [self.enc_i[:, :L], self.enc_t[:, :L]]
         lv_e = [self.enc_i[:, L:], self.enc_t[:, L:]]
@@ -294,23 +325,28 @@ class MnistMVAETrainer:
         wt = arena.span(0, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512)
         ops.colsum_accumulate(self.d_enc_i, gbi)
         ops.colsum_accumulate(self.d_enc_t, gbt)
-        ops.gemm_batch([
-            ops.gemm_desc(self.d_enc_i, self.ie_h2, gwi, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True),
-            ops.gemm_desc(self.d_enc_t, self.te_h2, gwt, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True),
-            ops.gemm_desc(self.d_enc_i, wi, self.ie_dA[0], B, 512, 2 * L, b_mn=True, aux=self.ie_a2,
-                          epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc2.bias"]),
-            ops.gemm_desc(self.d_enc_t, wt, self.te_dA[0], B, 512, 2 * L, b_mn=True, aux=self.te_a2,
-                          epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_encoder.fc2.bias"])], P)
-        ops.gemm_batch([
-            ops.gemm_desc(self.ie_dA[0], self.ie_h1, g["image_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
-                          split_k=split, accumulate=True),
-            ops.gemm_desc(self.te_dA[0], self.te_h1, g["text_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
-                          split_k=split, accumulate=True),
-            ops.gemm_desc(self.ie_dA[0], p["image_encoder.fc2.weight"], self.ie_dA[1], B, 512, 512, b_mn=True,
-                          aux=self.ie_a1, epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc1.bias"]),
-            ops.gemm_desc(self.te_dA[0], p["text_encoder.fc2.weight"], self.te_dA[1], B, 512, 512, b_mn=True)], P)
-        ops.gemm_batch([ops.gemm_desc(self.ie_dA[1], self.x, g["image_encoder.fc1.weight"], 512, 784, B, a_mn=True,
-                                      b_mn=True, split_k=split, accumulate=True)], P)
+        wg_hi = D(self.d_enc_i, self.ie_h2, gwi, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True)
+        wg_ht = D(self.d_enc_t, self.te_h2, gwt, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True)
+        dg_hi = D(self.d_enc_i, wi, self.ie_dA[0], B, 512, 2 * L, b_mn=True, aux=self.ie_a2,
+                  epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc2.bias"])
+        dg_ht = D(self.d_enc_t, wt, self.te_dA[0], B, 512, 2 * L, b_mn=True, aux=self.te_a2,
+                  epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_encoder.fc2.bias"])
+        wg_2i = D(self.ie_dA[0], self.ie_h1, g["image_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
+                  split_k=split, accumulate=True)
+        wg_2t = D(self.te_dA[0], self.te_h1, g["text_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
+                  split_k=split, accumulate=True)
+        dg_2i = D(self.ie_dA[0], p["image_encoder.fc2.weight"], self.ie_dA[1], B, 512, 512, b_mn=True,
+                  aux=self.ie_a1, epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc1.bias"])
+        dg_2t = D(self.te_dA[0], p["text_encoder.fc2.weight"], self.te_dA[1], B, 512, 512, b_mn=True)
+        wg_1i = D(self.ie_dA[1], self.x, g["image_encoder.fc1.weight"], 512, 784, B, a_mn=True, b_mn=True,
+                  split_k=split, accumulate=True)
+        if self.chain:   # both encoders' backward: one launch
+            ops.gemm_chain([dg_hi, dg_ht, wg_hi, wg_ht, dg_2i, dg_2t, wg_2i, wg_2t, wg_1i],
+                           [-1, -1, -1, -1, 0, 1, 0, 1, 4], self.chain_ws, P)
+        else:
+            ops.gemm_batch([wg_hi, wg_ht, dg_hi, dg_ht], P)
+            ops.gemm_batch([wg_2i, wg_2t, dg_2i, dg_2t], P)
+            ops.gemm_batch([wg_1i], P)
         ops.embedding_swish_bwd(p["text_encoder.fc1.weight"], self.text, self.te_dA[1], g["text_encoder.fc1.weight"])
 
     def _enqueue_fwd_bwd(self, training: bool, use_noise_input: bool) -> None:

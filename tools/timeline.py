@@ -9,15 +9,28 @@ import torch  # noqa: E402
 from multimodal_vae_public_b200 import ops  # noqa: E402
 
 prec = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+kind = sys.argv[2] if len(sys.argv) > 2 else "fwd"      # fwd | dgrad | wgrad
 M, N, K = 8192, 512, 512
 x = torch.randn(M, K, device="cuda"); w = torch.randn(N, K, device="cuda"); b = torch.randn(N, device="cuda")
 y = torch.empty(M, N, device="cuda"); h = torch.empty(M, N, device="cuda")
+dy = torch.randn(M, N, device="cuda"); dx = torch.empty(M, K, device="cuda"); dw = torch.zeros(N, K, device="cuda")
+
+
+def run():
+    if kind == "fwd":
+        ops.linear_fwd(x, w, b, y, h, precision=prec)
+    elif kind == "dgrad":
+        ops.linear_dgrad(dy, w, dx, a_prev=x, precision=prec)
+    else:
+        ops.linear_wgrad(dy, x, dw, split_k=16, precision=prec)
+
+
 for _ in range(20):
-    ops.linear_fwd(x, w, b, y, h, precision=prec)
+    run()
 torch.cuda.synchronize()
 dbg = torch.zeros(8 * 4 * 64, dtype=torch.int64, device="cuda")
 os.environ["MVAE_DBG_TIMELINE"] = str(dbg.data_ptr())
-ops.linear_fwd(x, w, b, y, h, precision=prec)
+run()
 torch.cuda.synchronize()
 del os.environ["MVAE_DBG_TIMELINE"]
 d = dbg.cpu().view(8, 4, 64)
