@@ -395,7 +395,7 @@ def measure_rooflines(tr, dev, prec, args):
     import torch
     from multimodal_vae_public_b200 import ops
     st = tr._stream
-    names = ["gemm_batch", "linear_fwd", "bce_logits_fwd_bwd", "ce_fwd_bwd", "poe_fwd", "poe_bwd", "colsum_accumulate",
+    names = ["gemm_batch", "gemm_chain", "linear_fwd", "bce_logits_fwd_bwd", "ce_fwd_bwd", "poe_fwd", "poe_bwd", "colsum_accumulate",
              "embedding_swish_fwd", "embedding_swish_bwd", "adam_flat", "elbo_finalize", "im2col_k4s2p1", "col2im_k4s2p1",
              "im2col_k4", "col2im_k4", "bn_forward", "bn_backward", "dropout_fwd", "dropout_bwd", "nchw_to_nhwc", "swish_bwd"]
     records = []
@@ -424,8 +424,8 @@ def measure_rooflines(tr, dev, prec, args):
     for n, s, e in records:
         per[n] = per.get(n, 0.0) + s.elapsed_time(e) / reps
         cnt[n] = cnt.get(n, 0) + 1
-    gemm_ms = per.get("gemm_batch", 0.0) + per.get("linear_fwd", 0.0)
-    gemm_launches = (cnt.get("gemm_batch", 0) + cnt.get("linear_fwd", 0)) // reps
+    gemm_ms = per.get("gemm_batch", 0.0) + per.get("gemm_chain", 0.0) + per.get("linear_fwd", 0.0)
+    gemm_launches = (cnt.get("gemm_batch", 0) + cnt.get("gemm_chain", 0) + cnt.get("linear_fwd", 0)) // reps
     out = {"gemm": {"ms_per_step": gemm_ms, "launches": gemm_launches,
                     "algorithmic_flops_per_step": {"mnist": executed_gemm_flops_per_sample, "fashion": fashion_gemm_flops_per_sample,
                                            "celeba": celeba_gemm_flops_per_sample,
