@@ -48,15 +48,25 @@ constexpr int MAX_PROBLEMS = MVAE_GEMM_MAX_CHAIN;             // problem slots o
 constexpr int WS_DONE = 0, WS_ERR = 1, WS_CTR0 = MVAE_GEMM_CHAIN_WS_HEADER;
 constexpr long long DEP_TIMEOUT_CYCLES = 1LL << 30;           // ~0.5 s: a broken chain fails loudly instead of hanging
 
-template <bool kSplit>
+template <bool kSplit, bool kPair = false>
 struct Cfg {
-  // tf32 : [A][B]            32 KiB x 6 stages
-  // 3x   : [A raw][B raw][B lo] 48 KiB x 4 stages; the A operand is re-staged as hi|lo in TENSOR MEMORY
-  static constexpr int kStageBytes = kSplit ? 3 * OPERAND_BYTES : 2 * OPERAND_BYTES;
-  static constexpr int kStages = kSplit ? 4 : 6;                                       // 192 KiB ring
+  // tf32     : [A][B]                        32 KiB x 6 stages
+  // 3x       : [A raw][B raw][B lo]          48 KiB x 4 stages; the A operand is re-staged as hi|lo in TENSOR MEMORY
+  // 3x, pair : [A raw][B raw half][B lo half] 32 KiB x 4 stages: a CTA pair (cta_group::2) works on a 256 x block_n tile,
+  //            each CTA holds its own 128 rows of A and HALF of the B tile; the tensor cores of the two SMs exchange
+  //            the B halves, so every SM reads (and splits) half as many B bytes from its shared memory per product
+  static constexpr int kBBytes = kPair ? OPERAND_BYTES / 2 : OPERAND_BYTES;           // B tile bytes held by one CTA
+  static constexpr int kStageBytes = kSplit ? OPERAND_BYTES + 2 * kBBytes : 2 * OPERAND_BYTES;
+  // Shared-memory ring depth.  The 3x modes also stage A in tensor memory (kTmemStages slots of 64 columns next to the
+  // 2 x 128 accumulator columns = all 512).  In pair mode the smem ring is DEEPER than the TMEM ring: the TMA runs up to
+  // 6 k-blocks ahead (covers the L2 -> smem latency), the splitters up to 4 ahead of the tensor core; measured with
+  // 4/4 the pair main loop was round-trip-latency bound at ~1300 cycles per k-block instead of the tensor pipe's 768.
+  static constexpr int kStages = kSplit ? (kPair ? 6 : 4) : 6;
+  static constexpr int kTmemStages = 4;
   static constexpr int kTmemCols = kSplit ? 512 : 256;
   static constexpr int kThreads = 32 * (2 + NUM_EPI_WARPS + (kSplit ? NUM_SPLIT_WARPS : 0));
   static constexpr int kSmemBytes = kStages * kStageBytes + EPI_STAGE_BYTES + 1024;  // + 1024 B alignment slack
+  static constexpr int kTileM = kPair ? 2 * BLOCK_M : BLOCK_M;   // rows of one scheduled tile
 };
 
 struct alignas(64) GemmProblem {
@@ -86,6 +96,8 @@ struct alignas(64) GemmProblem {
   int dep_ctr_base;       // first counter of the producer's row blocks (+ the row-block offset of A inside it)
   int dep_target;         // counter value of a complete producer row block: 8 epilogue warps x tiles_n x split_k
   int ctr_base;           // first counter of this problem's row blocks
+  int row_blocks;         // ceil(M / 128): counters of this problem
+  int dep_row_blocks;     // counters of the producer from dep_ctr_base on (row blocks beyond do not exist)
 };
 
 struct GemmBatch {
@@ -94,13 +106,13 @@ struct GemmBatch {
   int total_tiles;
   int* ws;          // chain workspace or nullptr (independent problems: no signalling, no waiting)
   int num_ctrs;
-  long long* dbg;   // optional timeline buffer (MVAE_DBG_TIMELINE): [block < 8][role < 4][64] clock64 stamps
+  long long* dbg;   // optional timeline buffer (MVAE_DBG_TIMELINE): [block < 8][role < 6][64] clock64 stamps
   int dbg_flags;    // MVAE_DBG_EPI: 1 = skip global stores, 2 = skip sigmoid math, 4 = skip smem transpose
 };
 
 __device__ __forceinline__ void dbg_stamp(const GemmBatch& b, int role, int& n) {
   if (b.dbg != nullptr && blockIdx.x < 8 && n < 64) {
-    b.dbg[(blockIdx.x * 4 + role) * 64 + n] = clock64();
+    b.dbg[(blockIdx.x * 6 + role) * 64 + n] = clock64();
     ++n;
   }
 }
@@ -376,9 +388,10 @@ __device__ __forceinline__ void epilogue_chunk_fast(const EpiParams& e, uint32_t
   __syncwarp();  // the staging tile is rewritten by the next chunk
 }
 
-template <bool kSplit>
-__global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __grid_constant__ GemmBatch batch) {
-  using C = Cfg<kSplit>;
+template <bool kSplit, bool kPair>
+__device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
+  using C = Cfg<kSplit, kPair>;
+  static_assert(!kPair || kSplit, "the CTA-pair variant exists for the 3xTF32 mode only");
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::kStages];
   __shared__ __align__(8) uint64_t ready_bar[C::kStages];
@@ -390,6 +403,10 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pair mode: rank 0 = leader (issues the MMAs, owns ready / tmem_empty barriers), rank 1 = peer
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const int tile0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < batch.num_problems; ++i) {
@@ -398,21 +415,27 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
     }
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&ready_bar[s], NUM_SPLIT_WARPS * 32);
+      ptx::mbar_init(&ready_bar[s], (kPair ? 2 : 1) * NUM_SPLIT_WARPS * 32);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+      ptx::mbar_init(&tmem_empty_bar[a], (kPair ? 2 : 1) * NUM_EPI_WARPS);
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_base_smem, C::kTmemCols);
-    ptx::tmem_relinquish();
+    if (kPair) {
+      ptx::tmem_alloc2(&tmem_base_smem, C::kTmemCols);
+      ptx::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(&tmem_base_smem, C::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync_all();   // also: the peer's barriers are initialised before anyone arrives on them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -423,25 +446,28 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       uint32_t phase = 0;
       int dn = 0;
       dbg_stamp(batch, 0, dn);
-      for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x) {
+      for (int t = tile0; t < batch.total_tiles; t += tile_step) {
         const TileInfo ti = decode_tile(batch, t);
         const GemmProblem& p = batch.p[ti.prob];
         const int block_n = p.block_n, a_mn = p.a_mn, b_mn = p.b_mn;
         const CUtensorMap* map_a = &p.map_a;
         const CUtensorMap* map_b = &p.map_b;
-        const int m0 = ti.m_blk * BLOCK_M;
-        const int n0 = ti.n_blk * block_n;
+        const int my_rb = kPair ? 2 * ti.m_blk + static_cast<int>(rank) : ti.m_blk;   // my 128-row block of C / A
+        const int m0 = my_rb * BLOCK_M;
+        const int n_mine = kPair ? block_n >> 1 : block_n;          // B rows this CTA stages
+        const int n0 = ti.n_blk * block_n + (kPair ? static_cast<int>(rank) * n_mine : 0);
         const uint32_t a_bytes = OPERAND_BYTES;
-        const uint32_t b_bytes = static_cast<uint32_t>(block_n) * BLOCK_K * 4;
+        const uint32_t b_bytes = static_cast<uint32_t>(n_mine) * BLOCK_K * 4;
         if (batch.ws != nullptr && p.dep >= 0) {
           // chain mode: the rows of A this tile reads are produced by earlier tiles of this same launch
-          int rb0 = ti.m_blk, rb1 = ti.m_blk;                       // K-major A: my row block
+          int rb0 = my_rb, rb1 = my_rb;                             // K-major A: my row block
           if (a_mn) {                                               // MN-major A (wgrad): my k range = producer rows
             const int k_end = ti.kb_end * BLOCK_K < p.K ? ti.kb_end * BLOCK_K : p.K;
             rb0 = (ti.kb_begin * BLOCK_K) / BLOCK_M;
             rb1 = (k_end - 1) / BLOCK_M;
           }
           const int* ctr = batch.ws + WS_CTR0 + p.dep_ctr_base;
+          if (rb1 >= p.dep_row_blocks) rb1 = p.dep_row_blocks - 1;  // (pair mode: the peer's rows may lie beyond M)
           for (int rb = rb0; rb <= rb1; ++rb) wait_row_block(ctr + rb, p.dep_target, batch.ws);
           fence_proxy_async_all();   // the acquired generic-proxy stores -> visible to this thread's TMA (async proxy) reads
         }
@@ -461,7 +487,7 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
           if (!b_mn) {
             ptx::tma_load_2d(sb, map_b, &full_bar[stage], k0, n0);  // box {32 k, block_n rows}
           } else {
-            for (int j = 0; j < block_n / 32; ++j)
+            for (int j = 0; j < n_mine / 32; ++j)
               ptx::tma_load_2d(sb + j * 4096, map_b, &full_bar[stage], n0 + 32 * j, k0);
           }
           dbg_stamp(batch, 0, dn);
@@ -470,54 +496,87 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer (single thread)
-    if (lane == 0) {
+    // ===================================================== MMA issuer (pair mode: the leader CTA's)
+    // The whole warp runs the loop in uniform control flow and ONE elected lane issues: tcgen05.mma / commit take their
+    // operands from uniform registers, and inside an `if (lane == 0)` region the compiler cannot prove uniformity -- it
+    // wrapped every MMA in an ELECT + 6x R2UR + branch sequence (~12 instructions).  Computed warp-uniformly the
+    // descriptors live in uniform registers and an MMA is a couple of uniform adds.
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int slot = 0;        // TMEM A staging slot of the current k-block (3x modes)
       int iter = 0;
       int dn = 0;
-      dbg_stamp(batch, 1, dn);
-      for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x, ++iter) {
+      if (lane == 0) dbg_stamp(batch, 1, dn);
+      for (int t = tile0; t < batch.total_tiles; t += tile_step, ++iter) {
         const TileInfo ti = decode_tile(batch, t);
         const GemmProblem& p = batch.p[ti.prob];
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
-        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        if (kPair) ptx::mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+        else ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N_MAX;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kSplit ? 0 : p.a_mn) << 15) |
                                (static_cast<uint32_t>(p.b_mn) << 16) |
-                               (static_cast<uint32_t>(p.block_n >> 3) << 17) | (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
-        const uint32_t a_lbo = p.a_lbo, a_sbo = p.a_sbo, a_kstep = p.a_kstep, a_lay = p.a_layout;
-        const uint32_t b_lbo = p.b_lbo, b_sbo = p.b_sbo, b_kstep = p.b_kstep, b_lay = p.b_layout;
+                               (static_cast<uint32_t>(p.block_n >> 3) << 17) | (static_cast<uint32_t>(C::kTileM >> 4) << 24);
+        // One thread issues every MMA of this SM (pair), so ITS instruction stream is the tensor pipe's feed rate: with
+        // the descriptors rebuilt from the problem table per MMA the loop issued one MMA per ~110 cycles (measured:
+        // tools/micro/mma_rate.cu, profiles/r01_notes.md) against the pipe's 64.  The descriptors of one tile differ
+        // only in the start-address field (bits [0,14), units of 16 B, no carry: smem < 256 KiB), so everything else
+        // is built once per tile and each MMA costs one 64-bit add.
+        const uint32_t smem0 = ptx::smem_u32(smem);
+        const uint64_t da0 = make_desc(smem0, p.a_lbo, p.a_sbo, p.a_layout);                   // stage 0, k-slice 0
+        const uint64_t db0 = make_desc(smem0 + OPERAND_BYTES, p.b_lbo, p.b_sbo, p.b_layout);
+        const uint64_t a_k16 = p.a_kstep >> 4, b_k16 = p.b_kstep >> 4;
+        const uint32_t a_tm0 = tmem_base + ACC_COLS;
         uint32_t accumulate = 0;
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
-          ptx::mbar_wait(kSplit ? &ready_bar[stage] : &full_bar[stage], phase);
+          if (kPair) ptx::mbar_wait_cluster(&ready_bar[stage], phase);   // both CTAs' splitters arrive here
+          else ptx::mbar_wait(kSplit ? &ready_bar[stage] : &full_bar[stage], phase);
           ptx::tc_fence_after();
-          dbg_stamp(batch, 1, dn);
-          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
-          const uint32_t sb = sa + OPERAND_BYTES;
+          if (lane == 0) dbg_stamp(batch, 1, dn);
+          const uint64_t st16 = static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
+          const uint64_t db = db0 + st16;
+          if (kSplit) {
+            // A (hi | lo) comes from tensor memory, B raw (= hi by hardware truncation) and B lo from smem
+            const uint64_t db_lo = db + (C::kBBytes >> 4);
+            const uint32_t a_hi = a_tm0 + slot * A_STAGE_COLS;
+            const uint32_t a_lo = a_hi + 32;
+            if (ptx::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-            const uint64_t db = make_desc(sb + ks * b_kstep, b_lbo, b_sbo, b_lay);
-            if (kSplit) {
-              // A (hi | lo) comes from tensor memory, B raw (= hi by hardware truncation) and B lo from smem
-              const uint32_t a_hi = tmem_base + ACC_COLS + stage * A_STAGE_COLS + ks * UMMA_K;
-              const uint32_t a_lo = a_hi + 32;
-              const uint64_t db_lo = make_desc(sb + OPERAND_BYTES + ks * b_kstep, b_lbo, b_sbo, b_lay);
-              ptx::mma_tf32_ts(d_tmem, a_lo, db, idesc, accumulate);  // lo*hi
-              ptx::mma_tf32_ts(d_tmem, a_hi, db_lo, idesc, 1u);       // hi*lo
-              ptx::mma_tf32_ts(d_tmem, a_hi, db, idesc, 1u);          // hi*hi
-            } else {
-              const uint64_t da = make_desc(sa + ks * a_kstep, a_lbo, a_sbo, a_lay);
-              ptx::mma_tf32_ss(d_tmem, da, db, idesc, accumulate);
+            for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
+              const uint32_t acc0 = ks == 0 ? accumulate : 1u;
+              if (kPair) {
+                ptx::mma_tf32_ts2(d_tmem, a_lo + ks * UMMA_K, db + ks * b_k16, idesc, acc0);   // lo*hi
+                ptx::mma_tf32_ts2(d_tmem, a_hi + ks * UMMA_K, db_lo + ks * b_k16, idesc, 1u);  // hi*lo
+                ptx::mma_tf32_ts2(d_tmem, a_hi + ks * UMMA_K, db + ks * b_k16, idesc, 1u);     // hi*hi
+              } else {
+                ptx::mma_tf32_ts(d_tmem, a_lo + ks * UMMA_K, db + ks * b_k16, idesc, acc0);    // lo*hi
+                ptx::mma_tf32_ts(d_tmem, a_hi + ks * UMMA_K, db_lo + ks * b_k16, idesc, 1u);   // hi*lo
+                ptx::mma_tf32_ts(d_tmem, a_hi + ks * UMMA_K, db + ks * b_k16, idesc, 1u);      // hi*hi
+              }
             }
-            accumulate = 1u;
+            if (kPair) ptx::mma_commit2(&empty_bar[stage]);  // frees the slot in BOTH CTAs when these MMAs retire
+            else ptx::mma_commit(&empty_bar[stage]);         // frees the smem slot when these MMAs retire
+            }
+          } else {
+            const uint64_t da = da0 + st16;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks)
+                ptx::mma_tf32_ss(d_tmem, da + ks * a_k16, db + ks * b_k16, idesc, ks == 0 ? accumulate : 1u);
+              ptx::mma_commit(&empty_bar[stage]);         // frees the smem slot when these MMAs retire
+            }
           }
-          ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          accumulate = 1u;
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++slot == C::kTmemStages) slot = 0;
         }
-        ptx::mma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (ptx::elect_one()) {
+          if (kPair) ptx::mma_commit2(&tmem_full_bar[acc]);  // accumulator complete -> both CTAs' epilogues
+          else ptx::mma_commit(&tmem_full_bar[acc]);         // accumulator complete -> epilogue
+        }
       }
     }
   } else if (warp < 2 + NUM_EPI_WARPS) {
@@ -534,13 +593,14 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
     float4* stage_buf = reinterpret_cast<float4*>(smem + C::kStages * C::kStageBytes) + ew * (32 * 8);
     int iter = 0;
     int dn = 0, dn3 = 0;
-    for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x, ++iter) {
+    for (int t = tile0; t < batch.total_tiles; t += tile_step, ++iter) {
       const TileInfo ti = decode_tile(batch, t);
       const GemmProblem& p = batch.p[ti.prob];
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       const int n0 = ti.n_blk * p.block_n;
-      const int row_base = ti.m_blk * BLOCK_M + quarter * 32;
+      const int my_rb = kPair ? 2 * ti.m_blk + static_cast<int>(rank) : ti.m_blk;
+      const int row_base = my_rb * BLOCK_M + quarter * 32;
       const int block_n = p.block_n;
       const int nchunks = (block_n + 31) >> 5;
       const int last_c = (half + 2 < nchunks) ? half + 2 : half;
@@ -578,11 +638,16 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       if (ew == 0 && lane == 0) dbg_stamp(batch, 2, dn);
-      int* const my_ctr = batch.ws != nullptr ? batch.ws + WS_CTR0 + p.ctr_base + ti.m_blk : nullptr;
+      int* const my_ctr = (batch.ws != nullptr && my_rb < p.row_blocks) ? batch.ws + WS_CTR0 + p.ctr_base + my_rb : nullptr;
+      // pair mode: the accumulator-free barrier lives in the leader CTA and counts both CTAs' epilogue warps
+      const uint32_t tmem_empty_addr = kPair ? ptx::mapa_shared(&tmem_empty_bar[acc], 0) : 0u;
       if (half >= nchunks) {  // nothing to do for this warp on a narrow tile: release immediately
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        if (lane == 0) {
+          if (kPair) ptx::mbar_arrive_cluster(tmem_empty_addr);
+          else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
         if (my_ctr != nullptr && lane == 0) red_release_gpu_add(my_ctr, 1);
         continue;
       }
@@ -600,7 +665,10 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
           // all TMEM reads of this warp for this accumulator are done: hand it back to the MMA warp early
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if (kPair) ptx::mbar_arrive_cluster(tmem_empty_addr);
+            else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         if (ew == 0 && lane == 0) dbg_stamp(batch, 3, dn3);
         if (rows_inside && ncols == 32 && n0 + c0 + 32 <= e.N) {
@@ -646,11 +714,24 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
     const int row = quarter * 32 + lane;                       // tile row owned by this thread
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < batch.total_tiles; t += gridDim.x) {
+    int slot = 0;                       // TMEM A staging slot
+    int old_stage = 0;                  // smem stage (and its phase) of the k-block that used this TMEM slot last
+    uint32_t old_phase = 0;
+    int kcount = 0;
+    int dn4 = 0;
+    for (int t = tile0; t < batch.total_tiles; t += tile_step) {
       const TileInfo ti = decode_tile(batch, t);
       const int a_mn = batch.p[ti.prob].a_mn;
       for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
+        if (tid == 0) dbg_stamp(batch, 4, dn4);
         ptx::mbar_wait(&full_bar[stage], phase);
+        if (C::kStages != C::kTmemStages && kcount >= C::kTmemStages) {
+          // the TMEM slot is free once the MMAs of the k-block kTmemStages back have retired: that is the completion of
+          // ITS smem stage's empty barrier (the producer may not have refilled that stage yet, so full_bar says nothing)
+          ptx::mbar_wait(&empty_bar[old_stage], old_phase);
+          ptx::tc_fence_after();
+        }
+        if (tid == 0) dbg_stamp(batch, 4, dn4);
         const uint8_t* sa = smem + stage * C::kStageBytes;
         uint32_t hi[32], lo[32];
         if (!a_mn) {
@@ -678,37 +759,51 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
             lo[k] = __float_as_uint(x - h);
           }
         }
-        const uint32_t ta = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ACC_COLS + stage * A_STAGE_COLS;
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + ACC_COLS + slot * A_STAGE_COLS;
         ptx::tmem_st_32x32(ta, hi);
         ptx::tmem_st_32x32(ta + 32, lo);
+        if (tid == 0) dbg_stamp(batch, 4, dn4);
         // B: lo tile only
         const float4* braw = reinterpret_cast<const float4*>(sa + OPERAND_BYTES);
-        float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(sa) + 2 * OPERAND_BYTES);
+        float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(sa) + OPERAND_BYTES + C::kBBytes);
+        // all loads first, then all stores: interleaved, every load would wait for the previous store (the compiler
+        // cannot prove that braw and blo do not alias), which serialised 8 shared-memory round trips per k-block
+        constexpr int kBIters = C::kBBytes / 16 / (NUM_SPLIT_WARPS * 32);
+        float4 bx[kBIters];
 #pragma unroll
-        for (int i = 0; i < OPERAND_BYTES / 16 / (NUM_SPLIT_WARPS * 32); ++i) {
-          const int idx = tid + i * (NUM_SPLIT_WARPS * 32);
-          const float4 x = braw[idx];
+        for (int i = 0; i < kBIters; ++i) bx[i] = braw[tid + i * (NUM_SPLIT_WARPS * 32)];
+#pragma unroll
+        for (int i = 0; i < kBIters; ++i) {
           float4 l;
-          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
-          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
-          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          blo[idx] = l;
+          l.x = bx[i].x - __uint_as_float(__float_as_uint(bx[i].x) & 0xFFFFE000u);
+          l.y = bx[i].y - __uint_as_float(__float_as_uint(bx[i].y) & 0xFFFFE000u);
+          l.z = bx[i].z - __uint_as_float(__float_as_uint(bx[i].z) & 0xFFFFE000u);
+          l.w = bx[i].w - __uint_as_float(__float_as_uint(bx[i].w) & 0xFFFFE000u);
+          blo[tid + i * (NUM_SPLIT_WARPS * 32)] = l;
         }
+        if (tid == 0) dbg_stamp(batch, 4, dn4);
         ptx::tmem_st_wait();
         ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        if (tid == 0) dbg_stamp(batch, 4, dn4);
         ptx::tc_fence_before();
-        ptx::mbar_arrive(&ready_bar[stage]);
+        if (kPair) ptx::mbar_arrive_cluster(ptx::mapa_shared(&ready_bar[stage], 0));   // the leader's barrier
+        else ptx::mbar_arrive(&ready_bar[stage]);
         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        if (++slot == C::kTmemStages) slot = 0;
+        if (++kcount > C::kTmemStages) {
+          if (++old_stage == C::kStages) { old_stage = 0; old_phase ^= 1; }
+        }
       }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync_all();   // the peer's smem / TMEM / barriers stay valid until the leader is done too
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    if (kPair) ptx::tmem_dealloc2(tmem_base, C::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
   if (batch.ws != nullptr) {
     // the last CTA to get here zeroes the counters, so the workspace is ready for the next launch on this stream
@@ -724,6 +819,17 @@ __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __
       if (threadIdx.x == 0) batch.ws[WS_DONE] = 0;
     }
   }
+}
+
+template <bool kSplit>
+__global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __grid_constant__ GemmBatch batch) {
+  gemm_body<kSplit, false>(batch);
+}
+
+// CTA-pair variant (3xTF32): launched as clusters of two CTAs (adjacent SMs of a TPC), tcgen05 cta_group::2.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, true>::kThreads, 1)
+    gemm_pair_kernel(const __grid_constant__ GemmBatch batch) {
+  gemm_body<true, true>(batch);
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -788,6 +894,40 @@ namespace {
 
 // Shared host path of mvae_gemm_batch (independent problems) and mvae_gemm_chain (problems whose A operand is produced
 // by an earlier problem of the same launch; deps != nullptr, ws != nullptr).
+// MVAE_PAIR=1 routes 3xTF32 launches to the CTA-pair kernel (default off until it is the measured winner).
+bool use_pair_kernel(int precision) {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* v = getenv("MVAE_PAIR");
+    cached = (v != nullptr && atoi(v) != 0) ? 1 : 0;
+  }
+  return cached == 1 && precision == MVAE_PREC_3XTF32;
+}
+
+// Clusters of two CTAs that can be resident at once (one CTA per SM; <= 74 on a B200).  Chain mode needs every CTA of
+// the launch resident, so the grid never exceeds this.
+int max_pair_clusters() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * 74, 1, 1);
+  cfg.blockDim = dim3(Cfg<true, true>::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg<true, true>::kSmemBytes;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_pair_kernel, &cfg) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = mvae_device_sm_count() / 2 - 4;   // conservative guess
+  }
+  cached = n;
+  return cached;
+}
+
 int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t* deps, int n, int max_n, int32_t* ws,
                     int64_t ws_ints, int precision, void* stream) {
   if (descs == nullptr || n < 1 || n > max_n) return set_error(MVAE_ERR_BAD_ARG, "%s: n must be in [1,%d]", who, max_n);
@@ -796,6 +936,8 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
   GemmBatch batch;   // ~7 KiB of launch parameters (copied by value at launch)
   memset(&batch, 0, sizeof(batch));
   int tiles = 0, ctrs = 0;
+  const bool pair = use_pair_kernel(precision);
+  const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
   const MnEncoding mn = mn_encoding();
   for (int i = 0; i < n; ++i) {
     const mvae_gemm_desc& d = descs[i];
@@ -815,10 +957,12 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
     if ((d.ldc & 3) || (reinterpret_cast<uintptr_t>(d.C) & 15))
       return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: C must be 16B aligned with ldc %% 4 == 0", who, i);
     // MMA N: multiple of 16; MN-major B is fetched in 32-wide boxes.
-    int block_n = d.N >= BLOCK_N_MAX ? BLOCK_N_MAX : round_up(d.N, d.b_mn_major ? 32 : 16);
+    // Pair mode: each CTA stages half of the B tile, so the half must itself be a whole number of boxes / swizzle atoms.
+    int block_n = d.N >= BLOCK_N_MAX ? BLOCK_N_MAX : round_up(d.N, d.b_mn_major ? (pair ? 64 : 32) : 16);
     p.block_n = block_n;
     p.M = d.M; p.N = d.N; p.K = d.K;
-    p.tiles_m = (d.M + BLOCK_M - 1) / BLOCK_M;
+    p.tiles_m = (d.M + tile_m - 1) / tile_m;
+    p.row_blocks = (d.M + BLOCK_M - 1) / BLOCK_M;
     p.tiles_n = (d.N + block_n - 1) / block_n;
     p.num_kblocks = (d.K + BLOCK_K - 1) / BLOCK_K;
     int s = split > p.num_kblocks ? p.num_kblocks : split;
@@ -828,7 +972,7 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
     p.tile_begin = tiles;
     tiles += p.tiles_m * p.tiles_n * s;
     p.ctr_base = ctrs;
-    ctrs += p.tiles_m;
+    ctrs += p.row_blocks;
     p.a_mn = d.a_mn_major ? 1 : 0;
     p.b_mn = d.b_mn_major ? 1 : 0;
     p.epilogue = d.epilogue;
@@ -861,13 +1005,14 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
                          BLOCK_M, q);
       p.dep = q;
       p.dep_ctr_base = pq.ctr_base + static_cast<int>(row_off / BLOCK_M);
+      p.dep_row_blocks = pq.row_blocks - static_cast<int>(row_off / BLOCK_M);
       p.dep_target = NUM_EPI_WARPS * pq.tiles_n * pq.split_k;
     }
     int rc;
     if (!p.a_mn) rc = make_map(&p.map_a, d.A, d.K, d.M, d.lda, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
     else         rc = make_map(&p.map_a, d.A, d.M, d.K, d.lda, 32, BLOCK_K, mn.swizzle);
     if (rc) return rc;
-    if (!p.b_mn) rc = make_map(&p.map_b, d.B, d.K, d.N, d.ldb, BLOCK_K, block_n, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (!p.b_mn) rc = make_map(&p.map_b, d.B, d.K, d.N, d.ldb, BLOCK_K, pair ? block_n / 2 : block_n, CU_TENSOR_MAP_SWIZZLE_128B);
     else         rc = make_map(&p.map_b, d.B, d.N, d.K, d.ldb, 32, BLOCK_K, mn.swizzle);
     if (rc) return rc;
   }
@@ -887,8 +1032,16 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
   // chain mode needs every CTA resident at once (a waiting tile's producers must be running): one CTA per SM
   const int grid = tiles < sms ? tiles : sms;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  static bool attr_set[2] = {false, false};
-  if (precision == MVAE_PREC_3XTF32) {
+  static bool attr_set[3] = {false, false, false};
+  if (pair) {
+    if (!attr_set[2]) {
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<true, true>::kSmemBytes));
+      attr_set[2] = true;
+    }
+    const int clusters = tiles < max_pair_clusters() ? tiles : max_pair_clusters();
+    gemm_pair_kernel<<<2 * clusters, Cfg<true, true>::kThreads, Cfg<true, true>::kSmemBytes, st>>>(batch);
+  } else if (precision == MVAE_PREC_3XTF32) {
     if (!attr_set[1]) {
       MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<true>::kSmemBytes));

@@ -28,16 +28,20 @@ def run():
 for _ in range(20):
     run()
 torch.cuda.synchronize()
-dbg = torch.zeros(8 * 4 * 64, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(8 * 6 * 64, dtype=torch.int64, device="cuda")
 os.environ["MVAE_DBG_TIMELINE"] = str(dbg.data_ptr())
 run()
 torch.cuda.synchronize()
 del os.environ["MVAE_DBG_TIMELINE"]
-d = dbg.cpu().view(8, 4, 64)
-for blk in (0,):
+d = dbg.cpu().view(8, 6, 64)
+for blk in (0, 1):
     if blk >= 8:
         continue
     t0 = int(d[blk][d[blk] > 0].min())
-    for role, name in enumerate(("producer", "mma", "epilogue", "epi-chunk")):
+    for role, name in enumerate(("producer", "mma", "epilogue", "epi-chunk", "splitter")):
         ev = [int(v) - t0 for v in d[blk, role] if v > 0]
         print(f"block {blk} {name:9s} n={len(ev):2d}:", " ".join(str(e) for e in ev))
+        if name == "splitter":   # per k-block: [loop top, full seen, A in TMEM issued, B lo written, st waited + fenced]
+            rows = [ev[i:i + 5] for i in range(0, len(ev) - 4, 5)]
+            print("   per k-block (wait full | split A | split B | wait st+fence | to next):",
+                  " ; ".join("/".join(str(b - a) for a, b in zip(r, r[1:])) for r in rows[:12]))
