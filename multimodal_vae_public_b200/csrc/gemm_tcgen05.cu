@@ -108,7 +108,19 @@ struct GemmBatch {
   int num_ctrs;
   long long* dbg;   // optional timeline buffer (MVAE_DBG_TIMELINE): [block < 8][role < 6][64] clock64 stamps
   int dbg_flags;    // MVAE_DBG_EPI: 1 = skip global stores, 2 = skip sigmoid math, 4 = skip smem transpose
+  long long* tilelog;  // optional per-tile log (MVAE_DBG_TILELOG): [cta][TILELOG_MAX][4] = {tile, t_begin, t_deps_ready,
+                       // t_epilogue_done} in globaltimer ns -- a Gantt chart of a (chained) launch
 };
+
+constexpr int TILELOG_MAX = 64;
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tilelog(const GemmBatch& b, int slot, int field, long long v) {
+  if (b.tilelog != nullptr && slot < TILELOG_MAX) b.tilelog[(static_cast<long long>(blockIdx.x) * TILELOG_MAX + slot) * 4 + field] = v;
+}
 
 __device__ __forceinline__ void dbg_stamp(const GemmBatch& b, int role, int& n) {
   if (b.dbg != nullptr && blockIdx.x < 8 && n < 64) {
@@ -165,6 +177,11 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -199,6 +216,11 @@ __device__ __forceinline__ float sigmoidf_acc(float x) {
 
 __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -445,11 +467,13 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
       int stage = 0;
       uint32_t phase = 0;
       int dn = 0;
+      int tl = 0;
       dbg_stamp(batch, 0, dn);
-      for (int t = tile0; t < batch.total_tiles; t += tile_step) {
+      for (int t = tile0; t < batch.total_tiles; t += tile_step, ++tl) {
         const TileInfo ti = decode_tile(batch, t);
         const GemmProblem& p = batch.p[ti.prob];
         const int block_n = p.block_n, a_mn = p.a_mn, b_mn = p.b_mn;
+        if (batch.tilelog != nullptr) { tilelog(batch, tl, 0, t); tilelog(batch, tl, 1, globaltimer_ns()); }
         const CUtensorMap* map_a = &p.map_a;
         const CUtensorMap* map_b = &p.map_b;
         const int my_rb = kPair ? 2 * ti.m_blk + static_cast<int>(rank) : ti.m_blk;   // my 128-row block of C / A
@@ -468,9 +492,26 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           }
           const int* ctr = batch.ws + WS_CTR0 + p.dep_ctr_base;
           if (rb1 >= p.dep_row_blocks) rb1 = p.dep_row_blocks - 1;  // (pair mode: the peer's rows may lie beyond M)
-          for (int rb = rb0; rb <= rb1; ++rb) wait_row_block(ctr + rb, p.dep_target, batch.ws);
-          fence_proxy_async_all();   // the acquired generic-proxy stores -> visible to this thread's TMA (async proxy) reads
+          // Fast check first: the producers are usually long done, and the acquire loads of the slow path cost ~0.5 us
+          // EACH (measured 1.1 us per tile for one row block, 2.1 us for the four of a wgrad tile -- the TMA pipeline ran
+          // dry at every tile boundary).  Relaxed gpu-scope loads read the counters at L2, all in flight together; the
+          // operands themselves are then fetched by TMA from L2 (never through this SM's L1), after the proxy fence.
+          const int nrb = rb1 - rb0 + 1;
+          int seen[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) seen[j] = (j < nrb) ? ld_relaxed_gpu(ctr + rb0 + j) : p.dep_target;
+          bool all_done = nrb <= 6;
+#pragma unroll
+          for (int j = 0; j < 6; ++j) all_done = all_done && seen[j] >= p.dep_target;
+          // (No proxy fence on this side in the fast path: the writers ordered their generic-proxy stores against the async
+          // proxy BEFORE releasing the counter -- the same division of labour as st.shared -> fence.proxy.async -> barrier
+          // -> TMA store -- and a fence here cost another ~0.4 us per tile.)
+          if (!all_done) {
+            for (int rb = rb0; rb <= rb1; ++rb) wait_row_block(ctr + rb, p.dep_target, batch.ws);
+            fence_proxy_async_all();
+          }
         }
+        if (batch.tilelog != nullptr) tilelog(batch, tl, 2, globaltimer_ns());
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
@@ -695,12 +736,10 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
         // proxy (consumers read them through TMA), the warp converges, lane 0 releases at gpu scope.
         fence_proxy_async_all();
         __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          red_release_gpu_add(my_ctr, 1);
-        }
+        if (lane == 0) red_release_gpu_add(my_ctr, 1);   // release at gpu scope: covers the lanes' stores (syncwarp above)
       }
       if (ew == 0 && lane == 0) dbg_stamp(batch, 2, dn);
+      if (batch.tilelog != nullptr && ew == 0 && lane == 0) tilelog(batch, iter, 3, globaltimer_ns());
     }
   } else if (kSplit) {
     // ===================================================== operand splitters (3xTF32 only), warps 10..13
@@ -732,14 +771,15 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           ptx::tc_fence_after();
         }
         if (tid == 0) dbg_stamp(batch, 4, dn4);
-        const uint8_t* sa = smem + stage * C::kStageBytes;
+        // (shared-window ld/st: through generic pointers these compiled to LD.E / ST.E, the slower generic path)
+        const uint32_t sa = ptx::smem_u32(smem) + stage * C::kStageBytes;
         uint32_t hi[32], lo[32];
         if (!a_mn) {
           // K-major tile: row r at r*128 B, 16-byte chunks XOR-swizzled with (r & 7)
-          const uint8_t* rp = sa + row * 128;
+          const uint32_t rp = sa + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(rp + ((j ^ (row & 7)) << 4));
+            const float4 x = lds128(rp + ((j ^ (row & 7)) << 4));
             const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -750,10 +790,10 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           }
         } else {
           // MN-major tile: 4 boxes of [32 k-rows][32 m]; box = quarter; 32-byte chunks XOR-swizzled with (k & 3)
-          const uint8_t* bp = sa + quarter * 4096 + ((lane & 7) << 2);
+          const uint32_t bp = sa + quarter * 4096 + ((lane & 7) << 2);
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float x = *reinterpret_cast<const float*>(bp + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
+            const float x = lds32(bp + k * 128 + ((((lane >> 3) ^ (k & 3))) << 5));
             const float h = ptx::round_tf32(x);
             hi[k] = __float_as_uint(h);
             lo[k] = __float_as_uint(x - h);
@@ -764,14 +804,14 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
         ptx::tmem_st_32x32(ta + 32, lo);
         if (tid == 0) dbg_stamp(batch, 4, dn4);
         // B: lo tile only
-        const float4* braw = reinterpret_cast<const float4*>(sa + OPERAND_BYTES);
-        float4* blo = reinterpret_cast<float4*>(const_cast<uint8_t*>(sa) + OPERAND_BYTES + C::kBBytes);
+        const uint32_t braw = sa + OPERAND_BYTES + (tid << 4);
+        const uint32_t blo = braw + C::kBBytes;
         // all loads first, then all stores: interleaved, every load would wait for the previous store (the compiler
         // cannot prove that braw and blo do not alias), which serialised 8 shared-memory round trips per k-block
         constexpr int kBIters = C::kBBytes / 16 / (NUM_SPLIT_WARPS * 32);
         float4 bx[kBIters];
 #pragma unroll
-        for (int i = 0; i < kBIters; ++i) bx[i] = braw[tid + i * (NUM_SPLIT_WARPS * 32)];
+        for (int i = 0; i < kBIters; ++i) bx[i] = lds128(braw + i * (NUM_SPLIT_WARPS * 32 * 16));
 #pragma unroll
         for (int i = 0; i < kBIters; ++i) {
           float4 l;
@@ -779,7 +819,7 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           l.y = bx[i].y - __uint_as_float(__float_as_uint(bx[i].y) & 0xFFFFE000u);
           l.z = bx[i].z - __uint_as_float(__float_as_uint(bx[i].z) & 0xFFFFE000u);
           l.w = bx[i].w - __uint_as_float(__float_as_uint(bx[i].w) & 0xFFFFE000u);
-          blo[tid + i * (NUM_SPLIT_WARPS * 32)] = l;
+          sts128(blo + i * (NUM_SPLIT_WARPS * 32 * 16), l.x, l.y, l.z, l.w);
         }
         if (tid == 0) dbg_stamp(batch, 4, dn4);
         ptx::tmem_st_wait();
@@ -1027,6 +1067,7 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
   }
   if (const char* v = getenv("MVAE_DBG_TIMELINE")) batch.dbg = reinterpret_cast<long long*>(strtoull(v, nullptr, 0));
   if (const char* v = getenv("MVAE_DBG_EPI")) batch.dbg_flags = atoi(v);
+  if (const char* v = getenv("MVAE_DBG_TILELOG")) batch.tilelog = reinterpret_cast<long long*>(strtoull(v, nullptr, 0));
   const int sms = mvae_device_sm_count();
   if (sms <= 0) return set_error(MVAE_ERR_CUDA, "no CUDA device");
   // chain mode needs every CTA resident at once (a waiting tile's producers must be running): one CTA per SM
