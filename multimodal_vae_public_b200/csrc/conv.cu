@@ -16,28 +16,38 @@
 namespace mvae {
 namespace {
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU sigmoid (ex2.approx + rcp.approx, relative error ~(2 + |x|) * 2^-23): the IEEE expf + division version made
+// these bandwidth-bound kernels instruction-bound (same finding as the BCE kernel, profiles/r01_notes.md).
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
 // one thread = one float4 of channels (or one scalar when C < 4) of one (output pixel, tap)
 template <int VEC>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ cols, int B, int H,
                                                      int W, int C, int64_t ld_cols, int stride, int pad) {
-  const int OH = (H + 2 * pad - 4) / stride + 1, OW = (W + 2 * pad - 4) / stride + 1;
-  const int cv = C / VEC;
-  const int64_t total = static_cast<int64_t>(B) * OH * OW * 16 * cv;
-  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  // 32-bit index arithmetic (the host checks that the element count fits): the original 64-bit div/mod chain cost more
+  // instructions than the 16-byte copy it addresses and held the kernel at ~1.6 TB/s
+  const unsigned OH = (H + 2 * pad - 4) / stride + 1, OW = (W + 2 * pad - 4) / stride + 1;
+  const unsigned cv = C / VEC;
+  const unsigned total = static_cast<unsigned>(B) * OH * OW * 16u * cv;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int c = static_cast<int>(gid % cv) * VEC;
-  int64_t r = gid / cv;
-  const int tap = static_cast<int>(r % 16);
-  r /= 16;                       // output pixel index m = (b*OH + oh)*OW + ow
-  const int ow = static_cast<int>(r % OW);
-  const int64_t r2 = r / OW;
-  const int oh = static_cast<int>(r2 % OH);
-  const int b = static_cast<int>(r2 / OH);
+  unsigned r = gid / cv;
+  const int c = static_cast<int>(gid - r * cv) * VEC;
+  const int tap = static_cast<int>(r & 15u);
+  r >>= 4;                       // output pixel index m = (b*OH + oh)*OW + ow
+  const unsigned r2 = r / OW;
+  const int ow = static_cast<int>(r - r2 * OW);
+  const unsigned bq = r2 / OH;
+  const int oh = static_cast<int>(r2 - bq * OH);
+  const int b = static_cast<int>(bq);
   const int kh = tap >> 2, kw = tap & 3;
   const int ih = stride * oh - pad + kh, iw = stride * ow - pad + kw;
-  float* dst = cols + r * ld_cols + tap * C + c;
+  float* dst = cols + static_cast<int64_t>(r) * ld_cols + tap * C + c;
   const bool in = (ih >= 0 && ih < H && iw >= 0 && iw < W);
   const float* src = x + ((static_cast<int64_t>(b) * H + ih) * W + iw) * C + c;
   if constexpr (VEC == 4) {
@@ -52,31 +62,32 @@ template <int VEC>
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ cols, int64_t ld_cols, float* out,
                                                      float* out_act, const float* __restrict__ aux, int B, int IH,
                                                      int IW, int C, int stride, int pad) {
-  const int OH = (IH - 1) * stride - 2 * pad + 4, OW = (IW - 1) * stride - 2 * pad + 4;
-  const int cv = C / VEC;
-  const int64_t total = static_cast<int64_t>(B) * OH * OW * cv;
-  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const unsigned OH = (IH - 1) * stride - 2 * pad + 4, OW = (IW - 1) * stride - 2 * pad + 4;
+  const unsigned cv = C / VEC;
+  const unsigned total = static_cast<unsigned>(B) * OH * OW * cv;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int c = static_cast<int>(gid % cv) * VEC;
-  int64_t r = gid / cv;          // output pixel
-  const int ow = static_cast<int>(r % OW);
-  const int64_t r2 = r / OW;
-  const int oh = static_cast<int>(r2 % OH);
-  const int b = static_cast<int>(r2 / OH);
+  const unsigned r = gid / cv;   // output pixel
+  const int c = static_cast<int>(gid - r * cv) * VEC;
+  const unsigned r2 = r / OW;
+  const int ow = static_cast<int>(r - r2 * OW);
+  const unsigned bq = r2 / OH;
+  const int oh = static_cast<int>(r2 - bq * OH);
+  const int b = static_cast<int>(bq);
   float acc[VEC];
 #pragma unroll
   for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
 #pragma unroll
   for (int kh = 0; kh < 4; ++kh) {
     const int th = oh + pad - kh;               // = stride * ih
-    if (th < 0 || th % stride != 0) continue;
-    const int ih = th / stride;
+    if (th < 0 || (stride == 2 ? (th & 1) : (th % stride)) != 0) continue;
+    const int ih = stride == 2 ? (th >> 1) : (th / stride);
     if (ih >= IH) continue;
 #pragma unroll
     for (int kw = 0; kw < 4; ++kw) {
       const int tw = ow + pad - kw;
-      if (tw < 0 || tw % stride != 0) continue;
-      const int iw = tw / stride;
+      if (tw < 0 || (stride == 2 ? (tw & 1) : (tw % stride)) != 0) continue;
+      const int iw = stride == 2 ? (tw >> 1) : (tw / stride);
       if (iw >= IW) continue;
       const float* src = cols + ((static_cast<int64_t>(b) * IH + ih) * IW + iw) * ld_cols + (kh * 4 + kw) * C + c;
       if constexpr (VEC == 4) {
@@ -87,20 +98,29 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ c
       }
     }
   }
-  const int64_t o = r * C + c;
+  const int64_t o = static_cast<int64_t>(r) * C + c;
   if (aux != nullptr) {  // backward through the Swish that produced this layer's input: multiply by Swish'(aux)
+    float a[VEC];
+    if constexpr (VEC == 4) {
+      const float4 av = __ldg(reinterpret_cast<const float4*>(aux + o));
+      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+    } else {
+      a[0] = aux[o];
+    }
 #pragma unroll
     for (int q = 0; q < VEC; ++q) {
-      const float a = aux[o + q];
-      const float s = sigmoid_f(a);
-      acc[q] *= s * (1.0f + a * (1.0f - s));
+      const float s = sigmoid_f(a[q]);
+      acc[q] *= s * (1.0f + a[q] * (1.0f - s));
     }
   }
-#pragma unroll
-  for (int q = 0; q < VEC; ++q) out[o + q] = acc[q];
-  if (out_act != nullptr) {
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) out_act[o + q] = acc[q] * sigmoid_f(acc[q]);
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(out + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    if (out_act != nullptr)
+      *reinterpret_cast<float4*>(out_act + o) = make_float4(acc[0] * sigmoid_f(acc[0]), acc[1] * sigmoid_f(acc[1]),
+                                                            acc[2] * sigmoid_f(acc[2]), acc[3] * sigmoid_f(acc[3]));
+  } else {
+    out[o] = acc[0];
+    if (out_act != nullptr) out_act[o] = acc[0] * sigmoid_f(acc[0]);
   }
 }
 
@@ -119,6 +139,7 @@ extern "C" int mvae_im2col_k4(const float* x, float* cols, int64_t ld_cols, int 
                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(cols)) & 15) == 0;
   const int OH = (H + 2 * pad - 4) / stride + 1, OW = (W + 2 * pad - 4) / stride + 1;
   const int64_t total = static_cast<int64_t>(B) * OH * OW * 16 * (v4 ? C / 4 : C);
+  if (total >= (1ll << 32) - 256) return set_error(MVAE_ERR_UNSUPPORTED, "im2col: more than 2^32 elements in one call");
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   if (v4) im2col_kernel<4><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols, stride, pad);
   else    im2col_kernel<1><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols, stride, pad);
@@ -137,9 +158,12 @@ extern "C" int mvae_col2im_k4(const float* cols, int64_t ld_cols, float* out, fl
   if (!cols || !out || B < 1 || IH < 1 || IW < 1 || C < 1 || ld_cols < 16 * C || stride < 1 || pad < 0)
     return set_error(MVAE_ERR_BAD_ARG, "col2im: bad arguments (ld_cols >= 16*C)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool v4 = (C % 4 == 0) && (ld_cols % 4 == 0) && (reinterpret_cast<uintptr_t>(cols) & 15) == 0;
+  const bool v4 = (C % 4 == 0) && (ld_cols % 4 == 0) &&
+                  ((reinterpret_cast<uintptr_t>(cols) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_act) |
+                    reinterpret_cast<uintptr_t>(aux)) & 15) == 0;
   const int OH = (IH - 1) * stride - 2 * pad + 4, OW = (IW - 1) * stride - 2 * pad + 4;
   const int64_t total = static_cast<int64_t>(B) * OH * OW * (v4 ? C / 4 : C);
+  if (total >= (1ll << 32) - 256) return set_error(MVAE_ERR_UNSUPPORTED, "col2im: more than 2^32 elements in one call");
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   if (v4) col2im_kernel<4><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C, stride, pad);
   else    col2im_kernel<1><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C, stride, pad);

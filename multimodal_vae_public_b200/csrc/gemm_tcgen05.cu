@@ -410,6 +410,38 @@ __device__ __forceinline__ void epilogue_chunk_fast(const EpiParams& e, uint32_t
   __syncwarp();  // the staging tile is rewritten by the next chunk
 }
 
+// 16-column tail chunk of an interior tile with the plain STORE epilogue (N = 48 outputs of the C = 3 conv layers: a
+// 32-column chunk + this one).  Staging rows are 64 B; float4 index row * 4 + (chunk ^ ((row >> 1) & 3)) keeps both the
+// row-wise writes and the 8-rows-x-64-B transposed reads conflict-free.
+template <bool kAtomic>
+__device__ __forceinline__ void epilogue_chunk_fast16(const EpiParams& e, uint32_t st_addr, const uint32_t (&r)[32],
+                                                      int lane, int row_base, int col0) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    sts128(st_addr + ((lane * 4 + (j ^ ((lane >> 1) & 3))) << 4), __uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+  __syncwarp();
+  const int sub = lane >> 2, cq = lane & 3;
+  const int col = col0 + 4 * cq;
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e.bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bv[q] = __ldg(e.bias + col + q);
+  }
+  float* cptr = e.C + static_cast<int64_t>(row_base + sub) * e.ldc + col;
+  const int64_t cstep = 8 * e.ldc;
+  const uint32_t rd = st_addr + (((sub * 4) + (cq ^ ((sub >> 1) & 3))) << 4);   // row 8 i + sub: + 512 B per i
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 s4 = lds128(rd + (i << 9));
+    const float v[4] = {s4.x + bv[0], s4.y + bv[1], s4.z + bv[2], s4.w + bv[3]};
+    if (kAtomic) ptx::red_add_v4_f32(cptr, v[0], v[1], v[2], v[3]);
+    else *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
+    cptr += cstep;
+  }
+  __syncwarp();  // the staging tile is rewritten by the next chunk
+}
+
 template <bool kSplit, bool kPair>
 __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
   using C = Cfg<kSplit, kPair>;
@@ -468,6 +500,20 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
       uint32_t phase = 0;
       int dn = 0;
       int tl = 0;
+      int seen[6] = {0, 0, 0, 0, 0, 0};   // dependency counters of the coming tile, read one tile ahead
+      bool peeked = false;
+      // row blocks [rb0, rb1] of the producer that hold the A rows of tile `ti` (K-major A: my row block; MN-major A,
+      // i.e. wgrad: the tile's k range)
+      auto dep_range = [&](const TileInfo& ti, const GemmProblem& p, int my_rb, const int*& ctr, int& rb0, int& rb1) {
+        rb0 = rb1 = my_rb;
+        if (p.a_mn) {
+          const int k_end = ti.kb_end * BLOCK_K < p.K ? ti.kb_end * BLOCK_K : p.K;
+          rb0 = (ti.kb_begin * BLOCK_K) / BLOCK_M;
+          rb1 = (k_end - 1) / BLOCK_M;
+        }
+        if (rb1 >= p.dep_row_blocks) rb1 = p.dep_row_blocks - 1;  // (pair mode: the peer's rows may lie beyond M)
+        ctr = batch.ws + WS_CTR0 + p.dep_ctr_base;
+      };
       dbg_stamp(batch, 0, dn);
       for (int t = tile0; t < batch.total_tiles; t += tile_step, ++tl) {
         const TileInfo ti = decode_tile(batch, t);
@@ -483,24 +529,20 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
         const uint32_t a_bytes = OPERAND_BYTES;
         const uint32_t b_bytes = static_cast<uint32_t>(n_mine) * BLOCK_K * 4;
         if (batch.ws != nullptr && p.dep >= 0) {
-          // chain mode: the rows of A this tile reads are produced by earlier tiles of this same launch
-          int rb0 = my_rb, rb1 = my_rb;                             // K-major A: my row block
-          if (a_mn) {                                               // MN-major A (wgrad): my k range = producer rows
-            const int k_end = ti.kb_end * BLOCK_K < p.K ? ti.kb_end * BLOCK_K : p.K;
-            rb0 = (ti.kb_begin * BLOCK_K) / BLOCK_M;
-            rb1 = (k_end - 1) / BLOCK_M;
-          }
-          const int* ctr = batch.ws + WS_CTR0 + p.dep_ctr_base;
-          if (rb1 >= p.dep_row_blocks) rb1 = p.dep_row_blocks - 1;  // (pair mode: the peer's rows may lie beyond M)
+          // chain mode: the rows of A this tile reads are produced by earlier tiles of this same launch.
           // Fast check first: the producers are usually long done, and the acquire loads of the slow path cost ~0.5 us
           // EACH (measured 1.1 us per tile for one row block, 2.1 us for the four of a wgrad tile -- the TMA pipeline ran
-          // dry at every tile boundary).  Relaxed gpu-scope loads read the counters at L2, all in flight together; the
-          // operands themselves are then fetched by TMA from L2 (never through this SM's L1), after the proxy fence.
-          const int nrb = rb1 - rb0 + 1;
-          int seen[6];
+          // dry at every tile boundary).  Relaxed gpu-scope loads read the counters at L2, all in flight together, and
+          // they were already issued while the PREVIOUS tile's loads were being enqueued (peek below); the operands
+          // themselves are then fetched by TMA from L2 (never through this SM's L1).
+          const int* ctr; int rb0, rb1;
+          dep_range(ti, p, my_rb, ctr, rb0, rb1);
+          if (!peeked) {
 #pragma unroll
-          for (int j = 0; j < 6; ++j) seen[j] = (j < nrb) ? ld_relaxed_gpu(ctr + rb0 + j) : p.dep_target;
-          bool all_done = nrb <= 6;
+            for (int j = 0; j < 6; ++j)   // unconditional loads (index clamped): nothing consumes the value until the check
+              seen[j] = ld_relaxed_gpu(ctr + (rb0 + j <= rb1 ? rb0 + j : rb1));
+          }
+          bool all_done = rb1 - rb0 < 6;
 #pragma unroll
           for (int j = 0; j < 6; ++j) all_done = all_done && seen[j] >= p.dep_target;
           // (No proxy fence on this side in the fast path: the writers ordered their generic-proxy stores against the async
@@ -509,6 +551,20 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           if (!all_done) {
             for (int rb = rb0; rb <= rb1; ++rb) wait_row_block(ctr + rb, p.dep_target, batch.ws);
             fence_proxy_async_all();
+          }
+        }
+        // peek at the NEXT tile's dependencies now; the values are looked at one tile later (counters only grow)
+        peeked = false;
+        if (batch.ws != nullptr && t + tile_step < batch.total_tiles) {
+          const TileInfo tn = decode_tile(batch, t + tile_step);
+          const GemmProblem& pn = batch.p[tn.prob];
+          if (pn.dep >= 0) {
+            const int* ctr; int rb0, rb1;
+            dep_range(tn, pn, kPair ? 2 * tn.m_blk + static_cast<int>(rank) : tn.m_blk, ctr, rb0, rb1);
+#pragma unroll
+            for (int j = 0; j < 6; ++j)   // unconditional loads (index clamped): nothing consumes the value until the check
+              seen[j] = ld_relaxed_gpu(ctr + (rb0 + j <= rb1 ? rb0 + j : rb1));
+            peeked = true;
           }
         }
         if (batch.tilelog != nullptr) tilelog(batch, tl, 2, globaltimer_ns());
@@ -726,6 +782,11 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
             epilogue_chunk_fast<MVAE_EPI_STORE, false, true>(e, st_addr, r, lane, row_base, n0 + c0, bv, auxv);
           else
             epilogue_chunk_fast<MVAE_EPI_STORE, false, false>(e, st_addr, r, lane, row_base, n0 + c0, bv, auxv);
+        } else if (rows_inside && ncols == 16 && n0 + c0 + 16 <= e.N && e.epilogue == MVAE_EPI_STORE &&
+                   e.colsum == nullptr) {
+          const uint32_t st_addr = ptx::smem_u32(stage_buf);
+          if (e.atomic) epilogue_chunk_fast16<true>(e, st_addr, r, lane, row_base, n0 + c0);
+          else epilogue_chunk_fast16<false>(e, st_addr, r, lane, row_base, n0 + c0);
         } else {
           epilogue_chunk(e, stage_buf, r, ncols, lane, row_base, n0 + c0, bv, a0, batch.dbg_flags);
         }

@@ -16,36 +16,67 @@
 namespace mvae {
 namespace {
 
-constexpr int kRowsPerBlock = 128;
 constexpr int kMaxSeg = 32;
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU sigmoid (ex2.approx + rcp.approx): the IEEE expf + division version made these kernels instruction-bound.
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 
-// grid = (S * chunks_per_seg, ceil(C/32)); block = 32 columns x 8 row lanes
+// Rows of a segment handled by one block of the column reductions.  The first version used 128 rows: one activation
+// tensor of the CelebA decoder ([3B*32*32, 32] at B = 1024: 3.1 M rows) then became 24 K blocks x 64 double atomics on
+// 192 addresses.  Sized here so that the launch has ~6 blocks per SM, each streaming >= 256 rows with 128-bit loads.
+int rows_per_block(int S, int seg_rows, int C) {
+  const int col_groups = (C + 31) / 32;
+  int sms = mvae_device_sm_count();
+  if (sms <= 0) sms = 148;
+  const int64_t target = 6ll * sms;                                  // blocks in the whole launch
+  int64_t chunks = target / (static_cast<int64_t>(S) * col_groups);  // chunks per segment
+  if (chunks < 1) chunks = 1;
+  int64_t rows = (seg_rows + chunks - 1) / chunks;
+  if (rows < 256) rows = 256;
+  rows = (rows + 31) / 32 * 32;
+  return static_cast<int>(rows);
+}
+
+// Block = 8 column groups (float4) x 32 row lanes over a 32-column slab.  Shared reduction of two partial sums per
+// column over the 32 row lanes; thread c < 32 issues the two double atomics of its column.
+__device__ __forceinline__ void block_colsum2(float (&a)[4], float (&b)[4], int cg, int rl, int c0, int C, double* acc_seg) {
+  __shared__ float s1[32][33], s2[32][33];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { s1[rl][cg * 4 + q] = a[q]; s2[rl][cg * 4 + q] = b[q]; }
+  __syncthreads();
+  if (threadIdx.x < 32 && c0 + threadIdx.x < C) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) { ta += s1[i][threadIdx.x]; tb += s2[i][threadIdx.x]; }
+    atomicAdd(acc_seg + (c0 + threadIdx.x) * 2, ta);
+    atomicAdd(acc_seg + (c0 + threadIdx.x) * 2 + 1, tb);
+  }
+}
+
+// grid = (S * chunks_per_seg, ceil(C/32)); block = 8 float4 column groups x 32 row lanes (C % 4 == 0)
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int64_t ld, int seg_rows, int C,
-                                                       int chunks_per_seg, double* __restrict__ acc /*[S][C][2]*/) {
-  __shared__ float s1[8][33], s2[8][33];
-  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int rl = threadIdx.x >> 5;
+                                                       int chunks_per_seg, int rows_per_chunk,
+                                                       double* __restrict__ acc /*[S][C][2]*/) {
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 32, c = c0 + cg * 4;
   const int seg = blockIdx.x / chunks_per_seg, chunk = blockIdx.x % chunks_per_seg;
-  const int r0 = chunk * kRowsPerBlock, r1 = min(seg_rows, r0 + kRowsPerBlock);
-  float a = 0.f, b = 0.f;
+  const int r0 = chunk * rows_per_chunk, r1 = min(seg_rows, r0 + rows_per_chunk);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < C) {
     const float* base = x + (static_cast<int64_t>(seg) * seg_rows) * ld + c;
-    for (int r = r0 + rl; r < r1; r += 8) {
-      const float v = base[static_cast<int64_t>(r) * ld];
-      a += v; b += v * v;
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 32) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + static_cast<int64_t>(r) * ld));
+      a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+      b[0] += v.x * v.x; b[1] += v.y * v.y; b[2] += v.z * v.z; b[3] += v.w * v.w;
     }
   }
-  s1[rl][threadIdx.x & 31] = a; s2[rl][threadIdx.x & 31] = b;
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    double ta = 0.0, tb = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { ta += s1[i][threadIdx.x & 31]; tb += s2[i][threadIdx.x & 31]; }
-    atomicAdd(acc + (static_cast<int64_t>(seg) * C + c) * 2, ta);
-    atomicAdd(acc + (static_cast<int64_t>(seg) * C + c) * 2 + 1, tb);
-  }
+  block_colsum2(a, b, cg, rl, c0, C, acc + static_cast<int64_t>(seg) * C * 2);
 }
 
 struct BnOrder {
@@ -97,11 +128,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        int rows, int seg_rows, int C4, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, int act) {
-  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= static_cast<int64_t>(rows) * C4) return;
-  const int r = static_cast<int>(gid / C4);
-  const int c = static_cast<int>(gid - static_cast<int64_t>(r) * C4) * 4;
-  const int s = r / seg_rows;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit index math (host checks the range)
+  if (gid >= static_cast<unsigned>(rows) * static_cast<unsigned>(C4)) return;
+  const int r = static_cast<int>(gid / static_cast<unsigned>(C4));
+  const int c = static_cast<int>(gid - static_cast<unsigned>(r) * static_cast<unsigned>(C4)) * 4;
+  const int s = static_cast<int>(static_cast<unsigned>(r) / static_cast<unsigned>(seg_rows));
   const int C = C4 * 4;
   const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * ldx + c);
   const float4 m = *reinterpret_cast<const float4*>(mean + s * C + c);
@@ -120,39 +151,42 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 // da = dh * swish'(a), a = gamma*xhat + beta ; per (segment, channel): acc2 += {sum da, sum da*xhat}
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ x, int64_t ldx,
                                                             const float* __restrict__ dh, int64_t lddh, int seg_rows, int C,
-                                                            int chunks_per_seg, int seg0, const float* __restrict__ mean,
-                                                            const float* __restrict__ invstd,
+                                                            int chunks_per_seg, int rows_per_chunk, int seg0,
+                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             int act, double* __restrict__ acc2 /*[S][C][2]*/) {
-  __shared__ float s1[8][33], s2[8][33];
-  const int c = blockIdx.y * 32 + (threadIdx.x & 31);
-  const int rl = threadIdx.x >> 5;
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 32, c = c0 + cg * 4;
   const int seg = seg0 + blockIdx.x / chunks_per_seg, chunk = blockIdx.x % chunks_per_seg;
-  const int r0 = chunk * kRowsPerBlock, r1 = min(seg_rows, r0 + kRowsPerBlock);
-  float a1 = 0.f, a2 = 0.f;
+  const int r0 = chunk * rows_per_chunk, r1 = min(seg_rows, r0 + rows_per_chunk);
+  float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    const float m = mean[seg * C + c], is = invstd[seg * C + c], g = gamma[c], b = beta[c];
+    const float4 m4 = *reinterpret_cast<const float4*>(mean + seg * C + c);
+    const float4 i4 = *reinterpret_cast<const float4*>(invstd + seg * C + c);
+    const float4 g4 = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 b4 = *reinterpret_cast<const float4*>(beta + c);
+    const float m[4] = {m4.x, m4.y, m4.z, m4.w}, is[4] = {i4.x, i4.y, i4.z, i4.w};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
     const int64_t row0 = static_cast<int64_t>(seg) * seg_rows;
-    for (int r = r0 + rl; r < r1; r += 8) {
-      const float xh = (x[(row0 + r) * ldx + c] - m) * is;
-      float d = dh[(row0 + r) * lddh + c];
-      if (act) {
-        const float a = g * xh + b;
-        const float sg = sigmoid_f(a);
-        d *= sg * (1.0f + a * (1.0f - sg));
+#pragma unroll 2
+    for (int r = r0 + rl; r < r1; r += 32) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * ldx + c));
+      const float4 dv = __ldg(reinterpret_cast<const float4*>(dh + (row0 + r) * lddh + c));
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      float d[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xh = (xs[q] - m[q]) * is[q];
+        if (act) {
+          const float a = g[q] * xh + bt[q];
+          const float sg = sigmoid_f(a);
+          d[q] *= sg * (1.0f + a * (1.0f - sg));
+        }
+        a1[q] += d[q]; a2[q] += d[q] * xh;
       }
-      a1 += d; a2 += d * xh;
     }
   }
-  s1[rl][threadIdx.x & 31] = a1; s2[rl][threadIdx.x & 31] = a2;
-  __syncthreads();
-  if (rl == 0 && c < C) {
-    double ta = 0.0, tb = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { ta += s1[i][threadIdx.x & 31]; tb += s2[i][threadIdx.x & 31]; }
-    atomicAdd(acc2 + (static_cast<int64_t>(seg) * C + c) * 2, ta);
-    atomicAdd(acc2 + (static_cast<int64_t>(seg) * C + c) * 2 + 1, tb);
-  }
+  block_colsum2(a1, a2, cg, rl, c0, C, acc2 + static_cast<int64_t>(seg) * C * 2);
 }
 
 // dgamma[c] += sum_seg sum(da*xhat), dbeta[c] += sum_seg sum(da) over the live segments [seg0, seg0+nseg)
@@ -175,21 +209,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            int act, const double* __restrict__ acc2, int batch_stats) {
-  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= static_cast<int64_t>(rows) * C4) return;
-  const int r = row_begin + static_cast<int>(gid / C4);
-  const int c = static_cast<int>(gid % C4) * 4;
-  const int s = r / seg_rows;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;   // 32-bit index math (host checks the range)
+  if (gid >= static_cast<unsigned>(rows) * static_cast<unsigned>(C4)) return;
+  const unsigned rq = gid / static_cast<unsigned>(C4);
+  const int r = row_begin + static_cast<int>(rq);
+  const int c = static_cast<int>(gid - rq * static_cast<unsigned>(C4)) * 4;
+  const int s = static_cast<int>(static_cast<unsigned>(r) / static_cast<unsigned>(seg_rows));
   const int C = C4 * 4;
   const float inv_n = 1.0f / static_cast<float>(seg_rows);
   const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<int64_t>(r) * ldx + c);
   const float4 dv = *reinterpret_cast<const float4*>(dh + static_cast<int64_t>(r) * lddh + c);
   const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
   const float ds[4] = {dv.x, dv.y, dv.z, dv.w};
+  const float4 m4 = *reinterpret_cast<const float4*>(mean + s * C + c);
+  const float4 i4 = *reinterpret_cast<const float4*>(invstd + s * C + c);
+  const float4 g4 = *reinterpret_cast<const float4*>(gamma + c);
+  const float4 b4 = *reinterpret_cast<const float4*>(beta + c);
+  const float ms[4] = {m4.x, m4.y, m4.z, m4.w}, iss[4] = {i4.x, i4.y, i4.z, i4.w};
+  const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w};
   float out[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float m = mean[s * C + c + q], is = invstd[s * C + c + q], g = gamma[c + q], b = beta[c + q];
+    const float m = ms[q], is = iss[q], g = gs[q], b = bs[q];
     const float xh = (xs[q] - m) * is;
     float d = ds[q];
     if (act) {
@@ -261,11 +302,14 @@ using namespace mvae;
 #define ST(stream) reinterpret_cast<cudaStream_t>(stream)
 
 extern "C" int mvae_bn_stats(const float* x, int64_t ldx, int S, int seg_rows, int C, double* acc, void* stream) {
-  if (!x || !acc || S < 1 || S > kMaxSeg || seg_rows < 1 || C < 1) return set_error(MVAE_ERR_BAD_ARG, "bn_stats: bad args");
-  const int chunks = (seg_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  if (!x || !acc || S < 1 || S > kMaxSeg || seg_rows < 1 || C < 1 || (C & 3) || (ldx & 3) ||
+      (reinterpret_cast<uintptr_t>(x) & 15))
+    return set_error(MVAE_ERR_BAD_ARG, "bn_stats: bad args (C, ldx multiples of 4, x 16-byte aligned)");
+  const int rpb = rows_per_block(S, seg_rows, C);
+  const int chunks = (seg_rows + rpb - 1) / rpb;
   MVAE_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * S * C, ST(stream)));
   dim3 grid(S * chunks, (C + 31) / 32);
-  bn_stats_kernel<<<grid, 256, 0, ST(stream)>>>(x, ldx, seg_rows, C, chunks, acc);
+  bn_stats_kernel<<<grid, 256, 0, ST(stream)>>>(x, ldx, seg_rows, C, chunks, rpb, acc);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
@@ -318,11 +362,12 @@ extern "C" int mvae_bn_bwd(const float* x, int64_t ldx, const float* dh, int64_t
   if (!x || !dh || !dx || !acc2 || !dgamma || !dbeta || S < 1 || S > kMaxSeg || seg0 < 0 || nseg < 1 || seg0 + nseg > S ||
       (C & 3) || (ldx & 3) || (lddh & 3) || (lddx & 3))
     return set_error(MVAE_ERR_BAD_ARG, "bn_bwd: bad args");
-  const int chunks = (seg_rows + kRowsPerBlock - 1) / kRowsPerBlock;
+  const int rpb = rows_per_block(nseg, seg_rows, C);
+  const int chunks = (seg_rows + rpb - 1) / rpb;
   MVAE_CUDA_CHECK(cudaMemsetAsync(acc2, 0, sizeof(double) * 2 * S * C, ST(stream)));
   dim3 grid(nseg * chunks, (C + 31) / 32);
-  bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(x, ldx, dh, lddh, seg_rows, C, chunks, seg0, mean, invstd, gamma, beta,
-                                                     swish_act, acc2);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, ST(stream)>>>(x, ldx, dh, lddh, seg_rows, C, chunks, rpb, seg0, mean, invstd, gamma,
+                                                     beta, swish_act, acc2);
   bn_bwd_params_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(acc2, C, seg0, nseg, dgamma, dbeta);
   const int rows = nseg * seg_rows;
   const int64_t n = static_cast<int64_t>(rows) * (C / 4);

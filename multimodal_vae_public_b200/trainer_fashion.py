@@ -218,8 +218,8 @@ class FashionMVAETrainer(MnistMVAETrainer):
         B, L, P = self.B, self.L, self.prec
         p, g = self.params, self.grads
 
-        def split_for(rows):   # ~16 k-blocks (512 rows) per wgrad tile
-            return max(1, min(rows // 512, 64))
+        def split_for(rows):   # ~16 k-blocks (512 rows) per wgrad tile, as many tiles as the reduction needs
+            return max(1, min(rows // 512, 4096))
 
         ops.bce_logits_fwd_bwd(self.logit_i, self.x, self.logit_i, self.lam_i / b_global, self.acc[0:3], seg_rows=B)
         ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)

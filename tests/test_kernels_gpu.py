@@ -28,7 +28,7 @@ TOL = {0: 3e-3, 1: 2e-5}
 
 @pytest.mark.parametrize("prec", [0, 1])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (512, 512, 784), (300, 10, 512), (1000, 128, 512), (8, 512, 64),
-                                   (4096, 784, 512)])
+                                   (4096, 784, 512), (1024, 48, 32), (640, 16, 64), (256, 176, 96)])
 def test_linear_fwd(ops, prec, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     x = torch.randn(M, K, device="cuda", generator=g); w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
@@ -69,6 +69,7 @@ def test_linear_dgrad(ops, prec, M, N, K):
 
 @pytest.mark.parametrize("prec", [0, 1])
 @pytest.mark.parametrize("M,N,K,split", [(32, 128, 128, 1), (2048, 512, 784, 5), (1000, 10, 512, 3), (4096, 512, 64, 8),
+                                         (4096, 256, 48, 4), (65536, 48, 32, 64),
                                          (8192, 128, 512, 16)])
 def test_linear_wgrad(ops, prec, M, N, K, split):
     g = torch.Generator(device="cuda").manual_seed(M + N * 7 + K)
