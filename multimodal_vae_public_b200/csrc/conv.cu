@@ -57,6 +57,35 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x
   }
 }
 
+// Channel counts that are not a multiple of 4 (the RGB layers, C = 3): one thread still WRITES one float4 of the
+// [pixels, 16*C] matrix (rows are 16*C floats, always a multiple of 4) and gathers its four scalars; the scalar-store
+// version ran at 0.7 TB/s.
+__global__ void __launch_bounds__(256) im2col_anyc_kernel(const float* __restrict__ x, float* __restrict__ cols, int B, int H,
+                                                          int W, int C, int64_t ld_cols, int stride, int pad) {
+  const unsigned OH = (H + 2 * pad - 4) / stride + 1, OW = (W + 2 * pad - 4) / stride + 1;
+  const unsigned rv = 4u * C;                          // float4 per row
+  const unsigned total = static_cast<unsigned>(B) * OH * OW * rv;
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const unsigned r = gid / rv;                         // output pixel index m = (b*OH + oh)*OW + ow
+  const unsigned j = gid - r * rv;
+  const unsigned r2 = r / OW;
+  const int ow = static_cast<int>(r - r2 * OW);
+  const unsigned bq = r2 / OH;
+  const int oh = static_cast<int>(r2 - bq * OH);
+  const float* xb = x + static_cast<int64_t>(bq) * H * W * C;
+  float v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const unsigned e = 4u * j + q;
+    const unsigned tap = e / static_cast<unsigned>(C);
+    const int c = static_cast<int>(e - tap * C);
+    const int ih = stride * oh - pad + static_cast<int>(tap >> 2), iw = stride * ow - pad + static_cast<int>(tap & 3);
+    v[q] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? __ldg(xb + (static_cast<int64_t>(ih) * W + iw) * C + c) : 0.f;
+  }
+  *reinterpret_cast<float4*>(cols + static_cast<int64_t>(r) * ld_cols + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // out[b, oh, ow, c] = sum over taps (kh,kw) with oh = 2*ih - 1 + kh, ow = 2*iw - 1 + kw of cols[(b,ih,iw), (kh,kw,c)]
 template <int VEC>
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ cols, int64_t ld_cols, float* out,
@@ -124,6 +153,53 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ c
   }
 }
 
+// C <= 4 and not a multiple of 4 (RGB): one thread = one output PIXEL (all its channels), instead of one thread per
+// scalar -- a third of the threads and of the index arithmetic, adjacent loads per tap.
+__global__ void __launch_bounds__(256) col2im_smallc_kernel(const float* __restrict__ cols, int64_t ld_cols, float* out,
+                                                            float* out_act, const float* __restrict__ aux, int B, int IH,
+                                                            int IW, int C, int stride, int pad) {
+  const unsigned OH = (IH - 1) * stride - 2 * pad + 4, OW = (IW - 1) * stride - 2 * pad + 4;
+  const unsigned total = static_cast<unsigned>(B) * OH * OW;
+  const unsigned r = blockIdx.x * blockDim.x + threadIdx.x;   // output pixel
+  if (r >= total) return;
+  const unsigned r2 = r / OW;
+  const int ow = static_cast<int>(r - r2 * OW);
+  const unsigned bq = r2 / OH;
+  const int oh = static_cast<int>(r2 - bq * OH);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kh = 0; kh < 4; ++kh) {
+    const int th = oh + pad - kh;
+    if (th < 0 || (stride == 2 ? (th & 1) : (th % stride)) != 0) continue;
+    const int ih = stride == 2 ? (th >> 1) : (th / stride);
+    if (ih >= IH) continue;
+#pragma unroll
+    for (int kw = 0; kw < 4; ++kw) {
+      const int tw = ow + pad - kw;
+      if (tw < 0 || (stride == 2 ? (tw & 1) : (tw % stride)) != 0) continue;
+      const int iw = stride == 2 ? (tw >> 1) : (tw / stride);
+      if (iw >= IW) continue;
+      const float* src = cols + ((static_cast<int64_t>(bq) * IH + ih) * IW + iw) * ld_cols + (kh * 4 + kw) * C;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) acc[c] += __ldg(src + c);
+    }
+  }
+  const int64_t o = static_cast<int64_t>(r) * C;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= C) break;
+    float v = acc[c];
+    if (aux != nullptr) {
+      const float a = aux[o + c];
+      const float sg = sigmoid_f(a);
+      v *= sg * (1.0f + a * (1.0f - sg));
+    }
+    out[o + c] = v;
+    if (out_act != nullptr) out_act[o + c] = v * sigmoid_f(v);
+  }
+}
+
 }  // namespace
 }  // namespace mvae
 
@@ -141,7 +217,10 @@ extern "C" int mvae_im2col_k4(const float* x, float* cols, int64_t ld_cols, int 
   const int64_t total = static_cast<int64_t>(B) * OH * OW * 16 * (v4 ? C / 4 : C);
   if (total >= (1ll << 32) - 256) return set_error(MVAE_ERR_UNSUPPORTED, "im2col: more than 2^32 elements in one call");
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  const bool out4 = (ld_cols % 4 == 0) && (reinterpret_cast<uintptr_t>(cols) & 15) == 0;
   if (v4) im2col_kernel<4><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols, stride, pad);
+  else if (out4) im2col_anyc_kernel<<<static_cast<unsigned>((total / 4 + 255) / 256), 256, 0, st>>>(x, cols, B, H, W, C, ld_cols,
+                                                                                                 stride, pad);
   else    im2col_kernel<1><<<blocks, 256, 0, st>>>(x, cols, B, H, W, C, ld_cols, stride, pad);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
@@ -166,6 +245,9 @@ extern "C" int mvae_col2im_k4(const float* cols, int64_t ld_cols, float* out, fl
   if (total >= (1ll << 32) - 256) return set_error(MVAE_ERR_UNSUPPORTED, "col2im: more than 2^32 elements in one call");
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   if (v4) col2im_kernel<4><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C, stride, pad);
+  else if (C <= 4)
+    col2im_smallc_kernel<<<static_cast<unsigned>((total / C + 255) / 256), 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH,
+                                                                                       IW, C, stride, pad);
   else    col2im_kernel<1><<<blocks, 256, 0, st>>>(cols, ld_cols, out, out_act, aux, B, IH, IW, C, stride, pad);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
