@@ -230,6 +230,26 @@ int mvae_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW, void* stre
 int mvae_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_mult_dev,
                    float beta1, float beta2, float eps, float grad_scale, int32_t* step_count, void* stream);
 
+/* The data-parallel exchange step as ONE kernel per rank over NVLink peer memory (the reference
+ * is single-process, mnist/train.py:196-219): gradient reduce-scatter by peer loads -> Adam on this rank's 1/world slice
+ * -> parameter all-gather by peer stores, with the two rendezvous points done through flags in peer-mapped memory.
+ * Replaces ncclAllReduce(gradient bucket) + mvae_adam_flat.
+ *   grad_ptrs[world]  : HOST array of peer-mapped device pointers, rank order; each bucket holds n gradients followed by
+ *                       `tail` extra floats (the loss scalars), all produced by the caller's backward pass on `stream`
+ *   param_ptrs[world] : peer-mapped parameter buckets (n floats); every rank ends up with identical updated values
+ *   flag_ptrs[world]  : peer-mapped uint32 arrays of >= 2*world + 3 words, zero-initialised once on every rank BEFORE any
+ *                       rank's first call ([0,world) "gradients final", [world,2world) "stores done", [2world] sticky
+ *                       error, [2world+1] scratch, [2world+2] launch counter = flag epoch)
+ *   m, v              : this rank's Adam moments, full length n (only the rank's slice is touched)
+ *   tail_out          : [tail] sums over ranks of the tail floats (each rank computes them for itself)
+ *   step_count        : device int32 Adam step counter; read by the kernel, incremented at its end (the launch can sit
+ *                       in a CUDA graph that is replayed every step)
+ * Every rank of the group must enqueue the call once per step (it spins, bounded at ~17 s, until the peers arrive). */
+int mvae_allreduce_adam_p2p(float* const* grad_ptrs, float* const* param_ptrs, uint32_t* const* flag_ptrs, float* m,
+                            float* v, int64_t n, int tail, float* tail_out, int rank, int world, float lr,
+                            const float* lr_mult_dev, float beta1, float beta2, float eps, int32_t* step_count,
+                            void* stream);
+
 /* elbo = sum_p ( recon_img[p] * lambda_image + recon_txt[p] * lambda_text + beta * kl[p] ) / B
  * from the double accumulators above -> float32 out[0] = total, out[1..P] per pass
  * (mnist/train.py:57-58,214); beta_dev: optional device float multiplying beta.                    */

@@ -568,6 +568,13 @@ __global__ void swish_bwd_kernel(const float* __restrict__ x, const float* __res
 }
 
 // ---------------------------------------------------------------- embedding + swish
+// MUFU sigmoid (ex2.approx + rcp.approx, relative error ~(2 + |x|) * 2^-23) for the bandwidth-bound kernels
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 __global__ void emb_swish_fwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx, float* a,
                                      float* h, int B, int D4) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -576,13 +583,13 @@ __global__ void emb_swish_fwd_kernel(const float* __restrict__ table, const int6
   const int c = static_cast<int>(i - static_cast<int64_t>(b) * D4);
   const float4 v = __ldg(reinterpret_cast<const float4*>(table) + idx[b] * D4 + c);
   if (a != nullptr) reinterpret_cast<float4*>(a)[i] = v;
-  reinterpret_cast<float4*>(h)[i] =
-      make_float4(v.x * sigmoid_f(v.x), v.y * sigmoid_f(v.y), v.z * sigmoid_f(v.z), v.w * sigmoid_f(v.w));
+  reinterpret_cast<float4*>(h)[i] = make_float4(v.x * sigmoid_fast(v.x), v.y * sigmoid_fast(v.y), v.z * sigmoid_fast(v.z),
+                                                v.w * sigmoid_fast(v.w));
 }
 // Embedding backward through Swish = segmented row sum by class (only V rows receive gradient).
 // grid = (ceil(D/128), row chunks of kEmbRows); block = 128 threads (one column each); per-class partial sums
 // live in shared memory, one atomic per (class, column) per block.
-constexpr int kEmbRows = 128;
+constexpr int kEmbRows = 32;   // 128 rows per block left 128 blocks x 4 warps on the machine: 25 us of exposed DRAM latency
 constexpr int kEmbMaxV = 32;
 __global__ void __launch_bounds__(128) emb_swish_bwd_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
                                                             const float* __restrict__ dh, int64_t lddh, float* dtable,
@@ -595,8 +602,15 @@ __global__ void __launch_bounds__(128) emb_swish_bwd_kernel(const float* __restr
   for (int r = r0 + threadIdx.x; r < r1; r += 128) sidx[r - r0] = static_cast<int>(idx[r]);
   __syncthreads();
   if (d < D) {
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) acc[sidx[r - r0]][threadIdx.x] += dh[static_cast<int64_t>(r) * lddh + d];
+    // all loads of a group of 8 rows in flight before the shared-memory accumulation
+    for (int rb = r0; rb < r1; rb += 8) {
+      float v8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v8[j] = (rb + j < r1) ? __ldg(dh + static_cast<int64_t>(rb + j) * lddh + d) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (rb + j < r1) acc[sidx[rb + j - r0]][threadIdx.x] += v8[j];
+    }
     for (int v = 0; v < V; ++v) {
       const float s = acc[v][threadIdx.x];
       if (s != 0.f) atomicAdd(dtable + static_cast<int64_t>(v) * D + d, s * dswish_f(table[static_cast<int64_t>(v) * D + d]));

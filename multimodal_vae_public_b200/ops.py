@@ -257,3 +257,13 @@ def adam_flat(p, g, m, v, step_count, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8,
 def elbo_finalize(recon_img, recon_txt, kl, P, lambda_image, lambda_text, beta, inv_batch, out, beta_dev=None):
     _lib.check(_lib.load().mvae_elbo_finalize(_p(recon_img), _p(recon_txt), _p(kl), P, lambda_image, lambda_text, beta,
                                               _p(beta_dev), inv_batch, out.data_ptr(), _stream()), "mvae_elbo_finalize")
+
+
+def allreduce_adam_p2p(grad_ptrs, param_ptrs, flag_ptrs, m, v, n, tail, tail_out, rank, world, step_count, lr,
+                       lr_mult_dev=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    """Fused NVLink reduce-scatter + Adam + all-gather (one launch per rank); the pointer lists are the peer-mapped base
+    addresses of every rank's gradient / parameter / flag buffers in rank order (see include/mvae_b200.h)."""
+    arr = lambda ptrs: (C.c_void_p * len(ptrs))(*[int(x) for x in ptrs])  # noqa: E731
+    _lib.check(_lib.load().mvae_allreduce_adam_p2p(arr(grad_ptrs), arr(param_ptrs), arr(flag_ptrs), m.data_ptr(), v.data_ptr(),
+                                                   n, tail, _p(tail_out), rank, world, lr, _p(lr_mult_dev), beta1, beta2,
+                                                   eps, step_count.data_ptr(), _stream()), "mvae_allreduce_adam_p2p")

@@ -71,7 +71,8 @@ def mnist_reference_order(n_latents: int) -> List[str]:
 class FlatArena:
     """One contiguous fp32 bucket with named, 16-byte aligned views."""
 
-    def __init__(self, layout: Sequence[Tuple[str, Tuple[int, ...]]], device, n_buffers: int = 1, tail: int = 0):
+    def __init__(self, layout: Sequence[Tuple[str, Tuple[int, ...]]], device, n_buffers: int = 1, tail: int = 0,
+                 alloc=None):
         self.offsets: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
         off = 0
         for name, shape in layout:
@@ -81,7 +82,11 @@ class FlatArena:
         self.numel = off
         # `tail` extra floats after the parameters (the gradient bucket carries the loss scalars there so that ONE
         # all-reduce moves gradients and loss)
-        self.buffers = [torch.zeros(off + tail, dtype=torch.float32, device=device) for _ in range(n_buffers)]
+        # `alloc(i, numel)` may supply buffer i (e.g. from NVLink-symmetric memory) -- it must come back zeroed
+        self.buffers = []
+        for i in range(n_buffers):
+            t = alloc(i, off + tail) if alloc is not None else None
+            self.buffers.append(t if t is not None else torch.zeros(off + tail, dtype=torch.float32, device=device))
 
     def view(self, buf: int, name: str) -> torch.Tensor:
         off, shape = self.offsets[name]
@@ -100,7 +105,7 @@ class MnistMVAETrainer:
     def __init__(self, n_latents: int = 64, batch_size: int = 4096, device="cuda", lr: float = 1e-3,
                  lambda_image: float = 1.0, lambda_text: float = 10.0, precision: int = PREC_3XTF32,
                  world_size: int = 1, seed: int = 0, rank: int = 0, use_graph: bool = True,
-                 process_group=None, chain: Optional[bool] = None):
+                 process_group=None, chain: Optional[bool] = None, dp_mode: Optional[str] = None):
         _lib.load()  # fail loudly if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _lib.MvaeError("MnistMVAETrainer needs a CUDA device (no CPU fallback)")
@@ -118,7 +123,16 @@ class MnistMVAETrainer:
         self.chain = os.environ.get("MVAE_CHAIN", "1") != "0" if chain is None else bool(chain)
         self.chain_ws = ops.chain_workspace(torch.device(device))
         self.layout = self._make_layout(n_latents)
-        self.arena = FlatArena(self.layout, self.dev, n_buffers=4, tail=4)  # params, grads(+loss tail), adam m, adam v
+        # Data-parallel exchange: "p2p" = ONE fused kernel per rank over NVLink peer memory (gradient reduce-scatter ->
+        # Adam on the rank's slice -> parameter all-gather, csrc/dp_p2p.cu); "nccl" = ncclAllReduce + flat Adam.
+        self.dp_mode = "none"
+        if world_size > 1:
+            self.dp_mode = os.environ.get("MVAE_DP", "p2p") if dp_mode is None else dp_mode
+            if self.dp_mode == "p2p" and not self._p2p_possible():
+                self.dp_mode = "nccl"
+        self._symm = {}
+        self.arena = FlatArena(self.layout, self.dev, n_buffers=4, tail=4,   # params, grads(+loss tail), adam m, adam v
+                               alloc=self._symm_alloc if self.dp_mode == "p2p" else None)
         self.params = {k: self.arena.view(0, k) for k, _ in self.layout}
         self.grads = {k: self.arena.view(1, k) for k, _ in self.layout}
         n = self.arena.numel
@@ -141,7 +155,10 @@ class MnistMVAETrainer:
         # one zero-initialised region per step: dZ + loss accumulators
         self.dZ = torch.zeros(3 * B, L, dtype=torch.float32, device=dev)
         self.acc = torch.zeros(9, dtype=torch.float64, device=dev)  # recon_img[3], recon_txt[3], kl[3]
-        self.loss_out = self.grad_bucket[n:n + 4]           # total, internal passes 0..2 (tail of the gradient bucket)
+        self.loss_tail = self.grad_bucket[n:n + 4]          # total, internal passes 0..2 (tail of the gradient bucket)
+        self.loss_out = self.loss_tail                      # what is copied to the host (the sums over ranks)
+        if self.dp_mode == "p2p":
+            self._p2p_finish_setup(n, 4)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.beta_dev = torch.ones(1, dtype=torch.float32, device=dev)   # KL annealing factor
         self.beta_host = torch.ones(1, dtype=torch.float32).pin_memory()
@@ -357,21 +374,75 @@ class MnistMVAETrainer:
         self._enqueue_forward(training, use_noise_input)
         self._enqueue_loss_and_backward(training, b_global)
         ops.elbo_finalize(self.acc[0:3], self.acc[3:6], self.acc[6:9], 3, self.lam_i, self.lam_t, 1.0, 1.0 / b_global,
-                          self.loss_out, beta_dev=self.beta_dev)
+                          self.loss_tail, beta_dev=self.beta_dev)
 
-    def _enqueue_allreduce(self) -> None:
+    def _enqueue_allreduce(self, update: bool = True) -> None:
         """The one exchange step of the data-parallel path: SUM all-reduce of the flat gradient bucket (+ loss tail)
         over NCCL.  Kept OUT of the CUDA graphs (capturing NCCL needs every rank's watchdog to stay quiet)."""
-        if self.world > 1:
+        if self.world > 1 and (self.dp_mode != "p2p" or not update):
             import torch.distributed as dist
             dist.all_reduce(self.grad_bucket, group=self.pg)
+            if self.dp_mode == "p2p":          # gradient-only step in p2p mode: the fused kernel is not run
+                self.loss_sum.copy_(self.loss_tail)
 
     def _enqueue_update(self) -> None:
-        ops.adam_flat(self.flat_params, self.flat_grads, self.adam_m, self.adam_v, self.step_count, lr=self.lr)
+        if self.dp_mode == "p2p":
+            ops.allreduce_adam_p2p(self._p2p_ptrs["grads"], self._p2p_ptrs["params"], self._p2p_ptrs["flags"], self.adam_m,
+                                   self.adam_v, self.arena.numel, 4, self.loss_sum, self.rank, self.world, self.step_count,
+                                   lr=self.lr)
+        else:
+            ops.adam_flat(self.flat_params, self.flat_grads, self.adam_m, self.adam_v, self.step_count, lr=self.lr)
+
+    # ------------------------------------------------------------------ NVLink peer-memory plumbing (torch symmetric memory)
+    def _group(self):
+        import torch.distributed as dist
+        return self.pg if self.pg is not None else dist.group.WORLD
+
+    def _p2p_possible(self) -> bool:
+        """Peer memory needs one GPU per rank on one node with P2P access (NVLink / NVSwitch)."""
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory  # noqa: F401
+            if not dist.is_initialized() or dist.get_backend(self._group()) != "nccl":
+                return False
+            ndev = torch.cuda.device_count()
+            return ndev >= self.world and all(
+                torch.cuda.can_device_access_peer(self.dev.index or torch.cuda.current_device(), d)
+                for d in range(self.world) if d != (self.dev.index or torch.cuda.current_device()))
+        except Exception:  # noqa: BLE001
+            return False
+
+    def _symm_alloc(self, i: int, numel: int):
+        """Parameters (buffer 0) and gradients (buffer 1) live in symmetric memory so that every rank can address every
+        other rank's copy; the Adam moments stay private."""
+        if i > 1:
+            return None
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(numel, dtype=torch.float32, device=self.dev)
+        t.zero_()
+        self._symm["params" if i == 0 else "grads"] = t
+        return t
+
+    def _p2p_finish_setup(self, n: int, tail: int) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        flags = symm.empty(2 * self.world + 4, dtype=torch.int32, device=self.dev)
+        flags.zero_()
+        self._symm["flags"] = flags
+        torch.cuda.synchronize(self.dev)
+        self._p2p_ptrs = {}
+        for k in ("params", "grads", "flags"):
+            h = symm.rendezvous(self._symm[k], self._group())
+            self._p2p_ptrs[k] = [int(x) for x in h.buffer_ptrs]
+            self._symm[k + "_handle"] = h          # keeps the mappings alive
+        self.loss_sum = torch.zeros(tail, dtype=torch.float32, device=self.dev)
+        self.loss_out = self.loss_sum              # what step() copies to the host: the sums over ranks
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self._group())          # every rank's flags are zero before anyone can signal
 
     def _enqueue_step(self, training: bool, use_noise_input: bool, update: bool) -> None:
         self._enqueue_fwd_bwd(training, use_noise_input)
-        self._enqueue_allreduce()
+        self._enqueue_allreduce(update)
         if update:
             self._enqueue_update()
 
@@ -417,7 +488,8 @@ class MnistMVAETrainer:
                 self.flat_params.copy_(saved[0]); self.adam_m.copy_(saved[1]); self.adam_v.copy_(saved[2])
                 self.step_count.copy_(saved[3])
                 self._stream.synchronize()
-                if self.world == 1:
+                if self.world == 1 or (self.dp_mode == "p2p" and update):
+                    # (p2p: the exchange is one of OUR kernels, so the whole step -- including it -- is one graph)
                     g, n = self._capture(lambda: self._enqueue_step(training, noise_given, update))
                     gr = (g, None)
                 else:
@@ -427,8 +499,8 @@ class MnistMVAETrainer:
                 self.launches_per_step = n
                 self._graphs[key] = gr
             gr[0].replay()
-            if self.world > 1:
-                self._enqueue_allreduce()
+            if self.world > 1 and not (self.dp_mode == "p2p" and update):
+                self._enqueue_allreduce(update)
                 if gr[1] is not None:
                     gr[1].replay()
 

@@ -79,6 +79,7 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
     """``step(image [B,3,64,64], attrs [B,18], combos=None)``; combos = bool [approx_m, 19] (sampled when None)."""
 
     def __init__(self, n_latents: int = 100, batch_size: int = 64, approx_m: int = 1, **kw):
+        kw.setdefault("dp_mode", "nccl")   # this flavour runs its own exchange (gradients + per-term losses) through NCCL
         self.approx_m = approx_m
         self.P = 20 + approx_m
         self.n_img_max = 2 + approx_m
