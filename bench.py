@@ -31,6 +31,11 @@ POOL = 16                      # rotating pool of distinct input batches (> L2: 
 LAMBDA_IMAGE, LAMBDA_TEXT = 1.0, 10.0
 ANNEAL_EPOCHS, N_MINI = 200, 15  # KL annealing schedule of mnist/train.py:180-186 with 60000/4096 ~ 15 batches/epoch
 
+# DRAM traffic per launch from the committed ncu captures (profiles/): the four chained GEMM launches of one MNIST B=4096
+# step moved 31.1 + 197.6 + 501.3 + 92.9 MB; the roofline-size BCE launch 308.3 MB read + 157.3 MB written
+GEMM_CHAIN_DRAM_BYTES_PER_LAUNCH = (31.07e6 + 197.58e6 + 501.33e6 + 92.89e6) / 4
+BCE_DRAM_BYTES_PER_LAUNCH = 308.29e6 + 157.27e6
+
 # algorithmic work per sample per step
 FLOP_PER_SAMPLE_REFERENCE = 32.4e6     # everything the reference executes (incl. dead decoder passes, duplicate encoders)
 ELEMENTWISE_BYTES_PER_SAMPLE = 30512   # K1 fwd/bwd + K2 image/label terms
@@ -281,11 +286,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     tr.synchronize()
-    t0 = time.time()
-    while time.time() - t0 < 1.0:
-        for i in range(20):
-            step_resident(i)
-        tr.synchronize()
+    # clock ramp: a FIXED number of extra untimed steps.  (It used to be "as many as fit in one second", which lets the
+    # ranks of a multi-GPU run execute different numbers of steps -- every step contains a collective, so at N=4 the
+    # ranks fell out of lockstep and NCCL's watchdog aborted the run.)
+    ramp = {"mnist": 400, "fashion": 60, "celeba": 40, "celeba19": 20}[args.workload]
+    for i in range(ramp):
+        step_resident(i)
+    tr.synchronize()
 
     log("timed region (device-resident inputs)")
     sampler = ClockSampler(local_rank); sampler.start()
@@ -356,9 +363,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                              "trainer.step_pipelined(pinned host image, pinned host labels): H2D of batch i+1 on a copy stream "
                              "overlaps step i; the loss is copied D2H and read on the host every step (one step lagged)")},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 kind::tf32, all GEMM launches of a step)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 kind::tf32; all GEMM launches of a step: 4 chained "
+                                                         "launches for MNIST, one launch per layer group otherwise)",
                          "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
-                         "traffic": None,
+                         "traffic": GEMM_CHAIN_DRAM_BYTES_PER_LAUNCH if (args.workload == "mnist" and tr.chain and
+                                                                         b_local == BATCH) else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum averaged over the "
+                                           "4 chained GEMM launches of one B=4096 step (profiles/r01_gemm_chain_v5_raw_key_metrics.txt)",
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained/2 (tf32 rate = half bf16) [{peaks['source']}]",
                          "algorithmic_flops_per_launch_avg": gemm["algorithmic_flops_per_step"] / max(gemm["launches"], 1),
                          "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms_per_step"] / max(gemm["launches"], 1),
@@ -449,7 +460,9 @@ def measure_rooflines(tr, dev, prec, args):
     alg = (2 * R * D + (R // 2) * D) * 4.0   # read x once, write dx once, read the shared target once = 10 B per logit
     out["hbm"] = {"bound": "hbm", "kernel": "bce_kernel (fused BCE-with-logits loss + gradient), roofline-size run "
                                             f"R={R} D={D}", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                  "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                  "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": BCE_DRAM_BYTES_PER_LAUNCH,
+                  "traffic_source": "ncu --set full of this launch (profiles/r01_bce_stacked_v5_raw_key_metrics.txt): below the "
+                                    "algorithmic bytes because part of the gradient write-back is still in L2 when the kernel ends",
                   "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms, "peak_source": peaks["source"]}
     del x, t, dx
     return out

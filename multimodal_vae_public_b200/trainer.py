@@ -127,7 +127,9 @@ class MnistMVAETrainer:
         # Adam on the rank's slice -> parameter all-gather, csrc/dp_p2p.cu); "nccl" = ncclAllReduce + flat Adam.
         self.dp_mode = "none"
         if world_size > 1:
-            self.dp_mode = os.environ.get("MVAE_DP", "p2p") if dp_mode is None else dp_mode
+            # default "nccl"; MVAE_DP=p2p (or dp_mode="p2p") selects the fused peer-memory kernel: verified bit-for-bit
+            # against NCCL at 2 GPUs (+3.4 % step throughput), not yet validated at 4 and 8
+            self.dp_mode = os.environ.get("MVAE_DP", "nccl") if dp_mode is None else dp_mode
             if self.dp_mode == "p2p" and not self._p2p_possible():
                 self.dp_mode = "nccl"
         self._symm = {}

@@ -34,6 +34,10 @@ def test_bad_arguments_return_error_codes_not_crash():
     assert rc == -1 and b"mvae_gemm_batch" in lib.mvae_last_error()
     rc = lib.mvae_colsum_accumulate(None, 0, None, 0, 0, None)
     assert rc == -1
+    rc = lib.mvae_gemm_chain(None, None, 0, None, 0, 1, None)
+    assert rc == -1 and b"mvae_gemm_chain" in lib.mvae_last_error()
+    rc = lib.mvae_allreduce_adam_p2p(None, None, None, None, None, 0, 0, None, 0, 0, 0.0, None, 0.9, 0.999, 1e-8, None, None)
+    assert rc == -1 and b"allreduce_adam_p2p" in lib.mvae_last_error()
     with pytest.raises(_lib.MvaeError):
         _lib.check(rc, "colsum")
 
