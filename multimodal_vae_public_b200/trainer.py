@@ -68,6 +68,40 @@ def mnist_reference_order(n_latents: int) -> List[str]:
     return keys
 
 
+def adam_state_to_torch(names: Sequence[str], exp_avg: Dict[str, torch.Tensor], exp_avg_sq: Dict[str, torch.Tensor],
+                        step: int, lr: float, betas=(0.9, 0.999), eps: float = 1e-8) -> dict:
+    """``torch.optim.Adam.state_dict()`` layout (what the reference stores under checkpoint['optimizer'],
+    mnist/train.py:263-268) from named first / second moments; ``names`` in ``model.parameters()`` order."""
+    state = {}
+    if step > 0:
+        for i, k in enumerate(names):
+            state[i] = {"step": torch.tensor(float(step)), "exp_avg": exp_avg[k].detach().clone().cpu(),
+                        "exp_avg_sq": exp_avg_sq[k].detach().clone().cpu()}
+    group = {"lr": lr, "betas": tuple(betas), "eps": eps, "weight_decay": 0, "amsgrad": False, "maximize": False,
+             "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+             "params": list(range(len(names)))}
+    return {"state": state, "param_groups": [group]}
+
+
+def adam_state_from_torch(sd: dict, names: Sequence[str]):
+    """Inverse of ``adam_state_to_torch``: (exp_avg by name, exp_avg_sq by name, step, lr).  Accepts state dicts written
+    by any torch version of the reference's era (``step`` as int or 0-dim tensor); parameters without state (never
+    stepped) come back as None."""
+    groups = sd["param_groups"]
+    order = [i for g in groups for i in g["params"]]
+    if len(order) != len(names):
+        raise ValueError(f"optimizer state has {len(order)} parameters, the model has {len(names)}")
+    m, v, step = {}, {}, 0
+    for pos, k in zip(order, names):
+        st = sd["state"].get(pos)
+        if st is None:
+            m[k] = v[k] = None
+            continue
+        m[k], v[k] = st["exp_avg"], st["exp_avg_sq"]
+        step = max(step, int(st["step"].item() if torch.is_tensor(st["step"]) else st["step"]))
+    return m, v, step, float(groups[0]["lr"])
+
+
 class FlatArena:
     """One contiguous fp32 bucket with named, 16-byte aligned views."""
 
@@ -214,6 +248,42 @@ class MnistMVAETrainer:
         """Copies of the parameters under the reference's state_dict keys, in the reference's order
         (mnist/model.py:20-27), so ``ref_model.load_state_dict(trainer.state_dict())`` works."""
         return {k: self.params[k].detach().clone() for k in mnist_reference_order(self.L)}
+
+    # ------------------------------------------------------------------ optimizer state (checkpoint['optimizer'])
+    def _with_arena_buffer(self, buf: int, fn):
+        """Run a state_dict-style method with ``self.params`` pointing at another arena buffer (Adam moments), so the
+        flavour's layout permutations (conv weights, FC column orders) are applied to the moments exactly as to the
+        parameters."""
+        saved = self.params
+        self.params = {k: self.arena.view(buf, k) for k, _ in self.layout}
+        try:
+            return fn()
+        finally:
+            self.params = saved
+
+    def optimizer_state_dict(self) -> dict:
+        """Adam state in ``torch.optim.Adam.state_dict()`` format, tensors in the reference's parameter layouts and
+        ``model.parameters()`` order: drop it into the reference's checkpoint dict (mnist/train.py:263-268)."""
+        names = [k for k in self.state_dict() if k in self.arena.offsets]
+        m = self._with_arena_buffer(2, self.state_dict)
+        v = self._with_arena_buffer(3, self.state_dict)
+        self._stream.synchronize()
+        return adam_state_to_torch(names, m, v, int(self.step_count.item()), self.lr)
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        """Resume from a reference checkpoint's optimizer state (moments, step count, learning rate)."""
+        names = [k for k in self.state_dict() if k in self.arena.offsets]
+        m, v, step, lr = adam_state_from_torch(sd, names)
+        shapes = {k: t.shape for k, t in self.state_dict().items()}
+        zeros = lambda k: torch.zeros(shapes[k], dtype=torch.float32)  # noqa: E731
+        m = {k: (t if t is not None else zeros(k)).to(self.dev) for k, t in m.items()}
+        v = {k: (t if t is not None else zeros(k)).to(self.dev) for k, t in v.items()}
+        full = self.state_dict()          # buffers (BatchNorm running statistics) pass through unchanged
+        self._with_arena_buffer(2, lambda: self.load_state_dict({**full, **m}))
+        self._with_arena_buffer(3, lambda: self.load_state_dict({**full, **v}))
+        self.step_count.fill_(step)
+        self.lr = lr
+        self._graphs.clear()              # the learning rate is baked into captured launches
 
     # ------------------------------------------------------------------ one step worth of launches
     def _p(self, name):
