@@ -223,6 +223,14 @@ int mvae_dropout_bwd(const float* dy, const float* mask, float* dx, int x_rows, 
 /* NCHW -> NHWC staging of the input image batch (the kernels work on NHWC). */
 int mvae_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW, void* stream);
 
+/* Device-resident input pipeline: the uint8 dataset stays in HBM; one launch builds a batch.
+ *   out[b, :] = data[idx[b], :] / 255   (transforms.ToTensor of the uint8 image, mnist/train.py:159-160)
+ *   labels_out[b] = labels[idx[b]]      (may be NULL together with labels)
+ * idx: int64 [B] row indices, e.g. a slice of a device-side permutation (DataLoader(shuffle=True), mnist/train.py:161).
+ * Replaces the host DataLoader + per-step H2D copy of mnist/train.py:188-193.  row_bytes % 4 == 0.                   */
+int mvae_gather_batch_u8(const uint8_t* data, int64_t row_bytes, const int64_t* labels, const int64_t* idx, int B,
+                         float* out, int64_t ld_out, int64_t* labels_out, void* stream);
+
 /* Fused flat Adam over one contiguous parameter bucket (torch.optim.Adam defaults, mnist/train.py:168,219):
  *   g is first multiplied by grad_scale (1/world_size after a sum-allreduce).
  *   lr_mult_dev: optional device float multiplying lr.

@@ -72,6 +72,7 @@ SIGNATURES = {
     "mvae_dropout_fwd": [_P, _I, _P, _P, _P, _I, _I, _F, _U64, _P, _P],
     "mvae_dropout_bwd": [_P, _P, _P, _I, _I, _I, _F, _P],
     "mvae_nchw_to_nhwc": [_P, _P, _I, _I, _I, _P],
+    "mvae_gather_batch_u8": [_P, _L, _P, _P, _I, _P, _L, _P, _P],
     "mvae_adam_flat": [_P, _P, _P, _P, _L, _F, _P, _F, _F, _F, _F, _P, _P],
     "mvae_allreduce_adam_p2p": [C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P, _P, _L, _I, _P, _I, _I, _F, _P, _F, _F, _F,
                                 _P, _P],

@@ -294,6 +294,25 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* y, int B
   y[i] = x[(static_cast<int64_t>(b) * C + c) * HW + p];
 }
 
+// ---------------------------------------------------------------- device-resident dataset -> batch
+// out[b, :] = data[idx[b], :] / 255 (torchvision ToTensor of a uint8 image, mnist/train.py:160), labels_out[b] =
+// labels[idx[b]]: one thread per 4 bytes of a row (uchar4 -> float4)
+__global__ void __launch_bounds__(256) gather_batch_u8_kernel(const uint8_t* __restrict__ data, int64_t row_bytes,
+                                                              const int64_t* __restrict__ labels,
+                                                              const int64_t* __restrict__ idx, int B, float* out,
+                                                              int64_t ld_out, int64_t* labels_out) {
+  const unsigned q4 = static_cast<unsigned>(row_bytes >> 2);
+  const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<unsigned>(B) * q4) return;
+  const unsigned b = gid / q4, j = gid - b * q4;
+  const int64_t row = idx[b];
+  const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(data + row * row_bytes) + j);
+  *reinterpret_cast<float4*>(out + static_cast<int64_t>(b) * ld_out + 4 * j) =
+      make_float4(static_cast<float>(v.x) / 255.0f, static_cast<float>(v.y) / 255.0f, static_cast<float>(v.z) / 255.0f,
+                  static_cast<float>(v.w) / 255.0f);
+  if (j == 0 && labels_out != nullptr) labels_out[b] = labels[row];
+}
+
 }  // namespace
 }  // namespace mvae
 
@@ -403,6 +422,21 @@ extern "C" int mvae_nchw_to_nhwc(const float* x, float* y, int B, int C, int HW,
   if (!x || !y || B < 1 || C < 1 || HW < 1) return set_error(MVAE_ERR_BAD_ARG, "nchw_to_nhwc: bad args");
   const int64_t n = static_cast<int64_t>(B) * C * HW;
   nchw_to_nhwc_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ST(stream)>>>(x, y, B, C, HW);
+  count_launch();
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  return MVAE_OK;
+}
+
+extern "C" int mvae_gather_batch_u8(const uint8_t* data, int64_t row_bytes, const int64_t* labels, const int64_t* idx, int B,
+                                    float* out, int64_t ld_out, int64_t* labels_out, void* stream) {
+  if (!data || !idx || !out || B < 1 || row_bytes < 4 || (row_bytes & 3) || (ld_out & 3) || ld_out < row_bytes ||
+      (labels_out != nullptr && labels == nullptr) ||
+      ((reinterpret_cast<uintptr_t>(data) & 3) | (reinterpret_cast<uintptr_t>(out) & 15)) != 0)
+    return set_error(MVAE_ERR_BAD_ARG, "gather_batch_u8: bad args (row_bytes %% 4 == 0, out 16-byte aligned, ld_out %% 4 == 0)");
+  const int64_t n = static_cast<int64_t>(B) * (row_bytes / 4);
+  if (n >= (1ll << 32) - 256) return set_error(MVAE_ERR_UNSUPPORTED, "gather_batch_u8: batch too large for one call");
+  gather_batch_u8_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ST(stream)>>>(data, row_bytes, labels, idx, B, out,
+                                                                                         ld_out, labels_out);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;

@@ -248,6 +248,15 @@ def nchw_to_nhwc(x, y, B, Cch, HW):
     _lib.check(_lib.load().mvae_nchw_to_nhwc(x.data_ptr(), y.data_ptr(), B, Cch, HW, _stream()), "mvae_nchw_to_nhwc")
 
 
+def gather_batch_u8(data_u8, labels, idx, out, labels_out=None):
+    """out[b, :] = data_u8[idx[b], :] / 255 ; labels_out[b] = labels[idx[b]] (device-resident dataset -> batch)."""
+    if data_u8.dtype != torch.uint8 or data_u8.dim() != 2 or not data_u8.is_contiguous() or idx.dtype != torch.int64:
+        raise _lib.MvaeError("gather_batch_u8: data must be a contiguous [N, D] uint8 tensor and idx int64")
+    _lib.check(_lib.load().mvae_gather_batch_u8(data_u8.data_ptr(), data_u8.shape[1], _p(labels), idx.data_ptr(), idx.numel(),
+                                                out.data_ptr(), out.stride(0), _p(labels_out), _stream()),
+               "mvae_gather_batch_u8")
+
+
 def adam_flat(p, g, m, v, step_count, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, lr_mult_dev=None):
     _lib.check(_lib.load().mvae_adam_flat(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
                                           _p(lr_mult_dev), beta1, beta2, eps, grad_scale, step_count.data_ptr(),

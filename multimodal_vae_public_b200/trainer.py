@@ -590,6 +590,41 @@ class MnistMVAETrainer:
             return float(self.loss_host[0])
         return None
 
+    # ------------------------------------------------------------------ device-resident dataset (no per-step H2D at all)
+    def attach_dataset(self, images_u8: torch.Tensor, labels: torch.Tensor) -> None:
+        """Keep the whole uint8 dataset in HBM (MNIST: 47 MB): ``images_u8`` [N, 784] / [N,1,28,28] uint8 as stored on
+        disk, ``labels`` [N].  Batches are then built on the device by one gather launch (ToTensor's /255 and the label
+        lookup fused), replacing DataLoader + H2D of mnist/train.py:159-165,188-193."""
+        if images_u8.dtype != torch.uint8:
+            raise _lib.MvaeError("attach_dataset: images must be uint8 (the /255 of ToTensor happens on the device)")
+        n = images_u8.shape[0]
+        self.ds_images = images_u8.reshape(n, -1).contiguous().to(self.dev)
+        if self.ds_images.shape[1] != self.x.shape[1]:
+            raise _lib.MvaeError(f"attach_dataset: rows of {self.ds_images.shape[1]} bytes, the model takes {self.x.shape[1]}")
+        self.ds_labels = labels.reshape(n).to(torch.int64).to(self.dev)
+
+    def epoch_permutation(self, seed: int) -> torch.Tensor:
+        """A device-side shuffle of the attached dataset (DataLoader(shuffle=True)); slice it into batches of B."""
+        g = torch.Generator(device=self.dev).manual_seed(seed)
+        return torch.randperm(self.ds_images.shape[0], generator=g, device=self.dev)
+
+    def step_from_dataset(self, idx: torch.Tensor, annealing_factor: float = 1.0, training: bool = True,
+                          update: bool = True, sync: bool = True) -> Optional[float]:
+        """One training iteration on rows ``idx`` (int64 [B], on the device) of the attached dataset."""
+        if idx.numel() != self.B or idx.dtype != torch.int64 or not idx.is_cuda:
+            raise _lib.MvaeError(f"step_from_dataset: idx must be a CUDA int64 tensor of {self.B} row indices")
+        with torch.cuda.stream(self._stream):
+            ops.gather_batch_u8(self.ds_images, self.ds_labels, idx.contiguous(), self.x, self.text)
+            self.beta_host[0] = float(annealing_factor)
+            self.beta_dev.copy_(self.beta_host, non_blocking=True)
+        self.run(training=training, noise_given=False, update=update)
+        with torch.cuda.stream(self._stream):
+            self.loss_host.copy_(self.loss_out, non_blocking=True)
+        if sync:
+            self._stream.synchronize()
+            return float(self.loss_host[0])
+        return None
+
     # ------------------------------------------------------------------ host-fed, double-buffered stepping
     def _pipe_init(self) -> None:
         B, dev = self.B, self.dev

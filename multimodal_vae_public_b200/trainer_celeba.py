@@ -262,6 +262,9 @@ class CelebAMVAETrainer(MnistMVAETrainer):
             return float(self.loss_host[0])
         return None
 
+    def attach_dataset(self, *a, **k):  # pragma: no cover
+        raise _lib.MvaeError("the device-resident dataset path is implemented for the MNIST-shape trainers")
+
     def step_pipelined(self, *a, **k):  # pragma: no cover
         raise _lib.MvaeError("step_pipelined is implemented for the MNIST-shape trainers; use step() for CelebA")
 

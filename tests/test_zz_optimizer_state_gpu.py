@@ -43,3 +43,33 @@ def test_mnist_trainer_resumes_from_torch_format_optimizer_state():
     for k in a.params:
         d = (a.params[k] - b.params[k]).abs().max().item()
         assert d <= 1e-6, (k, d)      # same moments, same step count: only the order of fp32 atomics may differ
+
+
+def test_device_resident_dataset_matches_host_fed_steps():
+    """batches gathered on the device from the uint8 dataset (/255 and label lookup fused)
+    give the same training steps as host-fed float batches."""
+    from multimodal_vae_public_b200 import ops
+    from multimodal_vae_public_b200.trainer import MnistMVAETrainer
+    rs = np.random.RandomState(5)
+    N, B = 1000, 64
+    images = torch.from_numpy(rs.randint(0, 256, (N, 1, 28, 28)).astype(np.uint8))
+    labels = torch.from_numpy(rs.randint(0, 10, N).astype(np.int64))
+    # the gather kernel alone: ToTensor semantics, exact
+    idx = torch.from_numpy(rs.permutation(N)[:B].astype(np.int64)).cuda()
+    out = torch.full((B, 784), -1.0, device="cuda"); lab = torch.full((B,), -1, dtype=torch.int64, device="cuda")
+    ops.gather_batch_u8(images.reshape(N, 784).cuda(), labels.cuda(), idx, out, lab)
+    assert torch.equal(out.cpu(), images.reshape(N, 784)[idx.cpu()].float().div(255))
+    assert torch.equal(lab.cpu(), labels[idx.cpu()])
+    # two trainers, same seed (same Philox noise): device-resident vs host-fed
+    a = MnistMVAETrainer(64, B, use_graph=False, seed=4)
+    b = MnistMVAETrainer(64, B, use_graph=False, seed=4)
+    a.attach_dataset(images, labels)
+    perm = a.epoch_permutation(seed=1)
+    assert sorted(perm.cpu().tolist()) == list(range(N))
+    for it in range(3):
+        sel = perm[it * B:(it + 1) * B]
+        la = a.step_from_dataset(sel, annealing_factor=0.5)
+        lb = b.step(images[sel.cpu()].float().div(255), labels[sel.cpu()], annealing_factor=0.5)
+        assert abs(la - lb) <= 1e-6 * abs(lb), (it, la, lb)
+    for k in a.params:
+        assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-6, k
