@@ -1,0 +1,62 @@
+"""Tensor-map geometry for implicit-GEMM 4x4 / stride-2 / pad-1 convolutions (groundwork for DESIGN.md section 8.1).
+
+The convolution layers currently materialise im2col matrices in HBM (16x the activation bytes).  With activations
+stored NHWC **with a one-pixel zero border**, the im2col matrix never has to exist: row m = (b, oh, ow), column
+k = (kh, kw, ci) of it is the element
+
+    xp[b, 2*oh + kh, 2*ow + kw, ci]          xp: [B, H+2, W+2, C]  (padded input)
+
+and for a fixed kh the 4*C values over (kw, ci) are CONTIGUOUS in memory.  The matrix is therefore a rank-5 strided
+view of xp with overlapping strides -- (r, ow, kh, oh, b), r = kw*C + ci -- which is exactly what a tiled TMA tensor
+map describes (no im2col-mode map needed), and a 128-row x 32-column operand tile of the GEMM is ONE box of that map
+whenever OW divides 128 (CelebA: OW = 32, 16, 8).  `conv_k4s2p1_view` returns the dims / strides / box of that map;
+`tests/test_conv_views_cpu.py` proves with numpy's as_strided that the view equals the reference im2col
+(fashionmnist/model.py:79-82, celeba/model.py:76-92 are the layers it will serve).  The weight matrices already use the
+matching column order [Cout, (kh, kw, ci)].
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Tuple
+
+
+@dataclass(frozen=True)
+class ConvView:
+    dims: Tuple[int, int, int, int, int]        # (r, ow, kh, oh, b) sizes, innermost first (cuTensorMapEncodeTiled order)
+    strides: Tuple[int, int, int, int, int]     # element strides of the same dims (strides[0] == 1)
+    box: Tuple[int, int, int, int, int]         # box of one 128-row x 32-column operand tile
+    rows: int                                   # M = B * OH * OW
+    cols: int                                   # K = 16 * C
+    kblocks_per_kh: int                         # 4*C / 32 k-blocks before kh advances
+
+    def tile_coords(self, m_blk: int, kb: int) -> Tuple[int, int, int, int, int]:
+        """TMA coordinates (r, ow, kh, oh, b) of operand tile (128-row block m_blk, 32-column block kb)."""
+        r, ow_n, _, oh_n, _ = self.dims
+        _, bow, _, boh, bb = self.box
+        kh, rb = divmod(kb, self.kblocks_per_kh)
+        row0 = m_blk * 128
+        b0, rem = divmod(row0, oh_n * ow_n)
+        oh0, ow0 = divmod(rem, ow_n)
+        assert ow0 == 0 and oh0 % boh == 0 and b0 % bb == 0, "tile does not start on a box boundary"
+        return (rb * 32, 0, kh, oh0, b0)
+
+
+def conv_k4s2p1_view(B: int, H: int, W: int, C: int) -> ConvView:
+    """Geometry of the implicit im2col matrix of Conv2d(C -> *, 4, 2, 1) over a padded NHWC input [B, H+2, W+2, C]."""
+    if H % 2 or W % 2:
+        raise ValueError("even H, W required")
+    OH, OW = H // 2, W // 2
+    if (4 * C) % 32:
+        raise ValueError("4*C must be a multiple of the 32-float k-block (C % 8 == 0)")
+    if OW > 128 or 128 % OW:
+        raise ValueError("OW must divide the 128-row tile (use the materialised path otherwise)")
+    boh = min(OH, 128 // OW)
+    if OH % boh:
+        raise ValueError("OH must be a multiple of the rows of one tile")
+    bb = 128 // (OW * boh)
+    Wp, Hp = W + 2, H + 2
+    dims = (4 * C, OW, 4, OH, B)
+    strides = (1, 2 * C, Wp * C, 2 * Wp * C, Hp * Wp * C)
+    if any((s * 4) % 16 for s in strides[1:]):
+        raise ValueError("TMA strides must be multiples of 16 bytes")
+    return ConvView(dims, strides, (32, OW, 1, boh, bb), B * OH * OW, 16 * C, (4 * C) // 32)

@@ -1,0 +1,56 @@
+"""The implicit-GEMM geometry of conv_views.py is the reference convolution's im2col (pure host arithmetic, numpy):
+the rank-5 overlapping-stride view of the zero-bordered NHWC input equals the explicit [B*OH*OW, 16*C] patch matrix of
+Conv2d(k=4, s=2, p=1) (fashionmnist/model.py:79-82, celeba/model.py:76-92), and every 128x32 operand tile is one box."""
+import numpy as np
+import pytest
+import torch
+
+from multimodal_vae_public_b200.conv_views import conv_k4s2p1_view
+
+
+def _explicit_im2col(x):   # x: [B, H, W, C] -> [B*OH*OW, (kh, kw, ci)]
+    B, H, W, C = x.shape
+    xp = np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0)))
+    OH, OW = H // 2, W // 2
+    out = np.empty((B, OH, OW, 4, 4, C), x.dtype)
+    for kh in range(4):
+        for kw in range(4):
+            out[:, :, :, kh, kw, :] = xp[:, kh:kh + 2 * OH:2, kw:kw + 2 * OW:2, :]
+    return out.reshape(B * OH * OW, 16 * C)
+
+
+@pytest.mark.parametrize("B,H,C", [(4, 64, 8), (2, 32, 32), (4, 16, 64), (3, 32, 16)])
+def test_view_equals_im2col_and_conv2d(B, H, C):
+    rs = np.random.RandomState(B + H + C)
+    x = rs.standard_normal((B, H, H, C)).astype(np.float32)
+    xp = np.ascontiguousarray(np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0))))
+    v = conv_k4s2p1_view(B, H, H, C)
+    # numpy wants outermost-first shapes / byte strides
+    view = np.lib.stride_tricks.as_strided(xp, shape=v.dims[::-1], strides=tuple(4 * s for s in v.strides[::-1]))
+    # (b, oh, kh, ow, r) -> rows (b, oh, ow), columns (kh, r)
+    mat = view.transpose(0, 1, 3, 2, 4).reshape(v.rows, v.cols)
+    ref = _explicit_im2col(x)
+    assert np.array_equal(mat, ref)
+    # and it is the reference convolution: im2col @ W^T with W in (kh, kw, ci) column order
+    w = rs.standard_normal((5, C, 4, 4)).astype(np.float32)
+    y = torch.nn.functional.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2).double(), torch.from_numpy(w).double(), None, 2, 1)
+    got = (mat.astype(np.float64) @ w.transpose(0, 2, 3, 1).reshape(5, -1).astype(np.float64).T)
+    got = got.reshape(B, H // 2, H // 2, 5).transpose(0, 3, 1, 2)
+    assert np.abs(got - y.numpy()).max() < 1e-9
+    # every 128 x 32 operand tile is one box of the view
+    bx = v.box
+    assert bx[1] * bx[3] * bx[4] == 128 or v.rows < 128
+    if v.rows % 128 == 0:
+        for m_blk in (0, v.rows // 128 - 1):
+            for kb in (0, v.cols // 32 - 1):
+                c = v.tile_coords(m_blk, kb)
+                sl = view[c[4]:c[4] + bx[4], c[3]:c[3] + bx[3], c[2]:c[2] + 1, c[1]:c[1] + bx[1], c[0]:c[0] + 32]
+                tile = sl.transpose(0, 1, 3, 2, 4).reshape(128, 32)     # smem order: b, oh, ow rows; r fastest
+                assert np.array_equal(tile, ref[m_blk * 128:(m_blk + 1) * 128, kb * 32:(kb + 1) * 32])
+
+
+def test_unsupported_geometries_are_rejected():
+    with pytest.raises(ValueError):
+        conv_k4s2p1_view(2, 28, 28, 64)       # OW = 14 does not divide 128 (FashionMNIST: stays on the materialised path)
+    with pytest.raises(ValueError):
+        conv_k4s2p1_view(2, 64, 64, 3)        # RGB input layer: 4*C = 12 floats per kh run
