@@ -60,3 +60,27 @@ def conv_k4s2p1_view(B: int, H: int, W: int, C: int) -> ConvView:
     if any((s * 4) % 16 for s in strides[1:]):
         raise ValueError("TMA strides must be multiples of 16 bytes")
     return ConvView(dims, strides, (32, OW, 1, boh, bb), B * OH * OW, 16 * C, (4 * C) // 32)
+
+
+# ---------------------------------------------------------------------------------------------------- ConvTranspose
+# ConvTranspose2d(Cin -> Cout, 4, 2, 1) (fashionmnist/model.py:112-114, celeba/model.py:116-126) as FOUR stride-1 2x2
+# convolutions, one per output parity class (ph, pw): y[b, 2j+ph, 2i+pw, :] only receives the taps kh = KH[ph][dh],
+# kw = KH[pw][dw] from the input pixels (j + ph + dh - 1, i + pw + dw - 1).  On the zero-bordered input that is again a
+# rank-5 strided view -- (r = (dw, ci), i, dh, j, b) with a base offset of (ph, pw) pixels -- times a [Cout, 4*Cin] slice
+# of the weights: no cols matrix, no col2im, one quarter of the output pixels per GEMM with a strided epilogue store.
+KH = ((3, 1), (2, 0))       # KH[parity][d]: kernel index met by input offset d of that output parity
+
+
+def convt_k4s2p1_subpixel_view(B: int, IH: int, IW: int, C: int, ph: int, pw: int):
+    """(dims, strides, base element offset) of the implicit patch matrix [B*IH*IW, 4*C] of output parity (ph, pw) over
+    the zero-bordered NHWC input [B, IH+2, IW+2, C]; dims innermost first: (r, i, dh, j, b), r = dw*C + ci."""
+    Wp, Hp = IW + 2, IH + 2
+    dims = (2 * C, IW, 2, IH, B)
+    strides = (1, C, Wp * C, Wp * C, Hp * Wp * C)
+    return dims, strides, (ph * Wp + pw) * C
+
+
+def convt_subpixel_weight(wt, ph: int, pw: int):
+    """[Cout, (dh, dw, ci)] operand of parity (ph, pw) from ConvTranspose2d's weight ``wt`` [Cin, Cout, 4, 4]."""
+    sub = wt[:, :, list(KH[ph]), :][:, :, :, list(KH[pw])]          # [Cin, Cout, dh, dw]
+    return sub.permute(1, 2, 3, 0).reshape(wt.shape[1], -1)

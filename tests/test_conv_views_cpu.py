@@ -54,3 +54,25 @@ def test_unsupported_geometries_are_rejected():
         conv_k4s2p1_view(2, 28, 28, 64)       # OW = 14 does not divide 128 (FashionMNIST: stays on the materialised path)
     with pytest.raises(ValueError):
         conv_k4s2p1_view(2, 64, 64, 3)        # RGB input layer: 4*C = 12 floats per kh run
+
+
+@pytest.mark.parametrize("B,IH,C,Co", [(2, 8, 16, 6), (3, 16, 8, 5), (1, 5, 4, 3)])
+def test_conv_transpose_is_four_subpixel_convolutions(B, IH, C, Co):
+    """ConvTranspose2d(k=4, s=2, p=1) (celeba/model.py:116-126) == four implicit 2x2 GEMMs over the zero-bordered input,
+    one per output parity, each storing a quarter of the output pixels."""
+    from multimodal_vae_public_b200.conv_views import convt_k4s2p1_subpixel_view, convt_subpixel_weight
+    rs = np.random.RandomState(IH + C)
+    x = rs.standard_normal((B, IH, IH, C)).astype(np.float32)
+    wt = torch.from_numpy(rs.standard_normal((C, Co, 4, 4)).astype(np.float32))
+    ref = torch.nn.functional.conv_transpose2d(torch.from_numpy(x).permute(0, 3, 1, 2).double(), wt.double(), None, 2, 1)
+    xp = np.ascontiguousarray(np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0))))
+    y = np.zeros((B, 2 * IH, 2 * IH, Co))
+    for ph in range(2):
+        for pw in range(2):
+            dims, strides, base = convt_k4s2p1_subpixel_view(B, IH, IH, C, ph, pw)
+            view = np.lib.stride_tricks.as_strided(xp.reshape(-1)[base:], shape=dims[::-1],
+                                                   strides=tuple(4 * s for s in strides[::-1]))
+            mat = view.transpose(0, 1, 3, 2, 4).reshape(B * IH * IH, 4 * C).astype(np.float64)   # rows (b, j, i), cols (dh, r)
+            w = convt_subpixel_weight(wt, ph, pw).double().numpy()
+            y[:, ph::2, pw::2, :] = (mat @ w.T).reshape(B, IH, IH, Co)
+    assert np.abs(y.transpose(0, 3, 1, 2) - ref.numpy()).max() < 1e-9
