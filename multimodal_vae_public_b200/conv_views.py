@@ -84,3 +84,14 @@ def convt_subpixel_weight(wt, ph: int, pw: int):
     """[Cout, (dh, dw, ci)] operand of parity (ph, pw) from ConvTranspose2d's weight ``wt`` [Cin, Cout, 4, 4]."""
     sub = wt[:, :, list(KH[ph]), :][:, :, :, list(KH[pw])]          # [Cin, Cout, dh, dw]
     return sub.permute(1, 2, 3, 0).reshape(wt.shape[1], -1)
+
+
+def wgrad_box(view: ConvView) -> Tuple[int, int, int, int, int]:
+    """Box of one MN-major wgrad operand tile of the same map: 32 reduction rows (output pixels) x 32 columns -- the B
+    operand of dW[Cout, (kh,kw,ci)] = dY^T[Cout, pixels] * im2col[pixels, (kh,kw,ci)] (and, for a ConvTranspose, of
+    dWt = im2col(dY)^T * X): 32 consecutive pixels are one row of OW = 32, two rows of 16 or four rows of 8."""
+    ow = view.dims[1]
+    if 32 % ow and ow % 32:
+        raise ValueError("OW must divide 32 or be a multiple of it")
+    bow = min(ow, 32)
+    return (32, bow, 1, 32 // bow, 1)

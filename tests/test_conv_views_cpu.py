@@ -76,3 +76,45 @@ def test_conv_transpose_is_four_subpixel_convolutions(B, IH, C, Co):
             w = convt_subpixel_weight(wt, ph, pw).double().numpy()
             y[:, ph::2, pw::2, :] = (mat @ w.T).reshape(B, IH, IH, Co)
     assert np.abs(y.transpose(0, 3, 1, 2) - ref.numpy()).max() < 1e-9
+
+
+def test_wgrad_operand_tile_is_one_box():
+    from multimodal_vae_public_b200.conv_views import wgrad_box
+    B, H, C = 2, 32, 16
+    rs = np.random.RandomState(0)
+    x = rs.standard_normal((B, H, H, C)).astype(np.float32)
+    xp = np.ascontiguousarray(np.pad(x, ((0, 0), (1, 1), (1, 1), (0, 0))))
+    v = conv_k4s2p1_view(B, H, H, C)
+    view = np.lib.stride_tricks.as_strided(xp, shape=v.dims[::-1], strides=tuple(4 * s for s in v.strides[::-1]))
+    ref = _explicit_im2col(x)
+    bx = wgrad_box(v)
+    assert bx[1] * bx[3] * bx[4] == 32
+    OW = H // 2
+    for p0 in (0, 96, 480):                      # first pixel (reduction row) of a 32-row k-block
+        b0, rem = divmod(p0, OW * OW)
+        oh0, ow0 = divmod(rem, OW)
+        assert ow0 % bx[1] == 0 and oh0 % bx[3] == 0
+        for kb in (0, 5, v.cols // 32 - 1):
+            kh, rb = divmod(kb, v.kblocks_per_kh)
+            sl = view[b0:b0 + 1, oh0:oh0 + bx[3], kh:kh + 1, ow0:ow0 + bx[1], rb * 32:rb * 32 + 32]
+            tile = sl.transpose(0, 1, 3, 2, 4).reshape(32, 32)          # [32 pixels (k rows)][32 columns (n)]
+            assert np.array_equal(tile, ref[p0:p0 + 32, kb * 32:kb * 32 + 32])
+
+
+def test_conv_transpose_backward_is_convolution_of_dy():
+    """What the decoder backward needs (celeba/model.py:116-126 under autograd): d x of ConvTranspose2d(k4,s2,p1) is
+    Conv2d(k4,s2,p1) of dy with the same weight tensor, and d Wt = im2col(dy)^T x -- both implicit GEMMs over the
+    zero-bordered dy, i.e. the same machinery as the encoder's forward / wgrad."""
+    rs = np.random.RandomState(3)
+    B, IH, Ci, Co = 2, 8, 6, 5
+    x = torch.from_numpy(rs.standard_normal((B, Ci, IH, IH))).requires_grad_(True)
+    wt = torch.from_numpy(rs.standard_normal((Ci, Co, 4, 4))).requires_grad_(True)
+    y = torch.nn.functional.conv_transpose2d(x, wt, None, 2, 1)
+    dy = torch.from_numpy(rs.standard_normal(tuple(y.shape)))
+    y.backward(dy)
+    dx = torch.nn.functional.conv2d(dy, wt, None, 2, 1)                 # wt read as a Conv2d weight [out=Ci, in=Co, 4, 4]
+    assert (dx - x.grad).abs().max().item() < 1e-10
+    cols = torch.from_numpy(_explicit_im2col(dy.permute(0, 2, 3, 1).numpy()))          # [B*IH*IW, (kh, kw, co)]
+    xm = x.detach().permute(0, 2, 3, 1).reshape(-1, Ci)                                  # [B*IH*IW, Ci]
+    dwt = (cols.t() @ xm).reshape(4, 4, Co, Ci).permute(3, 2, 0, 1)                      # -> [Ci, Co, kh, kw]
+    assert (dwt - wt.grad).abs().max().item() < 1e-9
