@@ -67,6 +67,6 @@ tot = {}
 for n, (desc, fl), s, e in recs:
     ms = s.elapsed_time(e)
     tot[n] = tot.get(n, 0.0) + ms
-    if ms > 0.05:
+    if ms > float(os.environ.get("MVAE_TIMES_MIN_MS", "0.05")):
         print(f"{n:22s} {ms * 1e3:8.1f} us  {fl / ms / 1e9 if fl else 0:7.1f} TFLOP/s  {desc[:150]}")
 print({k: round(v, 3) for k, v in sorted(tot.items(), key=lambda kv: -kv[1])})
