@@ -252,7 +252,10 @@ int mvae_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, floa
  *   tail_out          : [tail] sums over ranks of the tail floats (each rank computes them for itself)
  *   step_count        : device int32 Adam step counter; read by the kernel, incremented at its end (the launch can sit
  *                       in a CUDA graph that is replayed every step)
- * Every rank of the group must enqueue the call once per step (it spins, bounded at ~17 s, until the peers arrive). */
+ * Every rank of the group must enqueue the SAME sequence of these calls (it spins, bounded at ~9 s, until the peers arrive).
+ * The flags carry an explicit exchange number: a peer that is at a different exchange, or that does not arrive in time,
+ * sets the sticky error word flag_ptrs[rank][2*world] (1 = timeout, 2 = exchange-number mismatch); the rank then skips its
+ * Adam update and every parameter store of this and all later launches -- the host must check the word. */
 int mvae_allreduce_adam_p2p(float* const* grad_ptrs, float* const* param_ptrs, uint32_t* const* flag_ptrs, float* m,
                             float* v, int64_t n, int tail, float* tail_out, int rank, int world, float lr,
                             const float* lr_mult_dev, float beta1, float beta2, float eps, int32_t* step_count,

@@ -17,9 +17,14 @@
 //              all peers before the kernel ends: when the kernel is over, the local parameters are complete and nobody
 //              reads this rank's gradients any more (the next step zeroes them).
 //
-// Flags carry a 1-based launch number kept in the flag array itself (word 2N+2, advanced by the kernel), so a captured
-// CUDA graph replays unchanged and the numbering survives the caller resetting its Adam step counter.
-// All spins are bounded (~17 s): a missing peer raises the error word instead of hanging the GPU.
+// Flags carry an explicit 1-based exchange number (the "epoch") kept in the flag array itself (word 2N+2, advanced by the
+// kernel), so a captured CUDA graph replays unchanged and the numbering survives the caller resetting its Adam step
+// counter.  The protocol keeps the ranks in lockstep by construction (nobody can finish exchange e before every peer has
+// entered it), so a flag that ends a wait must EQUAL the local epoch; anything else means the ranks did not launch the
+// same sequence of exchanges (e.g. a rank ran an extra warm-up step) and is reported instead of being papered over.
+// Failure behaviour (sticky error word 2N: 1 = a peer did not arrive within ~9 s, 2 = a peer is at a different epoch):
+// the rank that sees it skips its Adam update and all its parameter stores, every later launch does the same, and the
+// host raises at its next synchronisation point (trainer.check_device_errors) -- no silent training on partial sums.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -30,7 +35,7 @@ namespace mvae {
 namespace {
 
 constexpr int kMaxWorld = 16;
-constexpr long long kSpinTimeout = 1LL << 35;   // cycles (~17 s)
+constexpr long long kSpinTimeout = 1LL << 34;   // cycles (~9 s)
 
 struct P2PArgs {
   float* grads[kMaxWorld];        // peer-mapped gradient buckets (n + tail floats), rank order
@@ -66,27 +71,48 @@ __device__ __forceinline__ void st_peer(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// wait until every peer wrote `epoch` into my flag words [base, base + N)
-__device__ __forceinline__ void wait_all(const P2PArgs& a, int base, uint32_t epoch) {
+// A rank that gives up tells its peers so (both of its flag slots in every peer's array get an impossible exchange
+// number): they fail fast with "mismatch" instead of each waiting for its own timeout.
+constexpr uint32_t kPoison = 0xFFFFFFFFu;
+__device__ __forceinline__ void poison_peers(const P2PArgs& a) {
+  for (int p = 0; p < a.world; ++p) {
+    if (p == a.rank) continue;
+    st_release_sys(a.flags[p] + a.rank, kPoison);
+    st_release_sys(a.flags[p] + a.world + a.rank, kPoison);
+  }
+}
+
+// Wait until every peer wrote `epoch` into my flag words [base, base + N).  Returns 0, or the error code that was also
+// recorded in the sticky error word: 1 = timeout, 2 = a peer's flag carries a different exchange number.
+__device__ __forceinline__ uint32_t wait_all(const P2PArgs& a, int base, uint32_t epoch) {
   uint32_t* mine = a.flags[a.rank];
   const long long t0 = clock64();
   for (int p = 0; p < a.world; ++p) {
-    while (ld_acquire_sys(mine + base + p) < epoch) {
-      __nanosleep(200);
+    uint32_t v;
+    while ((v = ld_acquire_sys(mine + base + p)) < epoch) {
+      __nanosleep(100);
+      if (*reinterpret_cast<volatile uint32_t*>(mine + 2 * a.world) != 0u) return 1u;   // another block already gave up
       if (clock64() - t0 > kSpinTimeout) {
-        atomicExch(mine + 2 * a.world, 1u);
-        return;
+        if (atomicCAS(mine + 2 * a.world, 0u, 1u) == 0u) poison_peers(a);
+        return 1u;
       }
     }
+    if (v != epoch) {
+      if (atomicCAS(mine + 2 * a.world, 0u, 2u) == 0u) poison_peers(a);
+      return 2u;
+    }
   }
+  return 0u;
 }
 
 __global__ void __launch_bounds__(256) allreduce_adam_p2p_kernel(const P2PArgs a) {
   __shared__ float s_step_size, s_inv_sqrt_bc2;
   __shared__ int s_last;
+  __shared__ uint32_t s_err;
   const int N = a.world;
   const uint32_t epoch = a.flags[a.rank][2 * N + 2] + 1u;               // same on every rank: all launch in lockstep
   const int adam_t = *a.step_count + 1;
+  const uint32_t sticky = *reinterpret_cast<volatile uint32_t*>(a.flags[a.rank] + 2 * N);   // an earlier exchange failed
   // ---- barrier 1: my gradients are final (this kernel is stream-ordered after my backward pass)
   if (blockIdx.x == 0 && threadIdx.x < N) st_release_sys(a.flags[threadIdx.x] + a.rank, epoch);
   if (threadIdx.x == 0) {
@@ -95,13 +121,14 @@ __global__ void __launch_bounds__(256) allreduce_adam_p2p_kernel(const P2PArgs a
     const double bc2 = 1.0 - pow(static_cast<double>(a.beta2), adam_t);
     s_step_size = static_cast<float>(lr_eff / bc1);
     s_inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(bc2));
-    wait_all(a, 0, epoch);          // every block polls its own (local) copy of the flags
+    s_err = sticky != 0u ? sticky : wait_all(a, 0, epoch);          // every block polls its own (local) copy of the flags
   }
   __syncthreads();
   const float step_size = s_step_size, inv_sqrt_bc2 = s_inv_sqrt_bc2;
-  // ---- my slice: reduce over peers, Adam, broadcast
+  const bool ok = s_err == 0u;
+  // ---- my slice: reduce over peers, Adam, broadcast (skipped entirely after a failed rendezvous)
   const int64_t begin = a.chunk * a.rank;
-  const int64_t end = begin + a.chunk < a.n ? begin + a.chunk : a.n;
+  const int64_t end = !ok ? begin : (begin + a.chunk < a.n ? begin + a.chunk : a.n);
   for (int64_t i = begin + (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < end;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x * 4) {
     // (the arena pads every tensor to a multiple of 4 floats and n itself is a multiple of 4)
@@ -127,7 +154,7 @@ __global__ void __launch_bounds__(256) allreduce_adam_p2p_kernel(const P2PArgs a
     for (int p = 0; p < N; ++p) st_peer(a.params[p] + i, P);
   }
   // ---- loss scalars behind the gradients: every rank sums them for itself
-  if (blockIdx.x == 0 && threadIdx.x < a.tail) {
+  if (ok && blockIdx.x == 0 && threadIdx.x < a.tail) {
     float s = 0.f;
     for (int p = 0; p < N; ++p) {
       float t;
@@ -146,10 +173,10 @@ __global__ void __launch_bounds__(256) allreduce_adam_p2p_kernel(const P2PArgs a
     __threadfence_system();
     if (threadIdx.x < N) st_release_sys(a.flags[threadIdx.x] + N + a.rank, epoch);
     if (threadIdx.x == 0) {
-      wait_all(a, N, epoch);
+      const uint32_t err2 = sticky != 0u ? sticky : wait_all(a, N, epoch);
       mine[2 * N + 1] = 0u;                       // done counter ready for the next launch
       mine[2 * N + 2] = epoch;                    // (every block read both counters at its start)
-      *a.step_count = adam_t;
+      if (err2 == 0u && *reinterpret_cast<volatile uint32_t*>(mine + 2 * N) == 0u) *a.step_count = adam_t;
       __threadfence_system();
     }
   }

@@ -164,8 +164,12 @@ class MnistMVAETrainer:
             # default "nccl"; MVAE_DP=p2p (or dp_mode="p2p") selects the fused peer-memory kernel: verified bit-for-bit
             # against NCCL at 2 GPUs (+3.4 % step throughput), not yet validated at 4 and 8
             self.dp_mode = os.environ.get("MVAE_DP", "nccl") if dp_mode is None else dp_mode
-            if self.dp_mode == "p2p" and not self._p2p_possible():
-                self.dp_mode = "nccl"
+            if self.dp_mode not in ("nccl", "p2p", "auto"):
+                raise _lib.MvaeError(f"dp_mode must be 'nccl', 'p2p' or 'auto', got {self.dp_mode!r}")
+            if self.dp_mode in ("p2p", "auto"):
+                # every rank must take the same path (a rank that fell back to NCCL on its own would deadlock both the
+                # flag rendezvous and the collective): agree on the minimum over ranks
+                self.dp_mode = "p2p" if self._p2p_agreed() else "nccl"
         self._symm = {}
         self.arena = FlatArena(self.layout, self.dev, n_buffers=4, tail=4,   # params, grads(+loss tail), adam m, adam v
                                alloc=self._symm_alloc if self.dp_mode == "p2p" else None)
@@ -197,7 +201,10 @@ class MnistMVAETrainer:
             self._p2p_finish_setup(n, 4)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.beta_dev = torch.ones(1, dtype=torch.float32, device=dev)   # KL annealing factor
-        self.beta_host = torch.ones(1, dtype=torch.float32).pin_memory()
+        # pinned staging ring for the annealing factor: an asynchronous H2D copy reads the pinned word when the COPY runs,
+        # so one buffer reused by back-to-back sync=False steps could hand a step the next step's KL weight
+        self._beta_ring = [(torch.ones(1, dtype=torch.float32).pin_memory(), torch.cuda.Event()) for _ in range(8)]
+        self._beta_idx = 0
         self.loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self._graphs: Dict[Tuple[bool, bool], object] = {}
         self._stream = torch.cuda.Stream(device=dev)
@@ -470,19 +477,37 @@ class MnistMVAETrainer:
         import torch.distributed as dist
         return self.pg if self.pg is not None else dist.group.WORLD
 
-    def _p2p_possible(self) -> bool:
-        """Peer memory needs one GPU per rank on one node with P2P access (NVLink / NVSwitch)."""
-        try:
-            import torch.distributed as dist
-            import torch.distributed._symmetric_memory  # noqa: F401
-            if not dist.is_initialized() or dist.get_backend(self._group()) != "nccl":
-                return False
-            ndev = torch.cuda.device_count()
-            return ndev >= self.world and all(
-                torch.cuda.can_device_access_peer(self.dev.index or torch.cuda.current_device(), d)
-                for d in range(self.world) if d != (self.dev.index or torch.cuda.current_device()))
-        except Exception:  # noqa: BLE001
+    def _p2p_agreed(self) -> bool:
+        """Peer memory needs one GPU per rank on one node with P2P access (NVLink / NVSwitch) -- decided collectively: the
+        ranks exchange their device ordinals, every rank checks access to every other rank's device, and the answer is the
+        MIN over ranks."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
             return False
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+            if dist.get_backend(self._group()) != "nccl":
+                ok = 0
+        except Exception:  # noqa: BLE001
+            ok = 0
+        if ok == 0 and dist.get_backend(self._group()) != "nccl":
+            return False           # (a gloo group on CPU tensors: every rank sees the same backend, no vote needed)
+        me = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+        mine = torch.tensor([me], dtype=torch.int64, device=self.dev)
+        devs = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(devs, mine, group=self._group())
+        devs = [int(d.item()) for d in devs]
+        if len(set(devs)) != self.world:          # two ranks on one GPU: no peer mapping to speak of
+            ok = 0
+        else:
+            try:
+                ok = min(ok, int(all(torch.cuda.can_device_access_peer(me, d) for d in devs if d != me)))
+            except Exception:  # noqa: BLE001
+                ok = 0
+        vote = torch.tensor([ok], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN, group=self._group())
+        return bool(vote.item())
 
     def _symm_alloc(self, i: int, numel: int):
         """Parameters (buffer 0) and gradients (buffer 1) live in symmetric memory so that every rank can address every
@@ -519,6 +544,31 @@ class MnistMVAETrainer:
             self._enqueue_update()
 
     # ------------------------------------------------------------------ public API
+    def _stage_beta(self, annealing_factor: float) -> None:
+        """KL annealing factor -> device scalar (call with the step stream current).  Ring of pinned words guarded by events:
+        a slot is rewritten only after the copy that read it has executed."""
+        buf, ev = self._beta_ring[self._beta_idx]
+        self._beta_idx = (self._beta_idx + 1) % len(self._beta_ring)
+        ev.synchronize()                 # (never recorded -> returns at once)
+        buf[0] = float(annealing_factor)
+        self.beta_dev.copy_(buf, non_blocking=True)
+        ev.record(self._stream)
+
+    def check_device_errors(self) -> None:
+        """Raise if a bounded device-side wait gave up since the last check: the chained GEMM's producer wait
+        (chain_ws[1]) or the peer-memory exchange's rendezvous (flag word 2*world).  Called at every host
+        synchronisation point (step(sync=True), flush(), synchronize()); costs one tiny D2H copy."""
+        bad = int(self.chain_ws[1].item())
+        if bad:
+            self.chain_ws[1] = 0
+            raise _lib.MvaeError("mvae_gemm_chain: a dependency wait timed out on the device (results of the last steps are "
+                                 "invalid); was the GPU time-sliced or a kernel of the chain preempted?")
+        if self.dp_mode == "p2p":
+            err = int(self._symm["flags"][2 * self.world].item())
+            if err:
+                raise _lib.MvaeError(f"mvae_allreduce_adam_p2p: rank {self.rank} gave up waiting for its peers (code {err}: "
+                                     "1 = timeout, 2 = a peer is at a different step); that step's update was skipped")
+
     def set_inputs(self, image: torch.Tensor, text: torch.Tensor, noise: Optional[torch.Tensor] = None,
                    annealing_factor: float = 1.0) -> None:
         """Stage one batch (host or device tensors) into the device-resident input buffers on the step stream.
@@ -527,12 +577,23 @@ class MnistMVAETrainer:
         with torch.cuda.stream(self._stream):
             self.x.copy_(image.reshape(B, 784), non_blocking=True)
             self.text.copy_(text.reshape(B), non_blocking=True)
-            self.beta_host[0] = float(annealing_factor)
-            self.beta_dev.copy_(self.beta_host, non_blocking=True)
+            self._stage_beta(annealing_factor)
             if noise is not None:
                 nz = self.noise.view(3, B, L)
                 for ref_i, int_i in enumerate(_REF_TO_INTERNAL):
                     nz[int_i].copy_(noise[ref_i], non_blocking=True)
+
+    def _warmup_state(self) -> List[torch.Tensor]:
+        """Every tensor an (eager, real) warm-up step may change and a later step reads: parameters, Adam moments and
+        step counter here; flavours add their non-arena state (BatchNorm running statistics ...)."""
+        return [self.flat_params, self.adam_m, self.adam_v, self.step_count]
+
+    def _warmup_snapshot(self):
+        return [t.clone() for t in self._warmup_state()]
+
+    def _warmup_restore(self, saved) -> None:
+        for t, s in zip(self._warmup_state(), saved):
+            t.copy_(s)
 
     def _capture(self, fn):
         g = torch.cuda.CUDAGraph()
@@ -554,11 +615,10 @@ class MnistMVAETrainer:
             gr = self._graphs.get(key)
             if gr is None:
                 # warm-up once eagerly (sets func attributes, loads modules, inits NCCL), then capture
-                saved = (self.flat_params.clone(), self.adam_m.clone(), self.adam_v.clone(), self.step_count.clone())
+                saved = self._warmup_snapshot()
                 self._enqueue_step(training, noise_given, update)
                 self._stream.synchronize()
-                self.flat_params.copy_(saved[0]); self.adam_m.copy_(saved[1]); self.adam_v.copy_(saved[2])
-                self.step_count.copy_(saved[3])
+                self._warmup_restore(saved)
                 self._stream.synchronize()
                 if self.world == 1 or (self.dp_mode == "p2p" and update):
                     # (p2p: the exchange is one of OUR kernels, so the whole step -- including it -- is one graph)
@@ -587,6 +647,7 @@ class MnistMVAETrainer:
             self.loss_host.copy_(self.loss_out, non_blocking=True)
         if sync:
             self._stream.synchronize()
+            self.check_device_errors()
             return float(self.loss_host[0])
         return None
 
@@ -615,27 +676,39 @@ class MnistMVAETrainer:
             raise _lib.MvaeError(f"step_from_dataset: idx must be a CUDA int64 tensor of {self.B} row indices")
         with torch.cuda.stream(self._stream):
             ops.gather_batch_u8(self.ds_images, self.ds_labels, idx.contiguous(), self.x, self.text)
-            self.beta_host[0] = float(annealing_factor)
-            self.beta_dev.copy_(self.beta_host, non_blocking=True)
+            self._stage_beta(annealing_factor)
         self.run(training=training, noise_given=False, update=update)
         with torch.cuda.stream(self._stream):
             self.loss_host.copy_(self.loss_out, non_blocking=True)
         if sync:
             self._stream.synchronize()
+            self.check_device_errors()
             return float(self.loss_host[0])
         return None
 
     # ------------------------------------------------------------------ host-fed, double-buffered stepping
-    def _pipe_init(self) -> None:
+    # flavour hooks of the pipelined path: shapes of one staged batch, and how a staged batch becomes the step's inputs
+    def _pipe_slot_tensors(self) -> Dict[str, torch.Tensor]:
         B, dev = self.B, self.dev
-        self._copy_stream = torch.cuda.Stream(device=dev)
+        return {"img": torch.empty(B, 784, dtype=torch.float32, device=dev),
+                "oth": torch.empty(B, dtype=torch.int64, device=dev)}
+
+    def _pipe_consume(self, slot) -> None:
+        """(step stream current) staged batch -> the device-resident input buffers the step reads."""
+        self.x.copy_(slot["img"], non_blocking=True)
+        self.text.copy_(slot["oth"], non_blocking=True)
+
+    def _pipe_after_run(self, training: bool, update: bool) -> None:
+        pass
+
+    def _pipe_init(self) -> None:
+        self._copy_stream = torch.cuda.Stream(device=self.dev)
         self._pipe = []
         for _ in range(2):
-            slot = {"img": torch.empty(B, 784, dtype=torch.float32, device=dev),
-                    "txt": torch.empty(B, dtype=torch.int64, device=dev),
-                    "beta": torch.ones(1, dtype=torch.float32).pin_memory(),
-                    "loss": torch.zeros(4, dtype=torch.float32).pin_memory(),
-                    "up": torch.cuda.Event(), "free": torch.cuda.Event(), "done": torch.cuda.Event(), "busy": False}
+            slot = dict(self._pipe_slot_tensors())
+            slot.update({"beta": torch.ones(1, dtype=torch.float32).pin_memory(),
+                         "loss": torch.zeros(4, dtype=torch.float32).pin_memory(),
+                         "up": torch.cuda.Event(), "free": torch.cuda.Event(), "done": torch.cuda.Event(), "busy": False})
             slot["free"].record(self._stream)
             self._pipe.append(slot)
         self._pipe_idx = 0
@@ -646,26 +719,25 @@ class MnistMVAETrainer:
         stream while the previous step is still computing, and the loss that is read back (and returned) is the
         PREVIOUS call's -- the usual one-step-lagged logging of an asynchronous training loop.  Returns None on the
         first call; ``flush()`` returns the last loss.  Every call still moves one batch host->device and one loss
-        device->host."""
+        device->host.  (``text`` = labels [B] for the MNIST-shape flavours, attrs [B,18] for CelebA.)"""
         if not hasattr(self, "_pipe"):
             self._pipe_init()
-        B = self.B
         k = self._pipe_idx
         self._pipe_idx ^= 1
         cur, prev = self._pipe[k], self._pipe[k ^ 1]
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(cur["free"])            # the compute stream finished reading this staging slot
-            cur["img"].copy_(image.reshape(B, 784), non_blocking=True)
-            cur["txt"].copy_(text.reshape(B), non_blocking=True)
+            cur["img"].copy_(image.reshape(cur["img"].shape), non_blocking=True)
+            cur["oth"].copy_(text.reshape(cur["oth"].shape), non_blocking=True)
             cur["up"].record(self._copy_stream)
         with torch.cuda.stream(self._stream):
             self._stream.wait_event(cur["up"])
-            self.x.copy_(cur["img"], non_blocking=True)
-            self.text.copy_(cur["txt"], non_blocking=True)
+            self._pipe_consume(cur)
             cur["free"].record(self._stream)
             cur["beta"][0] = float(annealing_factor)
             self.beta_dev.copy_(cur["beta"], non_blocking=True)
         self.run(training=training, noise_given=False, update=update)
+        self._pipe_after_run(training, update)
         with torch.cuda.stream(self._stream):
             cur["loss"].copy_(self.loss_out, non_blocking=True)
             cur["done"].record(self._stream)
@@ -686,6 +758,7 @@ class MnistMVAETrainer:
                     slot["busy"] = False
                     out = float(slot["loss"][0])
                     self.loss_host.copy_(slot["loss"])
+        self.check_device_errors()
         return out
 
     def losses(self) -> Dict[str, float]:
@@ -696,3 +769,4 @@ class MnistMVAETrainer:
 
     def synchronize(self) -> None:
         self._stream.synchronize()
+        self.check_device_errors()

@@ -237,8 +237,7 @@ class CelebAMVAETrainer(MnistMVAETrainer):
             self.x_nchw.copy_(image.reshape(B, 3 * 4096), non_blocking=True)
             ops.nchw_to_nhwc(self.x_nchw, self.x, B, 3, 4096)
             self.a_in[:, :N_ATTRS].copy_(attrs.reshape(B, N_ATTRS).to(torch.float32), non_blocking=True)
-            self.beta_host[0] = float(annealing_factor)
-            self.beta_dev.copy_(self.beta_host, non_blocking=True)
+            self._stage_beta(annealing_factor)
             if noise is not None:
                 nz = self.noise.view(3, B, L)
                 for ref_i, int_i in enumerate(_REF_TO_INTERNAL):
@@ -259,14 +258,28 @@ class CelebAMVAETrainer(MnistMVAETrainer):
             self.loss_host.copy_(self.loss_out, non_blocking=True)
         if sync:
             self._stream.synchronize()
+            self.check_device_errors()
             return float(self.loss_host[0])
         return None
 
     def attach_dataset(self, *a, **k):  # pragma: no cover
         raise _lib.MvaeError("the device-resident dataset path is implemented for the MNIST-shape trainers")
 
-    def step_pipelined(self, *a, **k):  # pragma: no cover
-        raise _lib.MvaeError("step_pipelined is implemented for the MNIST-shape trainers; use step() for CelebA")
+    # ---- pipelined host path (base class step_pipelined): one staged batch = NCHW image + [B,18] attrs
+    def _pipe_slot_tensors(self):
+        B, dev = self.B, self.dev
+        return {"img": torch.empty(B, 3 * 4096, dtype=torch.float32, device=dev),
+                "oth": torch.empty(B, N_ATTRS, dtype=torch.float32, device=dev)}
+
+    def _pipe_consume(self, slot) -> None:
+        ops.nchw_to_nhwc(slot["img"], self.x, self.B, 3, 4096)      # the layout change IS the copy out of the staging slot
+        self.a_in[:, :N_ATTRS].copy_(slot["oth"], non_blocking=True)
+        self._masks_given = False
+
+    def _pipe_after_run(self, training: bool, update: bool) -> None:
+        if training and update:
+            for p in _BN_LAYERS:
+                self.num_batches_tracked[p] += 3 if p.startswith(("image_decoder", "attrs_decoder")) else 2
 
     def run(self, training: bool = True, noise_given: bool = False, update: bool = True) -> None:
         # the graph key must also distinguish injected vs generated dropout masks
@@ -276,6 +289,11 @@ class CelebAMVAETrainer(MnistMVAETrainer):
             self._graphs.pop(key[:3])
         self._graphs[("variant", key[:3])] = self._graph_variant
         super().run(training=training, noise_given=noise_given, update=update)
+
+    def _warmup_state(self):
+        # BatchNorm running statistics live outside the arena and ARE updated by the eager warm-up step that precedes a
+        # graph capture: without restoring them the first step of every graph key applied the momentum update twice
+        return super()._warmup_state() + [self.buffers[k] for k in sorted(self.buffers)]
 
     # ------------------------------------------------------------------ helpers
     def _bn_f(self, x, h, S, seg_rows, prefix, order, training, act=True):

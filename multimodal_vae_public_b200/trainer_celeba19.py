@@ -274,8 +274,12 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
                     self.num_batches_tracked[p] += plan["n_img"] if p.startswith("image_encoder") else plan["P"]
         if sync:
             self._stream.synchronize()
+            self.check_device_errors()
             return float(self.loss19.item())
         return None
+
+    def step_pipelined(self, *a, **k):  # pragma: no cover
+        raise _lib.MvaeError("step_pipelined: the 19-expert flavour re-plans its passes on the host every step; use step()")
 
     def losses(self):
         """Per-pass ELBO terms in the reference's order (after a synchronised step)."""

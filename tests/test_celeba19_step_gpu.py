@@ -65,9 +65,9 @@ def test_celeba19_step_matches_reference_golden():
             np.testing.assert_allclose(sd[k].cpu().numpy(), ce[f"buffer/{k}"], rtol=2e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize("case", ["mixed", "no_image", "all_image"])
-def test_celeba19_step_matches_oracle_fp64(case):
-    B = 8
+@pytest.mark.parametrize("case,B", [("mixed", 8), ("no_image", 8), ("all_image", 8), ("mixed", 64), ("mixed", 512)])
+def test_celeba19_step_matches_oracle_fp64(case, B):
+    # B = 512: BASELINE.json configs[4]; B = 64: its per-GPU batch at 8 GPUs (the fp64 oracle step takes ~30 s of CPU)
     rs = np.random.RandomState(4)
     combos = np.zeros((3, 19), dtype=bool)
     if case == "mixed":

@@ -60,8 +60,9 @@ def test_celeba_step_matches_reference_golden(mode):
                 np.testing.assert_allclose(sd[k].cpu().numpy(), ce[f"train_buffer/{k}"], rtol=2e-4, atol=2e-5)
 
 
-def test_celeba_step_matches_oracle_fp64():
-    B = 24
+@pytest.mark.parametrize("B", [24, 128, 1024])
+def test_celeba_step_matches_oracle_fp64(B):
+    # B = 1024: BASELINE.json configs[3]; B = 128: its per-GPU batch at 8 GPUs (BatchNorm statistics are per shard)
     rs = np.random.RandomState(3)
     image = torch.from_numpy(rs.uniform(0, 1, (B, 3, 64, 64)).astype(np.float32))
     attrs = torch.from_numpy(rs.randint(0, 2, (B, 18)).astype(np.float32))
@@ -83,3 +84,56 @@ def test_celeba_step_matches_oracle_fp64():
     sd = tr.state_dict()
     for k, v in bufs.items():
         np.testing.assert_allclose(sd[k].cpu().numpy(), v.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_graph_warmup_does_not_touch_running_statistics():
+    """use_graph=True captures after one eager warm-up step; that warm-up is a REAL step and must leave no trace: after
+    one and after two steps the BatchNorm running statistics, num_batches_tracked and the parameters equal those of the
+    eager (use_graph=False) trainer.  (Round-1 defect: the warm-up's momentum update was applied a second time.)"""
+    from multimodal_vae_public_b200.trainer_celeba import CelebAMVAETrainer
+    B = 16
+    rs = np.random.RandomState(9)
+    image = torch.from_numpy(rs.uniform(0, 1, (B, 3, 64, 64)).astype(np.float32))
+    attrs = torch.from_numpy(rs.randint(0, 2, (B, 18)).astype(np.float32))
+    noise = torch.from_numpy(rs.standard_normal((3, B, L)).astype(np.float32))
+    masks = torch.from_numpy((rs.uniform(0, 1, (2, B, 512)) > 0.1).astype(np.float32))
+    st = CO.make_celeba_state(L, seed=4)
+    a = CelebAMVAETrainer(n_latents=L, batch_size=B, use_graph=False)
+    b = CelebAMVAETrainer(n_latents=L, batch_size=B, use_graph=True)
+    a.load_state_dict(st); b.load_state_dict(st)
+    for it in range(2):
+        la = a.step(image, attrs, annealing_factor=0.5, noise=noise, drop_masks=masks)
+        lb = b.step(image, attrs, annealing_factor=0.5, noise=noise, drop_masks=masks)
+        assert abs(la - lb) <= 2e-6 * abs(la), (it, la, lb)
+        sa, sb = a.state_dict(), b.state_dict()
+        for k in sa:
+            if "running_" in k:
+                np.testing.assert_allclose(sb[k].cpu().numpy(), sa[k].cpu().numpy(), rtol=1e-5, atol=1e-6, err_msg=f"{k} step {it}")
+            elif k.endswith("num_batches_tracked"):
+                assert int(sa[k]) == int(sb[k]), (k, it)
+    for k in a.params:
+        assert (a.params[k] - b.params[k]).abs().max().item() <= 2e-5, k
+
+
+def test_pipelined_host_fed_steps_equal_synchronous_steps():
+    """step_pipelined (H2D of batch i+1 overlaps step i, loss read one step late) == step, eval mode (no noise / masks)."""
+    from multimodal_vae_public_b200.trainer_celeba import CelebAMVAETrainer
+    B = 8
+    rs = np.random.RandomState(12)
+    batches = [(torch.from_numpy(rs.uniform(0, 1, (B, 3, 64, 64)).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rs.randint(0, 2, (B, 18)).astype(np.float32)).pin_memory()) for _ in range(4)]
+    a = CelebAMVAETrainer(n_latents=L, batch_size=B, use_graph=True)
+    b = CelebAMVAETrainer(n_latents=L, batch_size=B, use_graph=True)
+    b.load_state_dict(a.state_dict())
+    ref = [a.step(im, at, annealing_factor=0.5, training=False) for im, at in batches]
+    got = []
+    for im, at in batches:
+        v = b.step_pipelined(im, at, annealing_factor=0.5, training=False)
+        if v is not None:
+            got.append(v)
+    got.append(b.flush())
+    assert len(got) == len(ref)
+    for x, y in zip(ref, got):
+        assert abs(x - y) <= 2e-6 * abs(x)
+    for k in a.params:
+        assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-5, k

@@ -1,6 +1,8 @@
 """The data-parallel exchange as one fused kernel per rank over NVLink peer memory (mvae_allreduce_adam_p2p: gradient
 reduce-scatter by peer loads -> Adam on the rank's slice -> parameter all-gather by peer stores) must reproduce the
-single-process full-batch trajectory, exactly like the NCCL + flat-Adam path does.  Needs two GPUs with peer access."""
+single-process full-batch trajectory, exactly like the NCCL + flat-Adam path does.  Needs 2 / 4 / 8 GPUs with peer access
+(the cases a box cannot run are skipped; `gpurun --gpus 8 -- python -m pytest tests/test_dp_p2p_gpu.py` runs them all --
+log committed under profiles/)."""
 import os
 import socket
 
@@ -44,11 +46,12 @@ def _worker(rank, world, port, B, L, out, use_graph, mode):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_p2p_exchange_matches_single_process_and_nccl(tmp_path, use_graph):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    B, L, world = 256, 64, 2
+def test_p2p_exchange_matches_single_process_and_nccl(tmp_path, use_graph, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    B, L = 128 * world, 64
     res = {}
     for mode in ("p2p", "nccl"):
         out = str(tmp_path / f"dp_{mode}.pt")
@@ -60,11 +63,59 @@ def test_p2p_exchange_matches_single_process_and_nccl(tmp_path, use_graph):
     ref_losses = [ref.step(image, text, annealing_factor=0.25 * (it + 1), noise=noise) for it in range(4)]
     ref_losses.append(ref.step(image, text, annealing_factor=1.0, noise=noise, update=False))
     for mode in ("p2p", "nccl"):
-        r0, r1 = res[mode]
-        assert r0["err"] == 0 and r1["err"] == 0
+        r0 = res[mode][0]
+        assert all(r["err"] == 0 for r in res[mode])
         for it, l in enumerate(ref_losses):
+            assert np.isfinite(r0["losses"][it])
             assert abs(l - r0["losses"][it]) <= 2e-6 * abs(l), (mode, it, l, r0["losses"][it])
-            assert r0["losses"][it] == r1["losses"][it]          # every rank reports the same global loss
+            for r in res[mode][1:]:
+                assert r0["losses"][it] == r["losses"][it]          # every rank reports the same global loss
         for k, v in ref.params.items():
-            assert torch.equal(r0["params"][k], r1["params"][k]), k       # replicas stay bit-identical
+            for r in res[mode][1:]:
+                assert torch.equal(r0["params"][k], r["params"][k]), k       # replicas stay bit-identical
             assert (v.cpu() - r0["params"][k]).abs().max().item() <= 1e-4, (mode, k)
+
+
+def _worker_desync(rank, world, port, out):
+    """Rank 0 launches one exchange more than its peers: the flags' exchange numbers no longer match, the kernel must
+    record error 2 (not quietly reduce half-written gradients) and the host must raise at its next sync point."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from multimodal_vae_public_b200 import _lib
+    from multimodal_vae_public_b200.trainer import MnistMVAETrainer
+    B, L = 64, 64
+    image, text, noise = _data(B * world, L)
+    sl = slice(rank * B, (rank + 1) * B)
+    tr = MnistMVAETrainer(L, B, device=f"cuda:{rank}", world_size=world, rank=rank, seed=0, use_graph=False, dp_mode="p2p")
+    tr.step(image[sl], text[sl], noise=noise[:, sl])
+    dist.barrier()
+    flags = tr._symm["flags"]
+    if rank == 0:
+        flags[2 * world + 2] += 1           # as if this rank had run one more exchange than the others
+    torch.cuda.synchronize(); dist.barrier()
+    raised = False
+    p_before = tr.flat_params.clone()
+    try:
+        tr.step(image[sl], text[sl], noise=noise[:, sl])
+    except _lib.MvaeError:
+        raised = True
+    torch.cuda.synchronize()
+    torch.save({"raised": raised, "err": int(flags[2 * world].item()),
+                "unchanged": bool(torch.equal(p_before[tr.arena.numel // world * rank:][:1024],
+                                              tr.flat_params[tr.arena.numel // world * rank:][:1024]))}, f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_p2p_exchange_number_mismatch_is_reported(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = str(tmp_path / "desync.pt")
+    mp.spawn(_worker_desync, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = [torch.load(f"{out}.{k}") for k in range(2)]
+    # rank 1 sees rank 0's flag carrying a LARGER exchange number than its own: mismatch, update skipped, host raises;
+    # rank 0 waits for a number rank 1 never writes in this launch (it would time out) unless it sees the error first --
+    # whichever code it records, it must not apply an update either
+    assert r[1]["err"] == 2 and r[1]["raised"] and r[1]["unchanged"]
+    assert r[0]["err"] != 0 and r[0]["raised"] and r[0]["unchanged"]

@@ -81,8 +81,9 @@ def test_fashion_step_matches_reference_golden(prec):
         assert abs(g.double().norm().item() - d[2]) <= 5 * gt * d[2] + 1e-7, k
 
 
-@pytest.mark.parametrize("B", [32, 130])
+@pytest.mark.parametrize("B", [32, 130, 512, 4096])
 def test_fashion_step_matches_oracle_fp64(B):
+    # B = 4096: BASELINE.json configs[2]; B = 512: its per-GPU batch at 8 GPUs (the fp64 oracle step takes ~15 s of CPU)
     L = 64
     rs = np.random.RandomState(B)
     image = torch.from_numpy(rs.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32))

@@ -6,7 +6,9 @@ It checks the protocol's safety claims for 2..8 ranks and many launches:
     zeroed for the next step);
   * a rank's parameters are only written by peers while it is inside the exchange kernel of that launch (never during
     its forward / backward);
-  * nobody dead-locks, and the flag words only ever grow (launch numbers are reused as epochs).
+  * nobody dead-locks, and the flag words only ever grow (launch numbers are reused as epochs);
+  * the value that ends a wait always EQUALS the waiter's own launch number (the kernel reports anything else as a
+    lockstep violation instead of proceeding: error code 2 of dp_p2p.cu).
 This guards the LOGIC (barrier 1 / slice work / barrier 2, epoch reuse); memory-ordering questions are the kernel's."""
 import random
 import threading
@@ -45,6 +47,9 @@ def rank_thread(w: World, r: int, launches: int, rng: random.Random):
                 if time.time() - t0 > 20:
                     w.errors.append(f"rank {r}: deadlock waiting for rank {p} at launch {e}")
                     return False
+            if flags[r][p] != e:        # the kernel's "exchange-number mismatch" check must never fire in lockstep
+                w.errors.append(f"rank {r} launch {e}: rank {p}'s flag reads {flags[r][p]}")
+                return False
         return True
 
     for e in range(1, launches + 1):
