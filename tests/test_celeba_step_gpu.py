@@ -111,8 +111,12 @@ def test_graph_warmup_does_not_touch_running_statistics():
                 np.testing.assert_allclose(sb[k].cpu().numpy(), sa[k].cpu().numpy(), rtol=1e-5, atol=1e-6, err_msg=f"{k} step {it}")
             elif k.endswith("num_batches_tracked"):
                 assert int(sa[k]) == int(sb[k]), (k, it)
+    # parameters: a Linear bias that feeds a BatchNorm has an exactly-zero gradient in exact arithmetic; what reaches Adam is
+    # rounding noise whose sign depends on the order of the atomics, and Adam turns noise into +-lr per step -- so
+    # "equal" here means within 2 steps x lr (1e-4), everything else agrees far tighter
     for k in a.params:
-        assert (a.params[k] - b.params[k]).abs().max().item() <= 2e-5, k
+        tol = 2.5e-4 if k.endswith(".bias") else 2e-5
+        assert (a.params[k] - b.params[k]).abs().max().item() <= tol, k
 
 
 def test_pipelined_host_fed_steps_equal_synchronous_steps():
