@@ -147,6 +147,35 @@ int mvae_poe_bwd(const float* const* mu_e, const float* const* lv_e, int64_t ld_
                  const float* dmu_up, const float* dlv_up, float kl_scale, const float* kl_scale_dev,
                  float* const* dmu_e, float* const* dlv_e, int64_t ldd_e, void* stream);
 
+/* The same two kernels with an optional ROW INDEX per expert (gather_idx[e] = int64 [B] or NULL; gather_idx itself may be
+ * NULL): expert e is then a V-row table -- the label / attribute encoders of mnist/model.py:108-125 only ever see V
+ * distinct inputs, see mvae_label_table_fwd -- whose row gather_idx[e][b] is sample b's (mu | logvar); in backward the
+ * sample's gradient is ADDED (red.add) into row gather_idx[e][b] of dmu_e[e] / dlv_e[e], which the caller zero-initialises
+ * (this is the segmented sum by class that Embedding's autograd performs, mnist/model.py:116).                      */
+int mvae_poe_fwd_g(const float* const* mu_e, const float* const* lv_e, int64_t ld_e, int E,
+                   const int64_t* const* gather_idx, const uint32_t* pass_masks, int P, int B, int L, int variant,
+                   int training, const float* noise, float* noise_out, uint64_t seed, uint64_t offset,
+                   const int32_t* step_dev, float* z, int64_t ldz, float* mu_out, float* lv_out, double* kl_acc,
+                   void* stream);
+int mvae_poe_bwd_g(const float* const* mu_e, const float* const* lv_e, int64_t ld_e, int E,
+                   const int64_t* const* gather_idx, const uint32_t* pass_masks, int P, int B, int L, int variant,
+                   int training, const float* noise, const float* dz, int64_t lddz, const float* dmu_up,
+                   const float* dlv_up, float kl_scale, const float* kl_scale_dev, float* const* dmu_e,
+                   float* const* dlv_e, int64_t ldd_e, void* stream);
+
+/* Label encoder evaluated once per CLASS (V <= 16 rows) instead of once per sample: TextEncoder of mnist/model.py:108-125
+ * and fashionmnist/model.py:124-146 = Embedding(V, D) -> Swish -> Linear(D, D) -> Swish -> heads Linear(D, N3 = 2L).
+ *   fwd: a2 = swish(emb) w2^T + b2, h2 = swish(a2), tab = h2 w3^T + b3      (emb [V,D], w2 [D,D], w3 [N3,D], tab [V,N3])
+ *   bwd: given dtab [V,N3] (= class-wise sums of the per-sample gradients, accumulated by mvae_poe_bwd_g):
+ *        dw3 += dtab^T h2, db3 += colsum(dtab), dw2 += dA2^T swish(emb), db2 += colsum(dA2), d_emb += (dA2 w2) * swish'(emb)
+ *        with dA2 = (dtab w3) * swish'(a2) written to the scratch d_a2 [V,D].  Gradients ACCUMULATE (zero them once per
+ *        step like optimizer.zero_grad(), mnist/train.py:197).  Exact regrouping of the per-sample sums; plain fp32 FMA. */
+int mvae_label_table_fwd(const float* emb, const float* w2, const float* b2, const float* w3, const float* b3, float* a2,
+                         float* h2, float* tab, int V, int D, int N3, void* stream);
+int mvae_label_table_bwd(const float* emb, const float* w2, const float* w3, const float* a2, const float* h2,
+                         const float* dtab, float* d_a2, float* d_emb, float* dw2, float* db2, float* dw3, float* db3,
+                         int V, int D, int N3, void* stream);
+
 /* Stand-alone MVAE.reparametrize (mnist/model.py:29-35, training branch): z = noise*exp(0.5*logvar) + mu.
  * noise == NULL => Philox(seed, offset) draws written to noise_out.  Backward: dmu = dz (identity),
  * dlogvar = dz * noise * 0.5 * exp(0.5*logvar). */

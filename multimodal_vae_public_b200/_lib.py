@@ -55,6 +55,12 @@ SIGNATURES = {
                      _U64, _P, _P, _L, _P, _P, _P, _P],
     "mvae_poe_bwd": [C.POINTER(_P), C.POINTER(_P), _L, _I, C.POINTER(C.c_uint32), _I, _I, _I, _I, _I, _P, _P, _L, _P,
                      _P, _F, _P, C.POINTER(_P), C.POINTER(_P), _L, _P],
+    "mvae_poe_fwd_g": [C.POINTER(_P), C.POINTER(_P), _L, _I, C.POINTER(_P), C.POINTER(C.c_uint32), _I, _I, _I, _I, _I, _P, _P,
+                       _U64, _U64, _P, _P, _L, _P, _P, _P, _P],
+    "mvae_poe_bwd_g": [C.POINTER(_P), C.POINTER(_P), _L, _I, C.POINTER(_P), C.POINTER(C.c_uint32), _I, _I, _I, _I, _I, _P, _P,
+                       _L, _P, _P, _F, _P, C.POINTER(_P), C.POINTER(_P), _L, _P],
+    "mvae_label_table_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "mvae_label_table_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "mvae_kl_fwd_bwd": [_P, _P, _P, _P, _L, _F, _P, _P],
     "mvae_reparam_fwd": [_P, _P, _P, _P, _U64, _U64, _P, _L, _P],
     "mvae_reparam_bwd": [_P, _P, _P, _P, _L, _P],

@@ -126,6 +126,9 @@ struct PoeArgs {
   float kl_scale;
   const float* kl_scale_dev;
   int no_prior;          // 1: the implicit N(0,1) prior expert is NOT part of the product
+  // optional per-expert row index (label-table experts, csrc/label_table.cu): expert e's row for sample b is
+  // gidx[e][b] of a V-row table instead of row b; backward then red.add's the sample's gradient into that table row
+  const int64_t* gidx[kMaxExperts];
 };
 
 template <int VEC>
@@ -157,6 +160,211 @@ __device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
   }
 }
 
+// ---- MUFU forms for the bandwidth-bound fast path (ex2 / lg2 / rcp / sqrt: <= 2 ulp each; the outputs are compared
+// against the fp64 oracle at rtol 2e-5, tests/test_kernels_gpu.py).  The IEEE expf / logf / division forms cost ~10-20
+// instructions each and made these kernels instruction-bound: 1.9 TB/s at roofline size (profiles/r02_bench_v0_*).
+__device__ __forceinline__ float fexp(float x) { return __expf(x); }
+__device__ __forceinline__ float flog(float x) { return __logf(x); }
+__device__ __forceinline__ float frcp(float x) { return __fdividef(1.0f, x); }
+
+// Four N(0,1) draws from one Philox4x32-10 block, Box-Muller with MUFU log / sin / cos (|error| ~ 1e-6 on the draws:
+// irrelevant for noise; the stream stays a pure function of (seed, counter, step)).
+__device__ __forceinline__ void normal4_fast(uint64_t seed, uint64_t ctr, uint32_t step, float (&n)[4]) {
+  uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), step, 0x4d564145u};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const float u0 = (static_cast<float>(c[0]) + 0.5f) * 2.3283064365386963e-10f;
+  const float u1 = (static_cast<float>(c[1]) + 0.5f) * 2.3283064365386963e-10f;
+  const float u2 = (static_cast<float>(c[2]) + 0.5f) * 2.3283064365386963e-10f;
+  const float u3 = (static_cast<float>(c[3]) + 0.5f) * 2.3283064365386963e-10f;
+  const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1 - 3.141592653589793f, &s0, &c0);   // argument in [-pi, pi): MUFU range, full circle
+  __sincosf(6.283185307179586f * u3 - 3.141592653589793f, &s1, &c1);
+  n[0] = r0 * c0; n[1] = r0 * s0; n[2] = r1 * c1; n[3] = r1 * s1;
+}
+
+constexpr int kFastPasses = 4;   // passes whose KL partial sums a thread keeps in registers on the fast path
+
+// Fast path (E <= EMAX <= 4 experts, P <= 4 passes, L % 4 == 0, 16-byte aligned rows): one thread = 4 consecutive latent
+// dims of one sample, grid-stride over the samples, 128-bit loads / stores, MUFU math, KL partial sums in registers and
+// ONE double atomic per (block, pass) at the very end -- with one atomic per 256 threads per pass the same-address
+// atomics serialised in L2 at roofline size (16 K blocks x 3 passes on 3 addresses).
+template <int EMAX>
+__global__ void __launch_bounds__(256) poe_fwd_fast_kernel(const __grid_constant__ PoeArgs a) {
+  __shared__ double scratch[32];
+  const int l4n = a.L >> 2;
+  const int64_t total = static_cast<int64_t>(a.B) * l4n;
+  const float e1 = 1e-8f;
+  const float e2 = a.variant == 0 ? 1e-8f : 0.0f;
+  const float T0 = a.no_prior ? 0.0f : 1.0f / ((1.0f + e1) + e2);  // prior expert: mu = 0, logvar = 0
+  const uint32_t step = (a.training && a.noise == nullptr && a.step_dev) ? static_cast<uint32_t>(__ldg(a.step_dev)) : 0u;
+  float klacc[kFastPasses] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total;
+       gid += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(gid / l4n);
+    const int l = static_cast<int>(gid - static_cast<int64_t>(b) * l4n) * 4;
+    float T[EMAX][4], M[EMAX][4];
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      if (e < a.E) {
+        const int64_t row = a.gidx[e] ? __ldg(a.gidx[e] + b) : b;
+        float mu[4], lv[4];
+        load_vec<4>(a.mu_e[e] + row * a.ld_e + l, mu);
+        load_vec<4>(a.lv_e[e] + row * a.ld_e + l, lv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          T[e][q] = frcp((fexp(lv[q]) + e1) + e2);
+          M[e][q] = mu[q] * T[e][q];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { T[e][q] = 0.f; M[e][q] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kFastPasses; ++p) {
+      if (p < a.P) {
+        const uint32_t mask = a.masks[p];
+        float S[4], N[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { S[q] = T0; N[q] = 0.0f; }
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) {
+          if ((mask >> e) & 1u) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { S[q] += T[e][q]; N[q] += M[e][q]; }
+          }
+        }
+        const int64_t row = static_cast<int64_t>(p) * a.B + b;
+        float nz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.training) {
+          if (a.noise != nullptr) {
+            load_vec<4>(a.noise + row * a.L + l, nz);
+          } else {
+            normal4_fast(a.seed, a.offset + static_cast<uint64_t>(row) * l4n + (l >> 2), step, nz);
+            store_vec<4>(a.noise_out + row * a.L + l, nz);
+          }
+        }
+        float z[4], mu[4], lv[4];
+        float klf = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float pv = frcp(S[q]);
+          mu[q] = N[q] * pv;
+          const float ev = pv + e2;                 // = exp(logvar) of the fused posterior
+          lv[q] = flog(ev);
+          z[q] = a.training ? nz[q] * sqrtf(ev) + mu[q] : mu[q];        // exp(0.5 logvar) = sqrt(exp(logvar))
+          klf += 1.0f + lv[q] - mu[q] * mu[q] - ev;
+        }
+        klacc[p] += -0.5f * klf;
+        store_vec<4>(a.z + row * a.ldz + l, z);
+        if (a.mu_out) store_vec<4>(a.mu_out + row * a.L + l, mu);
+        if (a.lv_out) store_vec<4>(a.lv_out + row * a.L + l, lv);
+      }
+    }
+  }
+  if (a.kl_acc != nullptr) {
+#pragma unroll
+    for (int p = 0; p < kFastPasses; ++p)
+      if (p < a.P) block_atomic_add(static_cast<double>(klacc[p]), a.kl_acc + p, scratch);
+  }
+}
+
+template <int EMAX>
+__global__ void __launch_bounds__(256) poe_bwd_fast_kernel(const __grid_constant__ PoeArgs a) {
+  const int l4n = a.L >> 2;
+  const int64_t total = static_cast<int64_t>(a.B) * l4n;
+  const float e1 = 1e-8f;
+  const float e2 = a.variant == 0 ? 1e-8f : 0.0f;
+  const float kls = a.kl_scale * (a.kl_scale_dev ? __ldg(a.kl_scale_dev) : 1.0f);
+  const float T0 = a.no_prior ? 0.0f : 1.0f / ((1.0f + e1) + e2);
+  for (int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total;
+       gid += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(gid / l4n);
+    const int l = static_cast<int>(gid - static_cast<int64_t>(b) * l4n) * 4;
+    float T[EMAX][4], MU[EMAX][4], EX[EMAX][4], dMU[EMAX][4], dLV[EMAX][4];
+    int64_t erow[EMAX];
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { T[e][q] = 0.f; MU[e][q] = 0.f; EX[e][q] = 0.f; dMU[e][q] = 0.f; dLV[e][q] = 0.f; }
+      erow[e] = b;
+      if (e < a.E) {
+        if (a.gidx[e]) erow[e] = __ldg(a.gidx[e] + b);
+        float lv[4];
+        load_vec<4>(a.mu_e[e] + erow[e] * a.ld_e + l, MU[e]);
+        load_vec<4>(a.lv_e[e] + erow[e] * a.ld_e + l, lv);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          EX[e][q] = fexp(lv[q]);
+          T[e][q] = frcp((EX[e][q] + e1) + e2);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kFastPasses; ++p) {
+      if (p < a.P) {
+        const uint32_t mask = a.masks[p];
+        float S[4], N[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { S[q] = T0; N[q] = 0.f; }
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) {
+          if ((mask >> e) & 1u) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { S[q] += T[e][q]; N[q] += MU[e][q] * T[e][q]; }
+          }
+        }
+        const int64_t row = static_cast<int64_t>(p) * a.B + b;
+        float dz[4], nz[4] = {0.f, 0.f, 0.f, 0.f}, gmu_up[4] = {0.f, 0.f, 0.f, 0.f}, glv_up[4] = {0.f, 0.f, 0.f, 0.f};
+        load_vec<4>(a.dz + row * a.ldz + l, dz);
+        if (a.training) load_vec<4>(a.noise + row * a.L + l, nz);
+        if (a.dmu_up) load_vec<4>(a.dmu_up + row * a.L + l, gmu_up);
+        if (a.dlv_up) load_vec<4>(a.dlv_up + row * a.L + l, glv_up);
+        float g_mu[4], g_lvS[4], mu[4], invS[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          invS[q] = frcp(S[q]);
+          mu[q] = N[q] * invS[q];
+          const float pv = invS[q];
+          const float ev = pv + e2;                                 // exp(logvar)
+          g_mu[q] = dz[q] + gmu_up[q] + kls * mu[q];
+          float g_lv = glv_up[q] + kls * 0.5f * (ev - 1.0f);
+          if (a.training) g_lv += dz[q] * nz[q] * 0.5f * sqrtf(ev);
+          g_lvS[q] = g_lv * (-(pv * pv) * frcp(ev));                // d logvar / d S
+        }
+#pragma unroll
+        for (int e = 0; e < EMAX; ++e) {
+          if ((mask >> e) & 1u) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              dMU[e][q] += g_mu[q] * T[e][q] * invS[q];
+              const float dT = g_mu[q] * (MU[e][q] - mu[q]) * invS[q] + g_lvS[q];
+              dLV[e][q] += dT * (-(T[e][q] * T[e][q]) * EX[e][q]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EMAX; ++e) {
+      if (e < a.E) {
+        float* pm = a.dmu_e[e] + erow[e] * a.ldd_e + l;
+        float* pl = a.dlv_e[e] + erow[e] * a.ldd_e + l;
+        if (a.gidx[e]) {   // table-backed expert: all samples of a class add into the class's row
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pm), "f"(dMU[e][0]), "f"(dMU[e][1]),
+                       "f"(dMU[e][2]), "f"(dMU[e][3]) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pl), "f"(dLV[e][0]), "f"(dLV[e][1]),
+                       "f"(dLV[e][2]), "f"(dLV[e][3]) : "memory");
+        } else {
+          store_vec<4>(pm, dMU[e]);
+          store_vec<4>(pl, dLV[e]);
+        }
+      }
+    }
+  }
+}
+
 // One thread = VEC consecutive latent dims of one sample.  Expert precisions are computed once and
 // reused by every pass.
 template <int VEC, int EMAX>
@@ -174,8 +382,9 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const __grid_constant__ Po
   for (int e = 0; e < EMAX; ++e) {
     if (e < a.E && active) {
       float mu[VEC], lv[VEC];
-      load_vec<VEC>(a.mu_e[e] + static_cast<int64_t>(b) * a.ld_e + l, mu);
-      load_vec<VEC>(a.lv_e[e] + static_cast<int64_t>(b) * a.ld_e + l, lv);
+      const int64_t erow = a.gidx[e] ? a.gidx[e][b] : b;
+      load_vec<VEC>(a.mu_e[e] + erow * a.ld_e + l, mu);
+      load_vec<VEC>(a.lv_e[e] + erow * a.ld_e + l, lv);
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
         const float var = expf(lv[q]) + e1;
@@ -252,8 +461,9 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const __grid_constant__ Po
     for (int q = 0; q < VEC; ++q) { T[e][q] = 0.f; MU[e][q] = 0.f; EX[e][q] = 0.f; dMU[e][q] = 0.f; dLV[e][q] = 0.f; }
     if (e < a.E) {
       float lv[VEC];
-      load_vec<VEC>(a.mu_e[e] + static_cast<int64_t>(b) * a.ld_e + l, MU[e]);
-      load_vec<VEC>(a.lv_e[e] + static_cast<int64_t>(b) * a.ld_e + l, lv);
+      const int64_t erow = a.gidx[e] ? a.gidx[e][b] : b;
+      load_vec<VEC>(a.mu_e[e] + erow * a.ld_e + l, MU[e]);
+      load_vec<VEC>(a.lv_e[e] + erow * a.ld_e + l, lv);
 #pragma unroll
       for (int q = 0; q < VEC; ++q) {
         EX[e][q] = expf(lv[q]);
@@ -309,8 +519,17 @@ __global__ void __launch_bounds__(256) poe_bwd_kernel(const __grid_constant__ Po
 #pragma unroll
   for (int e = 0; e < EMAX; ++e) {
     if (e < a.E) {
-      store_vec<VEC>(a.dmu_e[e] + static_cast<int64_t>(b) * a.ldd_e + l, dMU[e]);
-      store_vec<VEC>(a.dlv_e[e] + static_cast<int64_t>(b) * a.ldd_e + l, dLV[e]);
+      if (a.gidx[e]) {
+        const int64_t erow = a.gidx[e][b];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          atomicAdd(a.dmu_e[e] + erow * a.ldd_e + l + q, dMU[e][q]);
+          atomicAdd(a.dlv_e[e] + erow * a.ldd_e + l + q, dLV[e][q]);
+        }
+      } else {
+        store_vec<VEC>(a.dmu_e[e] + static_cast<int64_t>(b) * a.ldd_e + l, dMU[e]);
+        store_vec<VEC>(a.dlv_e[e] + static_cast<int64_t>(b) * a.ldd_e + l, dLV[e]);
+      }
     }
   }
 }
@@ -688,7 +907,8 @@ __global__ void elbo_finalize_kernel(const double* recon_img, const double* reco
 }
 
 int fill_poe_args(PoeArgs& a, const float* const* mu_e, const float* const* lv_e, int64_t ld_e, int E,
-                  const uint32_t* masks, int P, int B, int L, int variant, int training) {
+                  const uint32_t* masks, int P, int B, int L, int variant, int training,
+                  const int64_t* const* gather_idx) {
   if (E < 1 || E > kMaxExperts) return set_error(MVAE_ERR_BAD_ARG, "poe: E=%d out of [1,%d]", E, kMaxExperts);
   if (P < 1 || P > kMaxPasses) return set_error(MVAE_ERR_BAD_ARG, "poe: P=%d out of [1,%d]", P, kMaxPasses);
   if (B < 1 || L < 1 || !mu_e || !lv_e || !masks) return set_error(MVAE_ERR_BAD_ARG, "poe: bad B/L/pointers");
@@ -697,6 +917,7 @@ int fill_poe_args(PoeArgs& a, const float* const* mu_e, const float* const* lv_e
   for (int e = 0; e < E; ++e) {
     if (!mu_e[e] || !lv_e[e]) return set_error(MVAE_ERR_BAD_ARG, "poe: expert %d has a NULL pointer", e);
     a.mu_e[e] = mu_e[e]; a.lv_e[e] = lv_e[e];
+    a.gidx[e] = gather_idx ? gather_idx[e] : nullptr;
   }
   for (int p = 0; p < P; ++p) {
     if (E < 32 && (masks[p] >> E) != 0) return set_error(MVAE_ERR_BAD_ARG, "poe: pass %d references an expert >= E", p);
@@ -705,6 +926,14 @@ int fill_poe_args(PoeArgs& a, const float* const* mu_e, const float* const* lv_e
   a.ld_e = ld_e; a.E = E; a.P = P; a.B = B; a.L = L; a.variant = variant & 1; a.no_prior = (variant >> 1) & 1;
   a.training = training;
   return MVAE_OK;
+}
+
+// grid of the grid-stride fast kernels: enough blocks to fill the machine (8 x 256 threads per SM), never more than the work
+unsigned fast_grid(int64_t n_threads) {
+  const int sms = mvae_device_sm_count() > 0 ? mvae_device_sm_count() : 148;
+  int64_t blocks = (n_threads + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sms) * 8;
+  return static_cast<unsigned>(blocks < cap ? blocks : cap);
 }
 
 bool vec4_ok(const PoeArgs& a, bool bwd) {
@@ -729,8 +958,17 @@ extern "C" int mvae_poe_fwd(const float* const* mu_e, const float* const* lv_e, 
                             const float* noise, float* noise_out, uint64_t seed, uint64_t offset,
                             const int32_t* step_dev, float* z, int64_t ldz, float* mu_out, float* lv_out,
                             double* kl_acc, void* stream) {
+  return mvae_poe_fwd_g(mu_e, lv_e, ld_e, E, nullptr, pass_masks, P, B, L, variant, training, noise, noise_out, seed, offset,
+                        step_dev, z, ldz, mu_out, lv_out, kl_acc, stream);
+}
+
+extern "C" int mvae_poe_fwd_g(const float* const* mu_e, const float* const* lv_e, int64_t ld_e, int E,
+                              const int64_t* const* gather_idx, const uint32_t* pass_masks, int P, int B, int L,
+                              int variant, int training, const float* noise, float* noise_out, uint64_t seed,
+                              uint64_t offset, const int32_t* step_dev, float* z, int64_t ldz, float* mu_out,
+                              float* lv_out, double* kl_acc, void* stream) {
   PoeArgs a = {};
-  int rc = fill_poe_args(a, mu_e, lv_e, ld_e, E, pass_masks, P, B, L, variant, training);
+  int rc = fill_poe_args(a, mu_e, lv_e, ld_e, E, pass_masks, P, B, L, variant, training, gather_idx);
   if (rc) return rc;
   if (!z) return set_error(MVAE_ERR_BAD_ARG, "poe_fwd: z is NULL");
   if (training && !noise && !noise_out)
@@ -738,7 +976,11 @@ extern "C" int mvae_poe_fwd(const float* const* mu_e, const float* const* lv_e, 
   a.noise = noise; a.noise_out = noise_out; a.seed = seed; a.offset = offset; a.step_dev = step_dev;
   a.z = z; a.ldz = ldz; a.mu_out = mu_out; a.lv_out = lv_out; a.kl_acc = kl_acc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (vec4_ok(a, false)) {
+  if (vec4_ok(a, false) && P <= kFastPasses && !getenv("MVAE_POE_SLOW")) {
+    const int64_t n = static_cast<int64_t>(B) * (L / 4);
+    if (E <= 2) poe_fwd_fast_kernel<2><<<fast_grid(n), 256, 0, st>>>(a);
+    else poe_fwd_fast_kernel<4><<<fast_grid(n), 256, 0, st>>>(a);
+  } else if (vec4_ok(a, false)) {
     const int64_t n = static_cast<int64_t>(B) * (L / 4);
     poe_fwd_kernel<4, 4><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a);
   } else {
@@ -755,8 +997,17 @@ extern "C" int mvae_poe_bwd(const float* const* mu_e, const float* const* lv_e, 
                             const float* noise, const float* dz, int64_t lddz, const float* dmu_up,
                             const float* dlv_up, float kl_scale, const float* kl_scale_dev, float* const* dmu_e,
                             float* const* dlv_e, int64_t ldd_e, void* stream) {
+  return mvae_poe_bwd_g(mu_e, lv_e, ld_e, E, nullptr, pass_masks, P, B, L, variant, training, noise, dz, lddz, dmu_up, dlv_up,
+                        kl_scale, kl_scale_dev, dmu_e, dlv_e, ldd_e, stream);
+}
+
+extern "C" int mvae_poe_bwd_g(const float* const* mu_e, const float* const* lv_e, int64_t ld_e, int E,
+                              const int64_t* const* gather_idx, const uint32_t* pass_masks, int P, int B, int L,
+                              int variant, int training, const float* noise, const float* dz, int64_t lddz,
+                              const float* dmu_up, const float* dlv_up, float kl_scale, const float* kl_scale_dev,
+                              float* const* dmu_e, float* const* dlv_e, int64_t ldd_e, void* stream) {
   PoeArgs a = {};
-  int rc = fill_poe_args(a, mu_e, lv_e, ld_e, E, pass_masks, P, B, L, variant, training);
+  int rc = fill_poe_args(a, mu_e, lv_e, ld_e, E, pass_masks, P, B, L, variant, training, gather_idx);
   if (rc) return rc;
   if (!dz || !dmu_e || !dlv_e) return set_error(MVAE_ERR_BAD_ARG, "poe_bwd: NULL dz/dmu_e/dlv_e");
   if (training && !noise) return set_error(MVAE_ERR_BAD_ARG, "poe_bwd: training needs the forward noise");
@@ -767,7 +1018,11 @@ extern "C" int mvae_poe_bwd(const float* const* mu_e, const float* const* lv_e, 
   a.noise = noise; a.dz = dz; a.ldz = lddz; a.kl_scale = kl_scale; a.kl_scale_dev = kl_scale_dev; a.ldd_e = ldd_e;
   a.dmu_up = dmu_up; a.dlv_up = dlv_up;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (vec4_ok(a, true)) {
+  if (vec4_ok(a, true) && P <= kFastPasses && !getenv("MVAE_POE_SLOW")) {
+    const int64_t n = static_cast<int64_t>(B) * (L / 4);
+    if (E <= 2) poe_bwd_fast_kernel<2><<<fast_grid(n), 256, 0, st>>>(a);
+    else poe_bwd_fast_kernel<4><<<fast_grid(n), 256, 0, st>>>(a);
+  } else if (vec4_ok(a, true)) {
     const int64_t n = static_cast<int64_t>(B) * (L / 4);
     poe_bwd_kernel<4, 4><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a);
   } else {

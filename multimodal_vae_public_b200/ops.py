@@ -128,24 +128,54 @@ def _ptr_array(ts):
     return (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
 
 
+def _gather_array(gather, E):
+    """gather: None or a list of E entries (int64 [B] CUDA tensor or None) -> (ctypes array or None)."""
+    if gather is None or all(g is None for g in gather):
+        return None
+    if len(gather) != E:
+        raise _lib.MvaeError("poe: one gather entry (index tensor or None) per expert")
+    for g in gather:
+        if g is not None and (g.dtype != torch.int64 or not g.is_cuda or not g.is_contiguous()):
+            raise _lib.MvaeError("poe: gather indices must be contiguous CUDA int64 tensors")
+    return (C.c_void_p * E)(*[None if g is None else g.data_ptr() for g in gather])
+
+
 def poe_fwd(mu_e, lv_e, masks, B, L, z, variant=0, training=True, noise=None, noise_out=None, seed=0, offset=0,
-            step_dev=None, mu_out=None, lv_out=None, kl_acc=None):
+            step_dev=None, mu_out=None, lv_out=None, kl_acc=None, gather=None):
+    """``gather[e]`` (optional int64 [B]): expert e is a V-row table, sample b uses row gather[e][b] (label tables)."""
     E, P = len(mu_e), len(masks)
     m = (C.c_uint32 * P)(*masks)
-    _lib.check(_lib.load().mvae_poe_fwd(_ptr_array(mu_e), _ptr_array(lv_e), mu_e[0].stride(0), E, m, P, B, L, variant,
-                                        int(training), _p(noise), _p(noise_out), seed, offset, _p(step_dev), z.data_ptr(),
-                                        z.stride(0),
-                                        _p(mu_out), _p(lv_out), _p(kl_acc), _stream()), "mvae_poe_fwd")
+    _lib.check(_lib.load().mvae_poe_fwd_g(_ptr_array(mu_e), _ptr_array(lv_e), mu_e[0].stride(0), E, _gather_array(gather, E),
+                                          m, P, B, L, variant, int(training), _p(noise), _p(noise_out), seed, offset,
+                                          _p(step_dev), z.data_ptr(), z.stride(0), _p(mu_out), _p(lv_out), _p(kl_acc),
+                                          _stream()), "mvae_poe_fwd")
 
 
 def poe_bwd(mu_e, lv_e, masks, B, L, dz, dmu_e, dlv_e, kl_scale, variant=0, training=True, noise=None,
-            kl_scale_dev=None, dmu_up=None, dlv_up=None):
+            kl_scale_dev=None, dmu_up=None, dlv_up=None, gather=None):
+    """With ``gather[e]`` the gradient of table expert e is ADDED into rows gather[e][b] of dmu_e[e] / dlv_e[e] (zero them)."""
     E, P = len(mu_e), len(masks)
     m = (C.c_uint32 * P)(*masks)
-    _lib.check(_lib.load().mvae_poe_bwd(_ptr_array(mu_e), _ptr_array(lv_e), mu_e[0].stride(0), E, m, P, B, L, variant,
-                                        int(training), _p(noise), dz.data_ptr(), dz.stride(0), _p(dmu_up), _p(dlv_up),
-                                        float(kl_scale), _p(kl_scale_dev), _ptr_array(dmu_e), _ptr_array(dlv_e), dmu_e[0].stride(0),
-                                        _stream()), "mvae_poe_bwd")
+    _lib.check(_lib.load().mvae_poe_bwd_g(_ptr_array(mu_e), _ptr_array(lv_e), mu_e[0].stride(0), E, _gather_array(gather, E),
+                                          m, P, B, L, variant, int(training), _p(noise), dz.data_ptr(), dz.stride(0),
+                                          _p(dmu_up), _p(dlv_up), float(kl_scale), _p(kl_scale_dev), _ptr_array(dmu_e),
+                                          _ptr_array(dlv_e), dmu_e[0].stride(0), _stream()), "mvae_poe_bwd")
+
+
+def label_table_fwd(emb, w2, b2, w3, b3, a2, h2, tab):
+    """Label encoder on its V-row table: a2 = swish(emb) w2^T + b2, h2 = swish(a2), tab = h2 w3^T + b3."""
+    V, D = emb.shape
+    N3 = w3.shape[0]
+    _lib.check(_lib.load().mvae_label_table_fwd(emb.data_ptr(), w2.data_ptr(), _p(b2), w3.data_ptr(), _p(b3), a2.data_ptr(),
+                                                h2.data_ptr(), tab.data_ptr(), V, D, N3, _stream()), "mvae_label_table_fwd")
+
+
+def label_table_bwd(emb, w2, w3, a2, h2, dtab, d_a2, d_emb, dw2, db2, dw3, db3):
+    V, D = emb.shape
+    N3 = w3.shape[0]
+    _lib.check(_lib.load().mvae_label_table_bwd(emb.data_ptr(), w2.data_ptr(), w3.data_ptr(), a2.data_ptr(), h2.data_ptr(),
+                                                dtab.data_ptr(), d_a2.data_ptr(), d_emb.data_ptr(), dw2.data_ptr(), _p(db2),
+                                                dw3.data_ptr(), _p(db3), V, D, N3, _stream()), "mvae_label_table_bwd")
 
 
 def reparam_fwd(mu, logvar, z, noise=None, noise_out=None, seed=0, offset=0):

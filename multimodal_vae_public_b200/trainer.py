@@ -139,7 +139,8 @@ class MnistMVAETrainer:
     def __init__(self, n_latents: int = 64, batch_size: int = 4096, device="cuda", lr: float = 1e-3,
                  lambda_image: float = 1.0, lambda_text: float = 10.0, precision: int = PREC_3XTF32,
                  world_size: int = 1, seed: int = 0, rank: int = 0, use_graph: bool = True,
-                 process_group=None, chain: Optional[bool] = None, dp_mode: Optional[str] = None):
+                 process_group=None, chain: Optional[bool] = None, dp_mode: Optional[str] = None,
+                 label_table: Optional[bool] = None):
         _lib.load()  # fail loudly if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _lib.MvaeError("MnistMVAETrainer needs a CUDA device (no CPU fallback)")
@@ -156,6 +157,9 @@ class MnistMVAETrainer:
         # completion counters instead of launch boundaries (mvae_gemm_chain); MVAE_CHAIN=0 restores one launch per layer
         self.chain = os.environ.get("MVAE_CHAIN", "1") != "0" if chain is None else bool(chain)
         self.chain_ws = ops.chain_workspace(torch.device(device))
+        # label-table mode: the label encoder only ever sees 10 distinct inputs, so it is evaluated once per CLASS
+        # (csrc/label_table.cu) and the PoE kernels gather row text[b]; MVAE_LABEL_TABLE=0 restores the per-sample GEMMs
+        self.label_table = os.environ.get("MVAE_LABEL_TABLE", "1") != "0" if label_table is None else bool(label_table)
         self.layout = self._make_layout(n_latents)
         # Data-parallel exchange: "p2p" = ONE fused kernel per rank over NVLink peer memory (gradient reduce-scatter ->
         # Adam on the rank's slice -> parameter all-gather, csrc/dp_p2p.cu); "nccl" = ncclAllReduce + flat Adam.
@@ -192,9 +196,17 @@ class MnistMVAETrainer:
         self.logit_t_buf = f(2 * B, 16)    # N = 10 padded to ld 16 for TMA
         self.logit_t = self.logit_t_buf[:, :10]
         self._alloc_activations(f)
-        # one zero-initialised region per step: dZ + loss accumulators
-        self.dZ = torch.zeros(3 * B, L, dtype=torch.float32, device=dev)
-        self.acc = torch.zeros(9, dtype=torch.float64, device=dev)  # recon_img[3], recon_txt[3], kl[3]
+        # ONE zero-initialised region per step (a single memset): dZ, the class-wise label-encoder gradient table and the
+        # loss accumulators
+        V = self._n_classes()
+        n_dz, n_tab = 3 * B * L, V * 2 * L
+        self.zero_region = torch.zeros(n_dz + n_tab + 32, dtype=torch.float32, device=dev)
+        self.dZ = self.zero_region[:n_dz].view(3 * B, L)
+        self.d_tab = self.zero_region[n_dz:n_dz + n_tab].view(V, 2 * L)
+        self.acc = self.zero_region[n_dz + n_tab:n_dz + n_tab + 18].view(torch.float64)  # recon_img[3], recon_txt[3], kl[3]
+        # label table: pre-activation / activation of the hidden layer and the (mu | logvar) rows, one per class
+        self.tt_a2, self.tt_h2, self.tt_dA2 = f(V, 512), f(V, 512), f(V, 512)
+        self.enc_tab = f(V, 2 * L)
         self.loss_tail = self.grad_bucket[n:n + 4]          # total, internal passes 0..2 (tail of the gradient bucket)
         self.loss_out = self.loss_tail                      # what is copied to the host (the sums over ranks)
         if self.dp_mode == "p2p":
@@ -214,6 +226,29 @@ class MnistMVAETrainer:
     # ------------------------------------------------------------------ flavour hooks
     def _make_layout(self, n_latents: int):
         return mnist_layout(n_latents)
+
+    def _n_classes(self) -> int:
+        return 10
+
+    def _label_encoder(self, buf: int):
+        """(embedding, w2, b2, heads w [2L,512], heads b [2L]) of the label encoder in arena buffer `buf` (0 = parameters,
+        1 = gradients)."""
+        L, a = self.L, self.arena
+        return (a.view(buf, "text_encoder.fc1.weight"), a.view(buf, "text_encoder.fc2.weight"),
+                a.view(buf, "text_encoder.fc2.bias"),
+                a.span(buf, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512),
+                a.span(buf, "text_encoder.fc31.bias", "text_encoder.fc32.bias"))
+
+    def _label_experts(self):
+        """Expert tensors of the PoE kernels: (mu_e, lv_e, dmu_e, dlv_e, gather) with the label encoder either as a
+        per-sample [B, 2L] matrix or as a [V, 2L] table indexed by the labels."""
+        L = self.L
+        if self.label_table:
+            et, dt, gather = self.enc_tab, self.d_tab, [None, self.text]
+        else:
+            et, dt, gather = self.enc_t, self.d_enc_t, None
+        return ([self.enc_i[:, :L], et[:, :L]], [self.enc_i[:, L:], et[:, L:]],
+                [self.d_enc_i[:, :L], dt[:, :L]], [self.d_enc_i[:, L:], dt[:, L:]], gather)
 
     def _alloc_activations(self, f) -> None:
         B = self.B
@@ -315,8 +350,18 @@ class MnistMVAETrainer:
                   bias=p["text_encoder.fc2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)
         heads_i = D(self.ie_h2, wi, self.enc_i, B, 2 * L, 512, bias=bi)
         heads_t = D(self.te_h2, wt, self.enc_t, B, 2 * L, 512, bias=bt)
-        ops.embedding_swish_fwd(p["text_encoder.fc1.weight"], self.text, None, self.te_h1)
-        if self.chain:
+        if self.label_table:
+            emb, w2, b2, w3, b3 = self._label_encoder(0)
+            ops.label_table_fwd(emb, w2, b2, w3, b3, self.tt_a2, self.tt_h2, self.enc_tab)
+            if self.chain:
+                ops.gemm_chain([fc1_i, fc2_i, heads_i], [-1, 0, 1], self.chain_ws, P)
+            else:
+                ops.gemm_batch([fc1_i], P); ops.gemm_batch([fc2_i], P); ops.gemm_batch([heads_i], P)
+        else:
+            ops.embedding_swish_fwd(p["text_encoder.fc1.weight"], self.text, None, self.te_h1)
+        if self.label_table:
+            pass
+        elif self.chain:
             # both encoders in ONE launch: the two independent first layers fill the machine together, then the
             # dependent layers follow tile by tile
             ops.gemm_chain([fc1_i, fc2_t, fc2_i, heads_t, heads_i], [-1, -1, 0, 1, 2], self.chain_ws, P)
@@ -325,13 +370,12 @@ class MnistMVAETrainer:
             ops.gemm_batch([fc2_i, fc2_t], P)
             ops.gemm_batch([heads_i, heads_t], P)
         # PoE + reparametrise + KL for the three passes
-        mu_e = [self.enc_i[:, :L], self.enc_t[:, :L]]
-        lv_e = [self.enc_i[:, L:], self.enc_t[:, L:]]
+        mu_e, lv_e, _, _, gather = self._label_experts()
         ops.poe_fwd(mu_e, lv_e, _PASS_MASKS, B, L, self.Z, variant=0, training=training,
                     noise=self.noise if (training and use_noise_input) else None,
                     noise_out=self.noise if (training and not use_noise_input) else None,
                     seed=self.seed * 1000003 + self.rank, offset=0, step_dev=self.step_count,
-                    kl_acc=self.acc[6:9])
+                    kl_acc=self.acc[6:9], gather=gather)
         # decoders: image decoder on rows [0,2B) (image-only, joint), text decoder on rows [B,3B) (joint, text-only)
         zi, zt = self.Z[: 2 * B], self.Z[B:]
         xin_i, xin_t = zi, zt
@@ -403,12 +447,9 @@ class MnistMVAETrainer:
         if self.chain:   # the whole decoder backward (16 problems) is one launch
             ops.gemm_chain(chain_descs, chain_deps, self.chain_ws, P)
         # ---- PoE / reparam / KL backward -> gradients of both encoders' outputs (summed over passes)
-        mu_e = [self.enc_i[:, :L], self.enc_t[:, :L]]
-        lv_e = [self.enc_i[:, L:], self.enc_t[:, L:]]
-        dmu = [self.d_enc_i[:, :L], self.d_enc_t[:, :L]]
-        dlv = [self.d_enc_i[:, L:], self.d_enc_t[:, L:]]
+        mu_e, lv_e, dmu, dlv, gather = self._label_experts()
         ops.poe_bwd(mu_e, lv_e, _PASS_MASKS, B, L, self.dZ, dmu, dlv, kl_scale=1.0 / b_global, variant=0,
-                    training=training, noise=self.noise if training else None, kl_scale_dev=self.beta_dev)
+                    training=training, noise=self.noise if training else None, kl_scale_dev=self.beta_dev, gather=gather)
         # ---- encoders backward
         nk = max(1, B // 32)
         split = max(1, min(nk // 16, 32))
@@ -420,7 +461,8 @@ class MnistMVAETrainer:
         wi = arena.span(0, "image_encoder.fc31.weight", "image_encoder.fc32.weight").view(2 * L, 512)
         wt = arena.span(0, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512)
         ops.colsum_accumulate(self.d_enc_i, gbi)
-        ops.colsum_accumulate(self.d_enc_t, gbt)
+        if not self.label_table:
+            ops.colsum_accumulate(self.d_enc_t, gbt)
         wg_hi = D(self.d_enc_i, self.ie_h2, gwi, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True)
         wg_ht = D(self.d_enc_t, self.te_h2, gwt, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True)
         dg_hi = D(self.d_enc_i, wi, self.ie_dA[0], B, 512, 2 * L, b_mn=True, aux=self.ie_a2,
@@ -436,6 +478,16 @@ class MnistMVAETrainer:
         dg_2t = D(self.te_dA[0], p["text_encoder.fc2.weight"], self.te_dA[1], B, 512, 512, b_mn=True)
         wg_1i = D(self.ie_dA[1], self.x, g["image_encoder.fc1.weight"], 512, 784, B, a_mn=True, b_mn=True,
                   split_k=split, accumulate=True)
+        if self.label_table:
+            # image encoder backward (one chained launch), then the label encoder's backward on its class table
+            if self.chain:
+                ops.gemm_chain([dg_hi, wg_hi, dg_2i, wg_2i, wg_1i], [-1, -1, 0, 0, 2], self.chain_ws, P)
+            else:
+                ops.gemm_batch([wg_hi, dg_hi], P); ops.gemm_batch([wg_2i, dg_2i], P); ops.gemm_batch([wg_1i], P)
+            emb, w2, _, w3, _ = self._label_encoder(0)
+            g_emb, g_w2, g_b2, g_w3, g_b3 = self._label_encoder(1)
+            ops.label_table_bwd(emb, w2, w3, self.tt_a2, self.tt_h2, self.d_tab, self.tt_dA2, g_emb, g_w2, g_b2, g_w3, g_b3)
+            return
         if self.chain:   # both encoders' backward: one launch
             ops.gemm_chain([dg_hi, dg_ht, wg_hi, wg_ht, dg_2i, dg_2t, wg_2i, wg_2t, wg_1i],
                            [-1, -1, -1, -1, 0, 1, 0, 1, 4], self.chain_ws, P)
@@ -448,8 +500,7 @@ class MnistMVAETrainer:
     def _enqueue_fwd_bwd(self, training: bool, use_noise_input: bool) -> None:
         b_global = self.B * self.world
         self.grad_bucket.zero_()
-        self.dZ.zero_()
-        self.acc.zero_()
+        self.zero_region.zero_()
         self._enqueue_forward(training, use_noise_input)
         self._enqueue_loss_and_backward(training, b_global)
         ops.elbo_finalize(self.acc[0:3], self.acc[3:6], self.acc[6:9], 3, self.lam_i, self.lam_t, 1.0, 1.0 / b_global,

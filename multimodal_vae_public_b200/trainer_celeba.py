@@ -124,6 +124,7 @@ class CelebAMVAETrainer(MnistMVAETrainer):
     def __init__(self, n_latents: int = 100, batch_size: int = 128, lr: float = 1e-4, lambda_image: float = 1.0,
                  lambda_attrs: float = 10.0, **kw):
         kw.pop("lambda_text", None)
+        kw["label_table"] = False        # the attribute encoder takes 2^18 distinct inputs: no class table here
         super().__init__(n_latents=n_latents, batch_size=batch_size, lr=lr, lambda_image=lambda_image,
                          lambda_text=lambda_attrs, **kw)
 

@@ -99,6 +99,12 @@ class FashionMVAETrainer(MnistMVAETrainer):
     def _make_layout(self, L: int):
         return [(k, _INTERNAL_SHAPE.get(k, shp)) for k, shp in fashion_reference_shapes(L)]
 
+    def _label_encoder(self, buf: int):
+        a = self.arena
+        return (a.view(buf, "text_encoder.net.0.weight"), a.view(buf, "text_encoder.net.2.weight"),
+                a.view(buf, "text_encoder.net.2.bias"), a.view(buf, "text_encoder.net.4.weight"),
+                a.view(buf, "text_encoder.net.4.bias"))
+
     def _alloc_activations(self, f) -> None:
         B = self.B
         # image encoder (B rows), NHWC
@@ -169,26 +175,31 @@ class FashionMVAETrainer(MnistMVAETrainer):
         ops.gemm_batch([ops.gemm_desc(self.cols1, p["image_encoder.features.0.weight"], self.c1_a, B * 196, 64, 16,
                                       out2=self.c1_h, epilogue=ops.EPI_BIAS_SWISH)], P)
         ops.im2col_k4s2p1(self.c1_h, self.cols2, B, 14, 14, 64)
-        ops.embedding_swish_fwd(p["text_encoder.net.0.weight"], self.text, None, self.te_h1)
+        lt = self.label_table
+        if lt:   # label encoder once per class (csrc/label_table.cu); the PoE kernels gather row text[b]
+            emb, w2, b2, w3, b3 = self._label_encoder(0)
+            ops.label_table_fwd(emb, w2, b2, w3, b3, self.tt_a2, self.tt_h2, self.enc_tab)
+        else:
+            ops.embedding_swish_fwd(p["text_encoder.net.0.weight"], self.text, None, self.te_h1)
         ops.gemm_batch([
             ops.gemm_desc(self.cols2, p["image_encoder.features.2.weight"], self.c2_a, B * 49, 128, 1024,
-                          out2=self.c2_h, epilogue=ops.EPI_BIAS_SWISH),
+                          out2=self.c2_h, epilogue=ops.EPI_BIAS_SWISH)] + ([] if lt else [
             ops.gemm_desc(self.te_h1, p["text_encoder.net.2.weight"], self.te_a2, B, 512, 512,
-                          bias=p["text_encoder.net.2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)], P)
+                          bias=p["text_encoder.net.2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)]), P)
         ops.gemm_batch([
             ops.gemm_desc(self.c2_h.view(B, 6272), p["image_encoder.classifier.0.weight"], self.fc_a, B, 512, 6272,
-                          bias=p["image_encoder.classifier.0.bias"], out2=self.fc_h, epilogue=ops.EPI_BIAS_SWISH),
+                          bias=p["image_encoder.classifier.0.bias"], out2=self.fc_h, epilogue=ops.EPI_BIAS_SWISH)] + ([] if lt else [
             ops.gemm_desc(self.te_h2, p["text_encoder.net.4.weight"], self.enc_t, B, 2 * L, 512,
-                          bias=p["text_encoder.net.4.bias"])], P)
+                          bias=p["text_encoder.net.4.bias"])]), P)
         ops.gemm_batch([ops.gemm_desc(self.fc_h, p["image_encoder.classifier.2.weight"], self.enc_i, B, 2 * L, 512,
                                       bias=p["image_encoder.classifier.2.bias"])], P)
         # ---- PoE + reparametrise + KL (three passes)
-        mu_e = [self.enc_i[:, :L], self.enc_t[:, :L]]
-        lv_e = [self.enc_i[:, L:], self.enc_t[:, L:]]
+        mu_e, lv_e, _, _, gather = self._label_experts()
         ops.poe_fwd(mu_e, lv_e, _PASS_MASKS, B, L, self.Z, variant=0, training=training,
                     noise=self.noise if (training and use_noise_input) else None,
                     noise_out=self.noise if (training and not use_noise_input) else None,
-                    seed=self.seed * 1000003 + self.rank, offset=0, step_dev=self.step_count, kl_acc=self.acc[6:9])
+                    seed=self.seed * 1000003 + self.rank, offset=0, step_dev=self.step_count, kl_acc=self.acc[6:9],
+                    gather=gather)
         # ---- decoders (image: rows [0,2B) of Z; text: rows [B,3B))
         zi, zt = self.Z[: 2 * B], self.Z[B:]
         ops.gemm_batch([
@@ -268,34 +279,38 @@ class FashionMVAETrainer(MnistMVAETrainer):
             ops.gemm_desc(self.td_dA[0], p["text_decoder.net.0.weight"], self.dZ[B:], 2 * B, L, 512, b_mn=True,
                           accumulate=True)], P)
         # ---- PoE / reparam / KL backward
-        mu_e = [self.enc_i[:, :L], self.enc_t[:, :L]]
-        lv_e = [self.enc_i[:, L:], self.enc_t[:, L:]]
-        dmu = [self.d_enc_i[:, :L], self.d_enc_t[:, :L]]
-        dlv = [self.d_enc_i[:, L:], self.d_enc_t[:, L:]]
+        mu_e, lv_e, dmu, dlv, gather = self._label_experts()
         ops.poe_bwd(mu_e, lv_e, _PASS_MASKS, B, L, self.dZ, dmu, dlv, kl_scale=1.0 / b_global, variant=0,
-                    training=training, noise=self.noise if training else None, kl_scale_dev=self.beta_dev)
+                    training=training, noise=self.noise if training else None, kl_scale_dev=self.beta_dev, gather=gather)
+        lt = self.label_table
         # ---- encoders backward: heads
         ops.colsum_accumulate(self.d_enc_i, g["image_encoder.classifier.2.bias"])
-        ops.colsum_accumulate(self.d_enc_t, g["text_encoder.net.4.bias"])
+        if not lt:
+            ops.colsum_accumulate(self.d_enc_t, g["text_encoder.net.4.bias"])
         ops.gemm_batch([
             ops.gemm_desc(self.d_enc_i, self.fc_h, g["image_encoder.classifier.2.weight"], 2 * L, 512, B, a_mn=True, b_mn=True,
                           split_k=split_for(B), accumulate=True),
             ops.gemm_desc(self.d_enc_i, p["image_encoder.classifier.2.weight"], self.d_fc, B, 512, 2 * L, b_mn=True,
-                          aux=self.fc_a, epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.classifier.0.bias"]),
+                          aux=self.fc_a, epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.classifier.0.bias"])] + ([] if lt else [
             ops.gemm_desc(self.d_enc_t, self.te_h2, g["text_encoder.net.4.weight"], 2 * L, 512, B, a_mn=True, b_mn=True,
                           split_k=split_for(B), accumulate=True),
             ops.gemm_desc(self.d_enc_t, p["text_encoder.net.4.weight"], self.te_dA[0], B, 512, 2 * L, b_mn=True,
-                          aux=self.te_a2, epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_encoder.net.2.bias"])], P)
+                          aux=self.te_a2, epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_encoder.net.2.bias"])]), P)
         # ---- classifier.0 (image) and net.2 (text)
         ops.gemm_batch([
             ops.gemm_desc(self.d_fc, self.c2_h.view(B, 6272), g["image_encoder.classifier.0.weight"], 512, 6272, B,
                           a_mn=True, b_mn=True, split_k=split_for(B), accumulate=True),
             ops.gemm_desc(self.d_fc, p["image_encoder.classifier.0.weight"], self.d_c2.view(B, 6272), B, 6272, 512,
-                          b_mn=True, aux=self.c2_a.view(B, 6272), epilogue=ops.EPI_MUL_DSWISH),
+                          b_mn=True, aux=self.c2_a.view(B, 6272), epilogue=ops.EPI_MUL_DSWISH)] + ([] if lt else [
             ops.gemm_desc(self.te_dA[0], self.te_h1, g["text_encoder.net.2.weight"], 512, 512, B, a_mn=True, b_mn=True,
                           split_k=split_for(B), accumulate=True),
-            ops.gemm_desc(self.te_dA[0], p["text_encoder.net.2.weight"], self.te_dA[1], B, 512, 512, b_mn=True)], P)
-        ops.embedding_swish_bwd(p["text_encoder.net.0.weight"], self.text, self.te_dA[1], g["text_encoder.net.0.weight"])
+            ops.gemm_desc(self.te_dA[0], p["text_encoder.net.2.weight"], self.te_dA[1], B, 512, 512, b_mn=True)]), P)
+        if lt:
+            emb, w2, _, w3, _ = self._label_encoder(0)
+            g_emb, g_w2, g_b2, g_w3, g_b3 = self._label_encoder(1)
+            ops.label_table_bwd(emb, w2, w3, self.tt_a2, self.tt_h2, self.d_tab, self.tt_dA2, g_emb, g_w2, g_b2, g_w3, g_b3)
+        else:
+            ops.embedding_swish_bwd(p["text_encoder.net.0.weight"], self.text, self.te_dA[1], g["text_encoder.net.0.weight"])
         # ---- conv2
         ops.gemm_batch([
             ops.gemm_desc(self.d_c2, self.cols2, g["image_encoder.features.2.weight"], 128, 1024, B * 49, a_mn=True,

@@ -234,3 +234,58 @@ def test_adam_matches_oracle(ops):
         O.adam_update(ref, {"w": torch.from_numpy(g)}, st, step=it, lr=1e-3)
         assert step.item() == it
         np.testing.assert_allclose(P.cpu().numpy(), ref["w"].numpy(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("V,D,N3", [(10, 512, 128), (2, 512, 200), (16, 64, 8)])
+def test_label_table_fwd_bwd(ops, V, D, N3):
+    """Label encoder on its V-row class table (Embedding -> Swish -> Linear+Swish -> heads) against fp64 autograd."""
+    rs = np.random.RandomState(V + D)
+    t = lambda *s: torch.from_numpy(rs.standard_normal(s).astype(np.float32))  # noqa: E731
+    emb, w2, b2, w3, b3, dtab = t(V, D), t(D, D) / D ** 0.5, t(D), t(N3, D) / D ** 0.5, t(N3), t(V, N3)
+    dev = [x.cuda() for x in (emb, w2, b2, w3, b3, dtab)]
+    a2 = torch.empty(V, D, device="cuda"); h2 = torch.empty(V, D, device="cuda"); tab = torch.empty(V, N3, device="cuda")
+    ops.label_table_fwd(dev[0], dev[1], dev[2], dev[3], dev[4], a2, h2, tab)
+    e64, w2_64, b2_64, w3_64, b3_64 = (x.double().requires_grad_(True) for x in (emb, w2, b2, w3, b3))
+    ra2 = O.swish(e64) @ w2_64.t() + b2_64
+    rtab = O.swish(ra2) @ w3_64.t() + b3_64
+    assert _rel(a2.cpu(), ra2.detach()) < 2e-6 and _rel(h2.cpu(), O.swish(ra2).detach()) < 2e-6
+    assert _rel(tab.cpu(), rtab.detach()) < 2e-6
+    (rtab * dtab.double()).sum().backward()
+    # gradients ACCUMULATE: start from a non-zero value to check that
+    base = 0.25
+    g = {k: torch.full(s, base, device="cuda") for k, s in (("emb", (V, D)), ("w2", (D, D)), ("b2", (D,)), ("w3", (N3, D)), ("b3", (N3,)))}
+    d_a2 = torch.full((V, D), float("nan"), device="cuda")
+    ops.label_table_bwd(dev[0], dev[1], dev[3], a2, h2, dev[5], d_a2, g["emb"], g["w2"], g["b2"], g["w3"], g["b3"])
+    for k, ref in (("emb", e64.grad), ("w2", w2_64.grad), ("b2", b2_64.grad), ("w3", w3_64.grad), ("b3", b3_64.grad)):
+        assert _rel(g[k].cpu() - base, ref) < 5e-6, k
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_poe_table_expert_equals_per_sample_expert(ops, variant):
+    """An expert given as a V-row table + row index per sample (mvae_poe_*_g) == the same expert expanded to [B, 2L]; its
+    backward is the class-wise sum of the per-sample gradients."""
+    rs = np.random.RandomState(3)
+    B, L, V = 700, 64, 10
+    masks = [0b01, 0b11, 0b10]
+    P = len(masks)
+    enc_i = torch.from_numpy((0.8 * rs.standard_normal((B, 2 * L))).astype(np.float32)).cuda()
+    tab = torch.from_numpy((0.8 * rs.standard_normal((V, 2 * L))).astype(np.float32)).cuda()
+    idx = torch.from_numpy(rs.randint(0, V, B)).cuda()
+    enc_t = tab[idx].contiguous()
+    noise = torch.from_numpy(rs.standard_normal((P * B, L)).astype(np.float32)).cuda()
+    dz = torch.from_numpy(rs.standard_normal((P * B, L)).astype(np.float32)).cuda()
+    out = {}
+    for mode in ("table", "rows"):
+        et = tab if mode == "table" else enc_t
+        gather = [None, idx] if mode == "table" else None
+        z = torch.empty(P * B, L, device="cuda"); kl = torch.zeros(P, dtype=torch.float64, device="cuda")
+        ops.poe_fwd([enc_i[:, :L], et[:, :L]], [enc_i[:, L:], et[:, L:]], masks, B, L, z, variant=variant, training=True,
+                    noise=noise, kl_acc=kl, gather=gather)
+        d_i = torch.empty(B, 2 * L, device="cuda"); d_t = torch.zeros_like(et)
+        ops.poe_bwd([enc_i[:, :L], et[:, :L]], [enc_i[:, L:], et[:, L:]], masks, B, L, dz, [d_i[:, :L], d_t[:, :L]],
+                    [d_i[:, L:], d_t[:, L:]], kl_scale=0.3 / B, variant=variant, training=True, noise=noise, gather=gather)
+        out[mode] = (z, kl, d_i, d_t)
+    assert torch.equal(out["table"][0], out["rows"][0]) and torch.equal(out["table"][2], out["rows"][2])
+    np.testing.assert_allclose(out["table"][1].cpu().numpy(), out["rows"][1].cpu().numpy(), rtol=1e-12)
+    seg = torch.zeros(V, 2 * L, dtype=torch.float64, device="cuda").index_add_(0, idx, out["rows"][3].double())
+    assert _rel(out["table"][3].cpu(), seg.cpu()) < 2e-6

@@ -137,7 +137,7 @@ def test_full_size_properties():
         sl = slice(r * B // 2, (r + 1) * B // 2)
         half.set_inputs(image[sl], text[sl], noise[:, sl], 0.5)
         with torch.cuda.stream(half._stream):
-            half.grad_bucket.zero_(); half.dZ.zero_(); half.acc.zero_()
+            half.grad_bucket.zero_(); half.zero_region.zero_()
             half._enqueue_forward(True, True)
             half._enqueue_loss_and_backward(True, B)
             T.ops.elbo_finalize(half.acc[0:3], half.acc[3:6], half.acc[6:9], 3, half.lam_i, half.lam_t, 1.0, 1.0 / B,
@@ -172,3 +172,28 @@ def test_pipelined_host_fed_steps_equal_synchronous_steps():
         assert abs(x - y) <= 2e-6 * abs(x)
     for k in a.params:
         assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-5, k
+
+
+@pytest.mark.parametrize("flavour", ["mnist", "fashion"])
+def test_label_table_mode_equals_per_sample_label_encoder(flavour):
+    """The label encoder evaluated once per class (default) and evaluated on all B rows (MVAE_LABEL_TABLE=0 path) are the
+    same function: same losses, same gradients up to summation order / 3xTF32-vs-FMA rounding."""
+    B, L = 300, 64
+    rs = np.random.RandomState(8)
+    image = torch.from_numpy(rs.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32))
+    text = torch.from_numpy(rs.randint(0, 10, B).astype(np.int64))
+    noise = torch.from_numpy(rs.standard_normal((3, B, L)).astype(np.float32))
+    if flavour == "mnist":
+        from multimodal_vae_public_b200.trainer import MnistMVAETrainer as T
+    else:
+        from multimodal_vae_public_b200.trainer_fashion import FashionMVAETrainer as T
+    a = T(n_latents=L, batch_size=B, use_graph=False, label_table=True)
+    b = T(n_latents=L, batch_size=B, use_graph=False, label_table=False)
+    b.load_state_dict(a.state_dict())
+    la = a.step(image, text, annealing_factor=0.5, noise=noise, update=False)
+    lb = b.step(image, text, annealing_factor=0.5, noise=noise, update=False)
+    assert abs(la - lb) <= 2e-6 * abs(la)
+    for k in a.grads:
+        ref = b.grads[k]
+        err = (a.grads[k] - ref).abs().max().item() / max(ref.abs().max().item(), 1e-12)
+        assert err <= 1e-4, (k, err)
