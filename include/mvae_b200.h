@@ -168,8 +168,8 @@ int mvae_poe_bwd_g(const float* const* mu_e, const float* const* lv_e, int64_t l
  *   fwd: a2 = swish(emb) w2^T + b2, h2 = swish(a2), tab = h2 w3^T + b3      (emb [V,D], w2 [D,D], w3 [N3,D], tab [V,N3])
  *   bwd: given dtab [V,N3] (= class-wise sums of the per-sample gradients, accumulated by mvae_poe_bwd_g):
  *        dw3 += dtab^T h2, db3 += colsum(dtab), dw2 += dA2^T swish(emb), db2 += colsum(dA2), d_emb += (dA2 w2) * swish'(emb)
- *        with dA2 = (dtab w3) * swish'(a2) written to the scratch d_a2 [V,D].  Gradients ACCUMULATE (zero them once per
- *        step like optimizer.zero_grad(), mnist/train.py:197).  Exact regrouping of the per-sample sums; plain fp32 FMA. */
+ *        with dA2 = (dtab w3) * swish'(a2) ACCUMULATED into the scratch d_a2 [V,D], which the caller zero-initialises before
+ *        every call.  Gradients ACCUMULATE too (zero them once per step like optimizer.zero_grad(), mnist/train.py:197).  Exact regrouping of the per-sample sums; plain fp32 FMA. */
 int mvae_label_table_fwd(const float* emb, const float* w2, const float* b2, const float* w3, const float* b3, float* a2,
                          float* h2, float* tab, int V, int D, int N3, void* stream);
 int mvae_label_table_bwd(const float* emb, const float* w2, const float* w3, const float* a2, const float* h2,
@@ -221,6 +221,24 @@ int mvae_im2col_k4(const float* x, float* cols, int64_t ld_cols, int B, int H, i
                    void* stream);
 int mvae_col2im_k4(const float* cols, int64_t ld_cols, float* out, float* out_act, const float* aux, int B, int IH, int IW,
                    int C, int stride, int pad, void* stream);
+
+/* Direct (no im2col / cols buffers, CUDA cores, HBM-bound) 4x4 / stride 2 / pad 1 convolutions on the IMAGE side of the
+ * nets, where one side has 1 or 3 channels and a tensor-core GEMM would be 1-2 k-blocks deep:
+ *   conv_k4s2p1_cin_fwd   : Conv2d(Cin in {1,3} -> Cout) + Swish, fashionmnist/model.py:79 (1->64), celeba/model.py:77 (3->32)
+ *                           x [B,H,W,Cin] NHWC, wc [Cout][(kh,kw,ci)] -> a = conv(x) (pre-activation), h = swish(a): [B*H/2*W/2, Cout]
+ *   conv_k4s2p1_cin_wgrad : dwc[co][(kh,kw,ci)] += sum_pixels da[p][co] * x-tap   (the image needs no data gradient)
+ *   convT_k4s2p1_cout_fwd : ConvTranspose2d(Cin -> Cout in {1,3}), fashionmnist/model.py:114 (64->1), celeba/model.py:126 (32->3)
+ *                           hin [B,IH,IW,Cin], wt [(kh,kw,co)][Cin] -> out [B,2IH,2IW,Cout] (logits)
+ *   convT_k4s2p1_cout_bwd : given dout [B,2IH,2IW,Cout]: dhin = (ConvT^T dout) * swish'(ain)  (ain = pre-activation that
+ *                           produced hin = swish(ain)), dwt += sum_pixels dcols^T hin                                    */
+int mvae_conv_k4s2p1_cin_fwd(const float* x, const float* wc, float* a, float* h, int B, int H, int W, int Cin, int Cout,
+                             void* stream);
+int mvae_conv_k4s2p1_cin_wgrad(const float* x, const float* da, float* dwc, int B, int H, int W, int Cin, int Cout,
+                               void* stream);
+int mvae_convt_k4s2p1_cout_fwd(const float* hin, const float* wt, float* out, int B, int IH, int IW, int Cin, int Cout,
+                               void* stream);
+int mvae_convt_k4s2p1_cout_bwd(const float* dout, const float* hin, const float* ain, const float* wt, float* dhin, float* dwt,
+                               int B, int IH, int IW, int Cin, int Cout, void* stream);
 
 /* Train-mode BatchNorm2d/1d (+ Swish) over [rows, C] activations split into S equal row segments (one per stacked
  * model() call), celeba/model.py:80,83,86,118,121,124,149,152,176,179,182.  eps = 1e-5, momentum = 0.1 (nn defaults).

@@ -70,6 +70,10 @@ SIGNATURES = {
     "mvae_col2im_k4s2p1": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _P],
     "mvae_im2col_k4": [_P, _P, _L, _I, _I, _I, _I, _I, _I, _P],
     "mvae_col2im_k4": [_P, _L, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "mvae_conv_k4s2p1_cin_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mvae_conv_k4s2p1_cin_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mvae_convt_k4s2p1_cout_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "mvae_convt_k4s2p1_cout_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "mvae_bn_stats": [_P, _L, _I, _I, _I, _P, _P],
     "mvae_bn_finalize": [_P, _I, _I, _I, _F, _F, _P, _P, _P, _P, C.POINTER(C.c_int32), _I, _P],
     "mvae_bn_eval_stats": [_P, _P, _I, _I, _F, _P, _P, _P],

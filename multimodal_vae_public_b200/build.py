@@ -12,7 +12,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["common.cu", "gemm_tcgen05.cu", "elementwise.cu", "conv.cu", "norm.cu", "dp_p2p.cu", "label_table.cu"]
+SOURCES = ["common.cu", "gemm_tcgen05.cu", "elementwise.cu", "conv.cu", "norm.cu", "dp_p2p.cu", "label_table.cu", "conv_small.cu"]
 HEADERS = ["common.h", "ptx.cuh", os.path.join("..", "..", "include", "mvae_b200.h")]
 LIB = os.path.join(HERE, "libmvae_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

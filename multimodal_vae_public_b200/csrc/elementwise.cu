@@ -190,7 +190,7 @@ constexpr int kFastPasses = 4;   // passes whose KL partial sums a thread keeps 
 // ONE double atomic per (block, pass) at the very end -- with one atomic per 256 threads per pass the same-address
 // atomics serialised in L2 at roofline size (16 K blocks x 3 passes on 3 addresses).
 template <int EMAX>
-__global__ void __launch_bounds__(256) poe_fwd_fast_kernel(const __grid_constant__ PoeArgs a) {
+__global__ void __launch_bounds__(256, 3) poe_fwd_fast_kernel(const __grid_constant__ PoeArgs a) {
   __shared__ double scratch[32];
   const int l4n = a.L >> 2;
   const int64_t total = static_cast<int64_t>(a.B) * l4n;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) poe_fwd_fast_kernel(const __grid_constant
 }
 
 template <int EMAX>
-__global__ void __launch_bounds__(256) poe_bwd_fast_kernel(const __grid_constant__ PoeArgs a) {
+__global__ void __launch_bounds__(256, 3) poe_bwd_fast_kernel(const __grid_constant__ PoeArgs a) {
   const int l4n = a.L >> 2;
   const int64_t total = static_cast<int64_t>(a.B) * l4n;
   const float e1 = 1e-8f;

@@ -233,6 +233,31 @@ def col2im_k4(cols, out, B, IH, IW, Cch, stride, pad, out_act=None, aux=None):
                                           Cch, stride, pad, _stream()), "mvae_col2im_k4")
 
 
+def conv_cin_fwd(x, wc, a, h, B, H, W, Cin, Cout):
+    """Direct Conv2d(k4 s2 p1, Cin in {1,3} -> Cout) + Swish: x NHWC -> a (pre-activation), h = swish(a) [B*H/2*W/2, Cout]."""
+    _lib.check(_lib.load().mvae_conv_k4s2p1_cin_fwd(x.data_ptr(), wc.data_ptr(), a.data_ptr(), h.data_ptr(), B, H, W, Cin, Cout,
+                                                    _stream()), "mvae_conv_k4s2p1_cin_fwd")
+
+
+def conv_cin_wgrad(x, da, dwc, B, H, W, Cin, Cout):
+    """dwc[Cout, 16 Cin] += da^T im2col(x) without materialising im2col."""
+    _lib.check(_lib.load().mvae_conv_k4s2p1_cin_wgrad(x.data_ptr(), da.data_ptr(), dwc.data_ptr(), B, H, W, Cin, Cout,
+                                                      _stream()), "mvae_conv_k4s2p1_cin_wgrad")
+
+
+def convT_cout_fwd(hin, wt, out, B, IH, IW, Cin, Cout):
+    """Direct ConvTranspose2d(k4 s2 p1, Cin -> Cout in {1,3}): hin NHWC [B,IH,IW,Cin] -> out [B,2IH,2IW,Cout]."""
+    _lib.check(_lib.load().mvae_convt_k4s2p1_cout_fwd(hin.data_ptr(), wt.data_ptr(), out.data_ptr(), B, IH, IW, Cin, Cout,
+                                                      _stream()), "mvae_convt_k4s2p1_cout_fwd")
+
+
+def convT_cout_bwd(dout, hin, ain, wt, dhin, dwt, B, IH, IW, Cin, Cout):
+    """Backward of the above through the Swish below it: dhin = (ConvT^T dout) * swish'(ain), dwt += dcols^T hin."""
+    _lib.check(_lib.load().mvae_convt_k4s2p1_cout_bwd(dout.data_ptr(), hin.data_ptr(), ain.data_ptr(), wt.data_ptr(),
+                                                      dhin.data_ptr(), dwt.data_ptr(), B, IH, IW, Cin, Cout, _stream()),
+               "mvae_convt_k4s2p1_cout_bwd")
+
+
 def bn_forward(x, h, S, seg_rows, gamma, beta, mean, invstd, acc, running_mean=None, running_var=None, update_order=(),
                training=True, act=True, eps=1e-5, momentum=0.1):
     """Train/eval BatchNorm (+Swish) over x [S*seg_rows, C] -> h; fills mean/invstd [S, C]."""

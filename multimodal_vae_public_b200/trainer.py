@@ -200,12 +200,15 @@ class MnistMVAETrainer:
         # loss accumulators
         V = self._n_classes()
         n_dz, n_tab = 3 * B * L, V * 2 * L
-        self.zero_region = torch.zeros(n_dz + n_tab + 32, dtype=torch.float32, device=dev)
+        n_da2 = V * 512
+        self.zero_region = torch.zeros(n_dz + n_tab + n_da2 + 32, dtype=torch.float32, device=dev)
         self.dZ = self.zero_region[:n_dz].view(3 * B, L)
         self.d_tab = self.zero_region[n_dz:n_dz + n_tab].view(V, 2 * L)
-        self.acc = self.zero_region[n_dz + n_tab:n_dz + n_tab + 18].view(torch.float64)  # recon_img[3], recon_txt[3], kl[3]
+        self.tt_dA2 = self.zero_region[n_dz + n_tab:n_dz + n_tab + n_da2].view(V, 512)   # accumulation target of the table bwd
+        o = n_dz + n_tab + n_da2
+        self.acc = self.zero_region[o:o + 18].view(torch.float64)  # recon_img[3], recon_txt[3], kl[3]
         # label table: pre-activation / activation of the hidden layer and the (mu | logvar) rows, one per class
-        self.tt_a2, self.tt_h2, self.tt_dA2 = f(V, 512), f(V, 512), f(V, 512)
+        self.tt_a2, self.tt_h2 = f(V, 512), f(V, 512)
         self.enc_tab = f(V, 2 * L)
         self.loss_tail = self.grad_bucket[n:n + 4]          # total, internal passes 0..2 (tail of the gradient bucket)
         self.loss_out = self.loss_tail                      # what is copied to the host (the sums over ranks)

@@ -106,7 +106,10 @@ class FashionMVAETrainer(MnistMVAETrainer):
                 a.view(buf, "text_encoder.net.4.bias"))
 
     def _alloc_activations(self, f) -> None:
+        import os
         B = self.B
+        # direct kernels for the 1-channel conv layers (default); MVAE_DIRECT_C1=0 restores im2col + tensor-core GEMM
+        self.direct_c1 = os.environ.get("MVAE_DIRECT_C1", "1") != "0"
         # image encoder (B rows), NHWC
         self.cols1 = f(B * 196, 16)
         self.c1_a, self.c1_h = f(B * 196, 64), f(B * 196, 64)
@@ -170,10 +173,15 @@ class FashionMVAETrainer(MnistMVAETrainer):
     def _enqueue_forward(self, training: bool, use_noise_input: bool) -> None:
         B, L, P = self.B, self.L, self.prec
         p = self.params
-        # ---- image encoder
-        ops.im2col_k4s2p1(self.x, self.cols1, B, 28, 28, 1)
-        ops.gemm_batch([ops.gemm_desc(self.cols1, p["image_encoder.features.0.weight"], self.c1_a, B * 196, 64, 16,
-                                      out2=self.c1_h, epilogue=ops.EPI_BIAS_SWISH)], P)
+        # ---- image encoder.  The 1-channel layers (conv1 here, the last transposed conv and their backward) run as direct
+        # HBM-bound kernels (csrc/conv_small.cu): no im2col / cols buffers, the 64-channel activation is streamed once
+        direct = self.direct_c1
+        if direct:
+            ops.conv_cin_fwd(self.x, p["image_encoder.features.0.weight"], self.c1_a, self.c1_h, B, 28, 28, 1, 64)
+        else:
+            ops.im2col_k4s2p1(self.x, self.cols1, B, 28, 28, 1)
+            ops.gemm_batch([ops.gemm_desc(self.cols1, p["image_encoder.features.0.weight"], self.c1_a, B * 196, 64, 16,
+                                          out2=self.c1_h, epilogue=ops.EPI_BIAS_SWISH)], P)
         ops.im2col_k4s2p1(self.c1_h, self.cols2, B, 14, 14, 64)
         lt = self.label_table
         if lt:   # label encoder once per class (csrc/label_table.cu); the PoE kernels gather row text[b]
@@ -218,11 +226,15 @@ class FashionMVAETrainer(MnistMVAETrainer):
             ops.gemm_desc(self.td_h[1], p["text_decoder.net.4.weight"], self.td_a[2], 2 * B, 512, 512,
                           bias=p["text_decoder.net.4.bias"], out2=self.td_h[2], epilogue=ops.EPI_BIAS_SWISH)], P)
         ops.col2im_k4s2p1(self.colsT1, self.t1_a, 2 * B, 7, 7, 64, out_act=self.t1_h)
-        ops.gemm_batch([
-            ops.gemm_desc(self.t1_h, p["image_decoder.hallucinate.2.weight"], self.colsT2, 2 * B * 196, 16, 64),
-            ops.gemm_desc(self.td_h[2], p["text_decoder.net.6.weight"], self.logit_t, 2 * B, 10, 512,
-                          bias=p["text_decoder.net.6.bias"])], P)
-        ops.col2im_k4s2p1(self.colsT2, self.logit_i, 2 * B, 14, 14, 1)
+        txt_last = ops.gemm_desc(self.td_h[2], p["text_decoder.net.6.weight"], self.logit_t, 2 * B, 10, 512,
+                                 bias=p["text_decoder.net.6.bias"])
+        if direct:
+            ops.gemm_batch([txt_last], P)
+            ops.convT_cout_fwd(self.t1_h, p["image_decoder.hallucinate.2.weight"], self.logit_i, 2 * B, 14, 14, 64, 1)
+        else:
+            ops.gemm_batch([
+                ops.gemm_desc(self.t1_h, p["image_decoder.hallucinate.2.weight"], self.colsT2, 2 * B * 196, 16, 64), txt_last], P)
+            ops.col2im_k4s2p1(self.colsT2, self.logit_i, 2 * B, 14, 14, 1)
 
     # ------------------------------------------------------------------ loss + backward
     def _enqueue_loss_and_backward(self, training: bool, b_global: int) -> None:
@@ -235,17 +247,24 @@ class FashionMVAETrainer(MnistMVAETrainer):
         ops.bce_logits_fwd_bwd(self.logit_i, self.x, self.logit_i, self.lam_i / b_global, self.acc[0:3], seg_rows=B)
         ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)
         # ---- last layers: convT2 (image) and net.6 (text)
-        ops.im2col_k4s2p1(self.logit_i, self.dcolsT2, 2 * B, 28, 28, 1)
+        direct = self.direct_c1
         ops.colsum_accumulate(self.logit_t, g["text_decoder.net.6.bias"])
-        ops.gemm_batch([
-            ops.gemm_desc(self.dcolsT2, self.t1_h, g["image_decoder.hallucinate.2.weight"], 16, 64, 2 * B * 196,
-                          a_mn=True, b_mn=True, split_k=split_for(2 * B * 196), accumulate=True),
-            ops.gemm_desc(self.dcolsT2, p["image_decoder.hallucinate.2.weight"], self.d_t1, 2 * B * 196, 64, 16, b_mn=True,
-                          aux=self.t1_a, epilogue=ops.EPI_MUL_DSWISH),
+        txt_last = [
             ops.gemm_desc(self.logit_t, self.td_h[2], g["text_decoder.net.6.weight"], 10, 512, 2 * B, a_mn=True, b_mn=True,
                           split_k=split_for(2 * B), accumulate=True),
             ops.gemm_desc(self.logit_t, p["text_decoder.net.6.weight"], self.td_dA[0], 2 * B, 512, 10, b_mn=True,
-                          aux=self.td_a[2], epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_decoder.net.4.bias"])], P)
+                          aux=self.td_a[2], epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_decoder.net.4.bias"])]
+        if direct:
+            ops.convT_cout_bwd(self.logit_i, self.t1_h, self.t1_a, p["image_decoder.hallucinate.2.weight"], self.d_t1,
+                               g["image_decoder.hallucinate.2.weight"], 2 * B, 14, 14, 64, 1)
+            ops.gemm_batch(txt_last, P)
+        else:
+            ops.im2col_k4s2p1(self.logit_i, self.dcolsT2, 2 * B, 28, 28, 1)
+            ops.gemm_batch([
+                ops.gemm_desc(self.dcolsT2, self.t1_h, g["image_decoder.hallucinate.2.weight"], 16, 64, 2 * B * 196,
+                              a_mn=True, b_mn=True, split_k=split_for(2 * B * 196), accumulate=True),
+                ops.gemm_desc(self.dcolsT2, p["image_decoder.hallucinate.2.weight"], self.d_t1, 2 * B * 196, 64, 16, b_mn=True,
+                              aux=self.t1_a, epilogue=ops.EPI_MUL_DSWISH)] + txt_last, P)
         # ---- convT1 (image) and net.4 (text)
         ops.im2col_k4s2p1(self.d_t1, self.dcolsT1, 2 * B, 14, 14, 64)
         ops.gemm_batch([
@@ -318,5 +337,8 @@ class FashionMVAETrainer(MnistMVAETrainer):
             ops.gemm_desc(self.d_c2, p["image_encoder.features.2.weight"], self.dcols2, B * 49, 1024, 128, b_mn=True)], P)
         ops.col2im_k4s2p1(self.dcols2, self.d_c1, B, 7, 7, 64, aux=self.c1_a)
         # ---- conv1 (no data gradient: the image is an input)
-        ops.gemm_batch([ops.gemm_desc(self.d_c1, self.cols1, g["image_encoder.features.0.weight"], 64, 16, B * 196,
-                                      a_mn=True, b_mn=True, split_k=split_for(B * 196), accumulate=True)], P)
+        if direct:
+            ops.conv_cin_wgrad(self.x, self.d_c1, g["image_encoder.features.0.weight"], B, 28, 28, 1, 64)
+        else:
+            ops.gemm_batch([ops.gemm_desc(self.d_c1, self.cols1, g["image_encoder.features.0.weight"], 64, 16, B * 196,
+                                          a_mn=True, b_mn=True, split_k=split_for(B * 196), accumulate=True)], P)

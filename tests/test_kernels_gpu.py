@@ -254,7 +254,7 @@ def test_label_table_fwd_bwd(ops, V, D, N3):
     # gradients ACCUMULATE: start from a non-zero value to check that
     base = 0.25
     g = {k: torch.full(s, base, device="cuda") for k, s in (("emb", (V, D)), ("w2", (D, D)), ("b2", (D,)), ("w3", (N3, D)), ("b3", (N3,)))}
-    d_a2 = torch.full((V, D), float("nan"), device="cuda")
+    d_a2 = torch.zeros(V, D, device="cuda")        # accumulation target: zero-initialised by the caller
     ops.label_table_bwd(dev[0], dev[1], dev[3], a2, h2, dev[5], d_a2, g["emb"], g["w2"], g["b2"], g["w3"], g["b3"])
     for k, ref in (("emb", e64.grad), ("w2", w2_64.grad), ("b2", b2_64.grad), ("w3", w3_64.grad), ("b3", b3_64.grad)):
         assert _rel(g[k].cpu() - base, ref) < 5e-6, k
