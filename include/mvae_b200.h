@@ -63,6 +63,12 @@ typedef struct {
   int32_t epilogue;               /* MVAE_EPI_*                                                     */
   int32_t split_k;                /* >= 1; > 1 => partial products are atomically added into C      */
   int32_t accumulate;             /* 1 => C += result (atomic red.add), 0 => C = result             */
+  float* split_ws;                /* optional [M][ceil4(N)] fp32 scratch, zero-initialised ONCE by the caller (the kernel     */
+                                  /* leaves it zeroed): with split_k > 1 and accumulate = 0 the k range of every output tile  */
+                                  /* is split over split_k CTAs, their partial sums meet here and the LAST arriver applies    */
+                                  /* the full epilogue (bias / Swish / Swish' / colsum) -- for layers with fewer output tiles  */
+                                  /* than SMs (small per-GPU batches, K = 6272 classifier layers).  mvae_gemm_chain only;     */
+                                  /* N % 4 == 0; one scratch per problem of a launch.                                          */
 } mvae_gemm_desc;
 
 /* Launch up to MVAE_GEMM_MAX_BATCH independent problems in ONE persistent kernel. */

@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ("out2", C.c_void_p), ("ldout2", C.c_int64),
         ("colsum", C.c_void_p),
         ("epilogue", C.c_int32), ("split_k", C.c_int32), ("accumulate", C.c_int32),
+        ("split_ws", C.c_void_p),
     ]
 
 

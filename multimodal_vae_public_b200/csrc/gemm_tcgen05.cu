@@ -98,6 +98,13 @@ struct alignas(64) GemmProblem {
   int ctr_base;           // first counter of this problem's row blocks
   int row_blocks;         // ceil(M / 128): counters of this problem
   int dep_row_blocks;     // counters of the producer from dep_ctr_base on (row blocks beyond do not exist)
+  // ---- fused split-K ("last arriver"): the k range of an output tile is split over split_k CTAs whose partial
+  // accumulators are red.add'ed into a zeroed fp32 scratch matrix; per (tile, epilogue warp) an arrival counter tells the
+  // last of them that its 32-row slab is complete -- it reads the sums back, applies the real epilogue (bias / Swish /
+  // Swish' / column sums), stores C / out2, re-zeroes the scratch and publishes the row block to the chain.
+  float* split_ws;        // [M][ldp] scratch or nullptr (plain split-K: partial sums red.add'ed straight into C)
+  int64_t ldp;
+  int tctr_base;          // first arrival counter of this problem (tiles_m * tiles_n * 8 counters)
 };
 
 struct GemmBatch {
@@ -442,6 +449,72 @@ __device__ __forceinline__ void epilogue_chunk_fast16(const EpiParams& e, uint32
   __syncwarp();  // the staging tile is rewritten by the next chunk
 }
 
+// Fused split-K, phase B (last arriver of a (tile, epilogue warp) slab): 32 rows x `ncols` columns of the summed partial
+// accumulators are read back from the scratch matrix (L2: the partials were red.add'ed there by other SMs), re-zeroed,
+// and pushed through the real epilogue.  Lane mapping as in epilogue_chunk: sub = lane / 8 rows of a group of 4,
+// cq = lane % 8 -> 4 consecutive columns; all 8 row loads of a lane are in flight together.  N % 4 == 0 (checked on host).
+__device__ __forceinline__ float4 ldcg128(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void epilogue_from_scratch(const EpiParams& e, float* P, int64_t ldp, int lane, int row_base,
+                                                      int col0, int ncols) {
+  const int sub = lane >> 3, cq = lane & 7;
+  const int col = col0 + 4 * cq;
+  const bool col_ok = 4 * cq < ncols && col < e.N;
+  float4 acc[8], aux[8];
+  const bool dsw = e.epilogue == MVAE_EPI_MUL_DSWISH;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + 4 * i + sub;
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    aux[i] = acc[i];
+    if (col_ok && row < e.M) {
+      acc[i] = ldcg128(P + static_cast<int64_t>(row) * ldp + col);
+      if (dsw) aux[i] = *reinterpret_cast<const float4*>(e.aux + static_cast<int64_t>(row) * e.ldaux + col);
+    }
+  }
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (col_ok && e.bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bv[q] = __ldg(e.bias + col + q);
+  }
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + 4 * i + sub;
+    if (!(col_ok && row < e.M)) continue;
+    *reinterpret_cast<float4*>(P + static_cast<int64_t>(row) * ldp + col) = make_float4(0.f, 0.f, 0.f, 0.f);   // ready for the next launch
+    float v[4] = {acc[i].x + bv[0], acc[i].y + bv[1], acc[i].z + bv[2], acc[i].w + bv[3]};
+    if (dsw) {
+      const float a[4] = {aux[i].x, aux[i].y, aux[i].z, aux[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float sg = sigmoidf_acc(a[q]);
+        v[q] *= sg * (1.0f + a[q] * (1.0f - sg));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cs[q] += v[q];
+    *reinterpret_cast<float4*>(e.C + static_cast<int64_t>(row) * e.ldc + col) = make_float4(v[0], v[1], v[2], v[3]);
+    if (e.epilogue == MVAE_EPI_BIAS_SWISH)
+      *reinterpret_cast<float4*>(e.out2 + static_cast<int64_t>(row) * e.ldout2 + col) =
+          make_float4(v[0] * sigmoidf_acc(v[0]), v[1] * sigmoidf_acc(v[1]), v[2] * sigmoidf_acc(v[2]), v[3] * sigmoidf_acc(v[3]));
+  }
+  if (e.colsum != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 8);
+      cs[q] += __shfl_xor_sync(0xffffffffu, cs[q], 16);
+    }
+    if (sub == 0 && col_ok) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ptx::red_add_f32(e.colsum + col + q, cs[q]);
+    }
+  }
+}
+
 template <bool kSplit, bool kPair>
 __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
   using C = Cfg<kSplit, kPair>;
@@ -705,6 +778,16 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
       e.C = p.C; e.bias = p.bias; e.aux = p.aux; e.out2 = p.out2; e.colsum = p.colsum;
       e.ldc = p.ldc; e.ldaux = p.ldaux; e.ldout2 = p.ldout2; e.M = p.M; e.N = p.N;
       e.epilogue = p.epilogue; e.atomic = p.atomic;
+      // fused split-K: phase A below adds the raw partial accumulator into the scratch matrix with the plain atomic
+      // STORE epilogue; the real epilogue parameters are kept in `ef` for the last arriver (phase B)
+      const bool fused = p.split_ws != nullptr;
+      const EpiParams ef = e;
+      if (fused) {
+        e.C = p.split_ws; e.ldc = p.ldp; e.bias = nullptr; e.aux = nullptr; e.out2 = nullptr; e.colsum = nullptr;
+        e.epilogue = MVAE_EPI_STORE; e.atomic = 1;
+      }
+      int* const tctr = fused ? batch.ws + WS_CTR0 + p.tctr_base + (ti.m_blk * p.tiles_n + ti.n_blk) * NUM_EPI_WARPS + ew
+                              : nullptr;
       const bool dsw = e.epilogue == MVAE_EPI_MUL_DSWISH;
       // interior tiles (the common case) take the specialised epilogue; edge tiles / unusual combinations the general one
       const bool rows_inside = row_base + 32 <= e.M && batch.dbg_flags == 0 &&
@@ -745,7 +828,13 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           if (kPair) ptx::mbar_arrive_cluster(tmem_empty_addr);
           else ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (my_ctr != nullptr && lane == 0) red_release_gpu_add(my_ctr, 1);
+        bool publish = true;
+        if (fused) {   // (this warp role has no columns on a narrow tile, but only ONE of the split CTAs may publish for it)
+          int last = 0;
+          if (lane == 0) last = atomicAdd(tctr, 1) == p.split_k - 1;
+          publish = __shfl_sync(0xffffffffu, last, 0) != 0;
+        }
+        if (publish && my_ctr != nullptr && lane == 0) red_release_gpu_add(my_ctr, 1);
         continue;
       }
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N_MAX;
@@ -791,6 +880,22 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           epilogue_chunk(e, stage_buf, r, ncols, lane, row_base, n0 + c0, bv, a0, batch.dbg_flags);
         }
         if (ew == 0 && lane == 0) dbg_stamp(batch, 3, dn3);
+      }
+      if (fused) {
+        // every lane's partial sums are on their way to L2; lane 0 (after the warp converged) orders them before the
+        // arrival count.  The split CTA that counts last owns the finished slab: phase B.
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          __threadfence();
+          last = atomicAdd(tctr, 1) == p.split_k - 1;
+          __threadfence();
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;                       // (nothing to publish: the slab is not complete yet)
+#pragma unroll 1
+        for (int c = half; c < nchunks; c += 2)
+          epilogue_from_scratch(ef, p.split_ws, p.ldp, lane, row_base, n0 + 32 * c, (block_n - 32 * c) >= 32 ? 32 : 16);
       }
       if (my_ctr != nullptr) {
         // chain mode: publish this warp's share of the tile.  Every lane orders its own stores against the async
@@ -1052,9 +1157,15 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
     if (d.epilogue < 0 || d.epilogue > MVAE_EPI_MUL_DSWISH)
       return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: unknown epilogue %d", who, i, d.epilogue);
     const int split = d.split_k < 1 ? 1 : d.split_k;
-    const bool atomic = split > 1 || d.accumulate;
+    // fused split-K: partial sums meet in the scratch matrix d.split_ws, the last arriver runs the real epilogue
+    const bool fused = split > 1 && !d.accumulate && d.split_ws != nullptr;
+    const bool atomic = !fused && (split > 1 || d.accumulate);
     if (atomic && (d.bias || d.epilogue != MVAE_EPI_STORE || d.colsum))
-      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: split_k/accumulate only with plain STORE epilogue", who, i);
+      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: split_k > 1 with a bias / activation / colsum epilogue needs split_ws "
+                       "(fused split-K); accumulate only with the plain STORE epilogue", who, i);
+    if (fused && (ws == nullptr || (d.N & 3) || (reinterpret_cast<uintptr_t>(d.split_ws) & 15) || pair))
+      return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: fused split-K needs mvae_gemm_chain (counter workspace), N %% 4 == 0 and a "
+                       "16-byte aligned split_ws", who, i);
     if ((d.ldc & 3) || (reinterpret_cast<uintptr_t>(d.C) & 15))
       return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: C must be 16B aligned with ldc %% 4 == 0", who, i);
     // MMA N: multiple of 16; MN-major B is fetched in 32-wide boxes.
@@ -1074,6 +1185,13 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
     tiles += p.tiles_m * p.tiles_n * s;
     p.ctr_base = ctrs;
     ctrs += p.row_blocks;
+    p.split_ws = nullptr; p.ldp = 0; p.tctr_base = 0;
+    if (fused && s > 1) {
+      p.split_ws = d.split_ws;
+      p.ldp = (d.N + 3) / 4 * 4;
+      p.tctr_base = ctrs;
+      ctrs += p.tiles_m * p.tiles_n * NUM_EPI_WARPS;
+    }
     p.a_mn = d.a_mn_major ? 1 : 0;
     p.b_mn = d.b_mn_major ? 1 : 0;
     p.epilogue = d.epilogue;
@@ -1107,7 +1225,8 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
       p.dep = q;
       p.dep_ctr_base = pq.ctr_base + static_cast<int>(row_off / BLOCK_M);
       p.dep_row_blocks = pq.row_blocks - static_cast<int>(row_off / BLOCK_M);
-      p.dep_target = NUM_EPI_WARPS * pq.tiles_n * pq.split_k;
+      // (fused split-K producers publish once per (tile, warp): only the last-arriving split CTA does)
+      p.dep_target = NUM_EPI_WARPS * pq.tiles_n * (pq.split_ws != nullptr ? 1 : pq.split_k);
     }
     int rc;
     if (!p.a_mn) rc = make_map(&p.map_a, d.A, d.K, d.M, d.lda, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);

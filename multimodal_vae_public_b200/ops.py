@@ -29,7 +29,7 @@ def _chk2d(t: torch.Tensor, name: str):
 
 
 def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, out2=None, epilogue=EPI_STORE,
-              split_k=1, accumulate=False, colsum=None) -> GemmDesc:
+              split_k=1, accumulate=False, colsum=None, split_ws=None) -> GemmDesc:
     d = GemmDesc()
     d.A, d.lda, d.a_mn_major = A.data_ptr(), A.stride(0), int(a_mn)
     d.B, d.ldb, d.b_mn_major = B.data_ptr(), B.stride(0), int(b_mn)
@@ -40,6 +40,7 @@ def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, 
     d.out2, d.ldout2 = _p(out2), (out2.stride(0) if out2 is not None else 0)
     d.colsum = _p(colsum)
     d.epilogue, d.split_k, d.accumulate = epilogue, split_k, int(accumulate)
+    d.split_ws = _p(split_ws)      # fused split-K scratch [M, ceil4(N)] (zeroed once; see include/mvae_b200.h)
     return d
 
 

@@ -160,6 +160,10 @@ class MnistMVAETrainer:
         # label-table mode: the label encoder only ever sees 10 distinct inputs, so it is evaluated once per CLASS
         # (csrc/label_table.cu) and the PoE kernels gather row text[b]; MVAE_LABEL_TABLE=0 restores the per-sample GEMMs
         self.label_table = os.environ.get("MVAE_LABEL_TABLE", "1") != "0" if label_table is None else bool(label_table)
+        # fused split-K (last-arriver epilogue) for problems with fewer output tiles than SMs; MVAE_FUSED_SPLIT=0 disables
+        self.fused_split = os.environ.get("MVAE_FUSED_SPLIT", "1") != "0"
+        self._split_ws: Dict[str, torch.Tensor] = {}
+        self._sms = torch.cuda.get_device_properties(torch.device(device)).multi_processor_count
         self.layout = self._make_layout(n_latents)
         # Data-parallel exchange: "p2p" = ONE fused kernel per rank over NVLink peer memory (gradient reduce-scatter ->
         # Adam on the rank's slice -> parameter all-gather, csrc/dp_p2p.cu); "nccl" = ncclAllReduce + flat Adam.
@@ -267,6 +271,35 @@ class MnistMVAETrainer:
         self.id_dA = [f(2 * B, 512) for _ in range(3)]; self.td_dA = [f(2 * B, 512) for _ in range(3)]
         self.ie_dA = [f(B, 512) for _ in range(2)]; self.te_dA = [f(B, 512) for _ in range(2)]
 
+    # ------------------------------------------------------------------ GEMM problem helpers
+    def _D(self, key: str, A, Bm, Cm, M: int, N: int, K: int, share: int = 1, **kw):
+        """``ops.gemm_desc`` for a forward / dgrad problem, with FUSED SPLIT-K chosen automatically when the problem has
+        fewer output tiles than its share of the SMs (small per-GPU batches, the K = 6272 classifier layers): the k range
+        of every tile is split over several CTAs, the last arriver applies the epilogue (include/mvae_b200.h, split_ws).
+        ``share`` = number of sibling problems of the same launch that want SMs at the same time; ``key`` names the
+        problem's scratch matrix."""
+        if self.fused_split and N % 4 == 0 and not kw.get("accumulate", False) and kw.get("split_k", 1) == 1:
+            bn = 128 if N >= 128 else (N + 31) // 32 * 32 if kw.get("b_mn") else (N + 15) // 16 * 16
+            tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+            kb = (K + 31) // 32
+            budget = max(1, self._sms // max(share, 1))
+            if 2 * tiles <= budget and kb >= 8:
+                split = min(budget // tiles, kb // 4, 16)
+                if split > 1:
+                    ws = self._split_ws.get(key)
+                    if ws is None or ws.numel() < M * ((N + 3) // 4 * 4):
+                        ws = self._split_ws[key] = torch.zeros(M * ((N + 3) // 4 * 4), dtype=torch.float32, device=self.dev)
+                    kw.update(split_k=split, split_ws=ws)
+        return ops.gemm_desc(A, Bm, Cm, M, N, K, **kw)
+
+    def _gemm(self, descs) -> None:
+        """Independent problems in one launch (a chained launch without dependencies when a problem uses fused split-K,
+        which needs the counter workspace)."""
+        if any(d.split_ws for d in descs):
+            ops.gemm_chain(descs, [-1] * len(descs), self.chain_ws, self.prec)
+        else:
+            ops.gemm_batch(descs, self.prec)
+
     # ------------------------------------------------------------------ parameters
     def init_parameters(self, seed: int = 0) -> None:
         """PyTorch-default initialisation scales (nn.Linear: U(+-1/sqrt(fan_in)); nn.Embedding: N(0,1))."""
@@ -345,14 +378,17 @@ class MnistMVAETrainer:
         wt = self.arena.span(0, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512)
         bt = self.arena.span(0, "text_encoder.fc31.bias", "text_encoder.fc32.bias")
         D = ops.gemm_desc
-        fc1_i = D(self.x, p["image_encoder.fc1.weight"], self.ie_a1, B, 512, 784, bias=p["image_encoder.fc1.bias"],
+        ch = self.chain      # (fused split-K lives in chained launches)
+        sh = 1 if self.label_table else 2
+        S = (lambda key, *a, **k: self._D(key, *a, **k)) if ch else (lambda key, *a, share=1, **k: D(*a, **k))
+        fc1_i = S("fc1_i", self.x, p["image_encoder.fc1.weight"], self.ie_a1, B, 512, 784, bias=p["image_encoder.fc1.bias"],
                   out2=self.ie_h1, epilogue=ops.EPI_BIAS_SWISH)
-        fc2_i = D(self.ie_h1, p["image_encoder.fc2.weight"], self.ie_a2, B, 512, 512,
+        fc2_i = S("fc2_i", self.ie_h1, p["image_encoder.fc2.weight"], self.ie_a2, B, 512, 512, share=sh,
                   bias=p["image_encoder.fc2.bias"], out2=self.ie_h2, epilogue=ops.EPI_BIAS_SWISH)
-        fc2_t = D(self.te_h1, p["text_encoder.fc2.weight"], self.te_a2, B, 512, 512,
+        fc2_t = S("fc2_t", self.te_h1, p["text_encoder.fc2.weight"], self.te_a2, B, 512, 512, share=2,
                   bias=p["text_encoder.fc2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)
-        heads_i = D(self.ie_h2, wi, self.enc_i, B, 2 * L, 512, bias=bi)
-        heads_t = D(self.te_h2, wt, self.enc_t, B, 2 * L, 512, bias=bt)
+        heads_i = S("heads_i", self.ie_h2, wi, self.enc_i, B, 2 * L, 512, share=sh, bias=bi)
+        heads_t = S("heads_t", self.te_h2, wt, self.enc_t, B, 2 * L, 512, share=2, bias=bt)
         if self.label_table:
             emb, w2, b2, w3, b3 = self._label_encoder(0)
             ops.label_table_fwd(emb, w2, b2, w3, b3, self.tt_a2, self.tt_h2, self.enc_tab)
@@ -386,13 +422,13 @@ class MnistMVAETrainer:
         for l in range(3):
             K = L if l == 0 else 512
             layers.append([
-                D(xin_i, p[f"image_decoder.fc{l + 1}.weight"], self.id_a[l], 2 * B, 512, K,
+                S(f"id{l}", xin_i, p[f"image_decoder.fc{l + 1}.weight"], self.id_a[l], 2 * B, 512, K, share=2,
                   bias=p[f"image_decoder.fc{l + 1}.bias"], out2=self.id_h[l], epilogue=ops.EPI_BIAS_SWISH),
-                D(xin_t, p[f"text_decoder.fc{l + 1}.weight"], self.td_a[l], 2 * B, 512, K,
+                S(f"td{l}", xin_t, p[f"text_decoder.fc{l + 1}.weight"], self.td_a[l], 2 * B, 512, K, share=2,
                   bias=p[f"text_decoder.fc{l + 1}.bias"], out2=self.td_h[l], epilogue=ops.EPI_BIAS_SWISH)])
             xin_i, xin_t = self.id_h[l], self.td_h[l]
         layers.append([
-            D(xin_i, p["image_decoder.fc4.weight"], self.logit_i, 2 * B, 784, 512, bias=p["image_decoder.fc4.bias"]),
+            S("id3", xin_i, p["image_decoder.fc4.weight"], self.logit_i, 2 * B, 784, 512, bias=p["image_decoder.fc4.bias"]),
             D(xin_t, p["text_decoder.fc4.weight"], self.logit_t, 2 * B, 10, 512, bias=p["text_decoder.fc4.bias"])])
         if self.chain:   # both decoders, all four layers: one launch (problem 2l+d reads the output of problem 2(l-1)+d)
             ops.gemm_chain([d for pair in layers for d in pair], [-1, -1, 0, 1, 2, 3, 4, 5], self.chain_ws, P)
@@ -412,6 +448,7 @@ class MnistMVAETrainer:
         ops.colsum_accumulate(dyi, g["image_decoder.fc4.bias"])
         ops.colsum_accumulate(dyt, g["text_decoder.fc4.bias"])
         D = ops.gemm_desc
+        S = (lambda key, *a, **k: self._D(key, *a, **k)) if self.chain else (lambda key, *a, share=1, **k: D(*a, **k))
         split = max(1, min(nk // 16, 32))   # ~16 k-blocks per wgrad tile, like the dgrad tiles of the same launch
         chain_descs, chain_deps = [], []
         for l in (4, 3, 2, 1):
@@ -427,10 +464,10 @@ class MnistMVAETrainer:
                   split_k=split, accumulate=True)]
             if l > 1:  # dA_{l-1} = (dy W_l) * swish'(a_{l-1}); its column sums are the bias gradient of layer l-1
                 dxi, dxt = self.id_dA[l - 2], self.td_dA[l - 2]
-                dgrads = [
-                    D(dyi, p[f"image_decoder.fc{l}.weight"], dxi, 2 * B, K, n_i, b_mn=True,
+                dgrads = [   # (share 4: the two dgrads compete with the two split-K wgrads of the layer for the SMs)
+                    S(f"dgi{l}", dyi, p[f"image_decoder.fc{l}.weight"], dxi, 2 * B, K, n_i, share=4, b_mn=True,
                       aux=self.id_a[l - 2], epilogue=ops.EPI_MUL_DSWISH, colsum=g[f"image_decoder.fc{l - 1}.bias"]),
-                    D(dyt, p[f"text_decoder.fc{l}.weight"], dxt, 2 * B, K, n_t, b_mn=True,
+                    S(f"dgt{l}", dyt, p[f"text_decoder.fc{l}.weight"], dxt, 2 * B, K, n_t, share=4, b_mn=True,
                       aux=self.td_a[l - 2], epilogue=ops.EPI_MUL_DSWISH, colsum=g[f"text_decoder.fc{l - 1}.bias"])]
             else:  # dZ is zero-initialised; both decoders add into it (the joint rows get both)
                 dxi, dxt = self.dZ[: 2 * B], self.dZ[B:]
@@ -469,14 +506,14 @@ class MnistMVAETrainer:
         wg_hi = D(self.d_enc_i, self.ie_h2, gwi, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True)
         wg_ht = D(self.d_enc_t, self.te_h2, gwt, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True)
         dg_hi = D(self.d_enc_i, wi, self.ie_dA[0], B, 512, 2 * L, b_mn=True, aux=self.ie_a2,
-                  epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc2.bias"])
+                  epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc2.bias"])   # (K = 128: 4 k-blocks, nothing to split)
         dg_ht = D(self.d_enc_t, wt, self.te_dA[0], B, 512, 2 * L, b_mn=True, aux=self.te_a2,
                   epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_encoder.fc2.bias"])
         wg_2i = D(self.ie_dA[0], self.ie_h1, g["image_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
                   split_k=split, accumulate=True)
         wg_2t = D(self.te_dA[0], self.te_h1, g["text_encoder.fc2.weight"], 512, 512, B, a_mn=True, b_mn=True,
                   split_k=split, accumulate=True)
-        dg_2i = D(self.ie_dA[0], p["image_encoder.fc2.weight"], self.ie_dA[1], B, 512, 512, b_mn=True,
+        dg_2i = S("dg_2i", self.ie_dA[0], p["image_encoder.fc2.weight"], self.ie_dA[1], B, 512, 512, share=2, b_mn=True,
                   aux=self.ie_a1, epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_encoder.fc1.bias"])
         dg_2t = D(self.te_dA[0], p["text_encoder.fc2.weight"], self.te_dA[1], B, 512, 512, b_mn=True)
         wg_1i = D(self.ie_dA[1], self.x, g["image_encoder.fc1.weight"], 512, 784, B, a_mn=True, b_mn=True,

@@ -194,13 +194,14 @@ class FashionMVAETrainer(MnistMVAETrainer):
                           out2=self.c2_h, epilogue=ops.EPI_BIAS_SWISH)] + ([] if lt else [
             ops.gemm_desc(self.te_h1, p["text_encoder.net.2.weight"], self.te_a2, B, 512, 512,
                           bias=p["text_encoder.net.2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)]), P)
-        ops.gemm_batch([
-            ops.gemm_desc(self.c2_h.view(B, 6272), p["image_encoder.classifier.0.weight"], self.fc_a, B, 512, 6272,
-                          bias=p["image_encoder.classifier.0.bias"], out2=self.fc_h, epilogue=ops.EPI_BIAS_SWISH)] + ([] if lt else [
+        # (classifier.0 has K = 6272 but only B/128 x 4 output tiles: fused split-K when that leaves SMs idle)
+        self._gemm([
+            self._D("cls0", self.c2_h.view(B, 6272), p["image_encoder.classifier.0.weight"], self.fc_a, B, 512, 6272,
+                    bias=p["image_encoder.classifier.0.bias"], out2=self.fc_h, epilogue=ops.EPI_BIAS_SWISH)] + ([] if lt else [
             ops.gemm_desc(self.te_h2, p["text_encoder.net.4.weight"], self.enc_t, B, 2 * L, 512,
-                          bias=p["text_encoder.net.4.bias"])]), P)
-        ops.gemm_batch([ops.gemm_desc(self.fc_h, p["image_encoder.classifier.2.weight"], self.enc_i, B, 2 * L, 512,
-                                      bias=p["image_encoder.classifier.2.bias"])], P)
+                          bias=p["text_encoder.net.4.bias"])]))
+        self._gemm([self._D("cls2", self.fc_h, p["image_encoder.classifier.2.weight"], self.enc_i, B, 2 * L, 512,
+                            bias=p["image_encoder.classifier.2.bias"])])
         # ---- PoE + reparametrise + KL (three passes)
         mu_e, lv_e, _, _, gather = self._label_experts()
         ops.poe_fwd(mu_e, lv_e, _PASS_MASKS, B, L, self.Z, variant=0, training=training,
@@ -278,15 +279,15 @@ class FashionMVAETrainer(MnistMVAETrainer):
                           aux=self.td_a[1], epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_decoder.net.2.bias"])], P)
         # ---- upsampler.2 (image) and net.2 (text)
         ops.colsum_accumulate(self.d_u2, g["image_decoder.upsampler.2.bias"])
-        ops.gemm_batch([
+        self._gemm([
             ops.gemm_desc(self.d_u2, self.u1_h, g["image_decoder.upsampler.2.weight"], 6272, 512, 2 * B, a_mn=True, b_mn=True,
                           split_k=split_for(2 * B), accumulate=True),
-            ops.gemm_desc(self.d_u2, p["image_decoder.upsampler.2.weight"], self.d_u1, 2 * B, 512, 6272, b_mn=True,
-                          aux=self.u1_a, epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_decoder.upsampler.0.bias"]),
+            self._D("dg_u2", self.d_u2, p["image_decoder.upsampler.2.weight"], self.d_u1, 2 * B, 512, 6272, share=3, b_mn=True,
+                    aux=self.u1_a, epilogue=ops.EPI_MUL_DSWISH, colsum=g["image_decoder.upsampler.0.bias"]),
             ops.gemm_desc(self.td_dA[1], self.td_h[0], g["text_decoder.net.2.weight"], 512, 512, 2 * B, a_mn=True, b_mn=True,
                           split_k=split_for(2 * B), accumulate=True),
             ops.gemm_desc(self.td_dA[1], p["text_decoder.net.2.weight"], self.td_dA[0], 2 * B, 512, 512, b_mn=True,
-                          aux=self.td_a[0], epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_decoder.net.0.bias"])], P)
+                          aux=self.td_a[0], epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_decoder.net.0.bias"])])
         # ---- first decoder layers -> dZ (zero-initialised, both decoders add)
         ops.gemm_batch([
             ops.gemm_desc(self.d_u1, self.Z[: 2 * B], g["image_decoder.upsampler.0.weight"], 512, L, 2 * B, a_mn=True,

@@ -167,3 +167,61 @@ def test_trainer_chain_matches_layerwise(B):
     assert max(losses) - min(losses) <= 1e-6 * abs(losses[0])
     assert abs(losses[0] - out[False][0]) <= 1e-5 * abs(out[False][0])
     assert int(tr.chain_ws[1]) == 0
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("M,N,K,split", [(512, 512, 6272, 9), (1024, 512, 784, 4), (300, 128, 512, 4), (128, 64, 2048, 16),
+                                         (1000, 784, 512, 2), (8, 512, 512, 4)])
+def test_fused_split_k_forward_stack(ops, prec, M, N, K, split):
+    """Fused split-K (last-arriver epilogue): layer 1 = bias + Swish with its k range split over `split` CTAs per output
+    tile, layer 2 consumes its out2 inside the same chained launch (dependency counters count ONE publication per tile
+    and warp), layer 2 itself split as well with a plain bias epilogue.  Scratch and counters must come back zeroed."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w1 = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5; b1 = torch.randn(N, device="cuda", generator=g)
+    w2 = torch.randn(64, N, device="cuda", generator=g) / N ** 0.5; b2 = torch.randn(64, device="cuda", generator=g)
+    a1 = torch.full((M, N), float("nan"), device="cuda"); h1 = torch.full((M, N), float("nan"), device="cuda")
+    y2 = torch.full((M, 64), float("nan"), device="cuda")
+    s1 = torch.zeros(M, N, device="cuda"); s2 = torch.zeros(M, 64, device="cuda")
+    wsb = ops.chain_workspace("cuda")
+    for rep in range(3):
+        ops.gemm_chain([ops.gemm_desc(x, w1, a1, M, N, K, bias=b1, out2=h1, epilogue=ops.EPI_BIAS_SWISH, split_k=split, split_ws=s1),
+                        ops.gemm_desc(h1, w2, y2, M, 64, N, bias=b2, split_k=2, split_ws=s2)], [-1, 0], wsb, prec)
+        torch.cuda.synchronize()
+        assert int(wsb[1]) == 0 and int(wsb.abs().sum()) == 0
+        assert float(s1.abs().max()) == 0.0 and float(s2.abs().max()) == 0.0, "scratch not re-zeroed"
+    r1 = x.double() @ w1.double().t() + b1.double()
+    assert _rel(a1, r1) < TOL[prec]
+    rh = r1 * torch.sigmoid(r1)
+    assert _rel(h1, rh) < TOL[prec]
+    assert _rel(y2, rh @ w2.double().t() + b2.double()) < 2 * TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("M,N,K,split", [(512, 512, 6272, 8), (1024, 64, 512, 4), (200, 512, 128, 2)])
+def test_fused_split_k_dgrad_with_dswish_and_colsum(ops, prec, M, N, K, split):
+    """dgrad form (B MN-major) with the MUL_DSWISH epilogue and the fused bias-gradient column sums, k range split."""
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + N + K)
+    dy = torch.randn(M, K, device="cuda", generator=g); w = torch.randn(K, N, device="cuda", generator=g) / K ** 0.5
+    aux = torch.randn(M, N, device="cuda", generator=g)
+    dx = torch.full((M, N), float("nan"), device="cuda"); cs = torch.zeros(N, device="cuda")
+    s = torch.zeros(M, N, device="cuda")
+    wsb = ops.chain_workspace("cuda")
+    ops.gemm_chain([ops.gemm_desc(dy, w, dx, M, N, K, b_mn=True, aux=aux, epilogue=ops.EPI_MUL_DSWISH, colsum=cs,
+                                  split_k=split, split_ws=s)], [-1], wsb, prec)
+    torch.cuda.synchronize()
+    sg = torch.sigmoid(aux.double())
+    ref = (dy.double() @ w.double()) * (sg * (1 + aux.double() * (1 - sg)))
+    assert _rel(dx, ref) < TOL[prec]
+    assert _rel(cs, ref.sum(0)) < TOL[prec] * 4
+    assert float(s.abs().max()) == 0.0 and int(wsb.abs().sum()) == 0
+
+
+def test_fused_split_k_needs_scratch_and_chain(ops):
+    from multimodal_vae_public_b200 import _lib
+    x = torch.randn(128, 256, device="cuda"); w = torch.randn(64, 256, device="cuda"); b = torch.randn(64, device="cuda")
+    y = torch.empty(128, 64, device="cuda")
+    with pytest.raises(_lib.MvaeError):      # bias epilogue + split_k without scratch
+        ops.gemm_chain([ops.gemm_desc(x, w, y, 128, 64, 256, bias=b, split_k=2)], [-1], ops.chain_workspace("cuda"), 1)
+    with pytest.raises(_lib.MvaeError):      # gemm_batch has no counter workspace
+        ops.gemm_batch([ops.gemm_desc(x, w, y, 128, 64, 256, bias=b, split_k=2, split_ws=torch.zeros(128, 64, device="cuda"))], 1)
