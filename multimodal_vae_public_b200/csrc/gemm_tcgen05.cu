@@ -515,7 +515,10 @@ __device__ __forceinline__ void epilogue_from_scratch(const EpiParams& e, float*
   }
 }
 
-template <bool kSplit, bool kPair>
+// kFused: the launch contains fused split-K problems.  A separate instantiation: the phase-B code next to the main
+// epilogue costs registers (100-200 bytes of spills at the 128-register budget of the 14-warp CTA), which launches without
+// such problems -- all the large ones -- must not pay.
+template <bool kSplit, bool kPair, bool kFused = false>
 __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
   using C = Cfg<kSplit, kPair>;
   static_assert(!kPair || kSplit, "the CTA-pair variant exists for the 3xTF32 mode only");
@@ -780,14 +783,13 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
       e.epilogue = p.epilogue; e.atomic = p.atomic;
       // fused split-K: phase A below adds the raw partial accumulator into the scratch matrix with the plain atomic
       // STORE epilogue; the real epilogue parameters are kept in `ef` for the last arriver (phase B)
-      const bool fused = p.split_ws != nullptr;
-      const EpiParams ef = e;
+      // (the real parameters are re-read from the problem table by the last arriver: keeping a second copy live across
+      // phase A cost ~100 bytes of spills in every launch, fused or not)
+      const bool fused = kFused && p.split_ws != nullptr;
       if (fused) {
         e.C = p.split_ws; e.ldc = p.ldp; e.bias = nullptr; e.aux = nullptr; e.out2 = nullptr; e.colsum = nullptr;
         e.epilogue = MVAE_EPI_STORE; e.atomic = 1;
       }
-      int* const tctr = fused ? batch.ws + WS_CTR0 + p.tctr_base + (ti.m_blk * p.tiles_n + ti.n_blk) * NUM_EPI_WARPS + ew
-                              : nullptr;
       const bool dsw = e.epilogue == MVAE_EPI_MUL_DSWISH;
       // interior tiles (the common case) take the specialised epilogue; edge tiles / unusual combinations the general one
       const bool rows_inside = row_base + 32 <= e.M && batch.dbg_flags == 0 &&
@@ -831,6 +833,7 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
         bool publish = true;
         if (fused) {   // (this warp role has no columns on a narrow tile, but only ONE of the split CTAs may publish for it)
           int last = 0;
+          int* const tctr = batch.ws + WS_CTR0 + p.tctr_base + (ti.m_blk * p.tiles_n + ti.n_blk) * NUM_EPI_WARPS + ew;
           if (lane == 0) last = atomicAdd(tctr, 1) == p.split_k - 1;
           publish = __shfl_sync(0xffffffffu, last, 0) != 0;
         }
@@ -887,15 +890,18 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
         __syncwarp();
         int last = 0;
         if (lane == 0) {
+          int* const tctr = batch.ws + WS_CTR0 + p.tctr_base + (ti.m_blk * p.tiles_n + ti.n_blk) * NUM_EPI_WARPS + ew;
           __threadfence();
           last = atomicAdd(tctr, 1) == p.split_k - 1;
           __threadfence();
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (!last) continue;                       // (nothing to publish: the slab is not complete yet)
+        e.C = p.C; e.bias = p.bias; e.aux = p.aux; e.out2 = p.out2; e.colsum = p.colsum;
+        e.ldc = p.ldc; e.epilogue = p.epilogue; e.atomic = 0;
 #pragma unroll 1
         for (int c = half; c < nchunks; c += 2)
-          epilogue_from_scratch(ef, p.split_ws, p.ldp, lane, row_base, n0 + 32 * c, (block_n - 32 * c) >= 32 ? 32 : 16);
+          epilogue_from_scratch(e, p.split_ws, p.ldp, lane, row_base, n0 + 32 * c, (block_n - 32 * c) >= 32 ? 32 : 16);
       }
       if (my_ctr != nullptr) {
         // chain mode: publish this warp's share of the tile.  Every lane orders its own stores against the async
@@ -1027,9 +1033,9 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
   }
 }
 
-template <bool kSplit>
+template <bool kSplit, bool kFused = false>
 __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __grid_constant__ GemmBatch batch) {
-  gemm_body<kSplit, false>(batch);
+  gemm_body<kSplit, false, kFused>(batch);
 }
 
 // CTA-pair variant (3xTF32): launched as clusters of two CTAs (adjacent SMs of a TPC), tcgen05 cta_group::2.
@@ -1142,6 +1148,7 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
   GemmBatch batch;   // ~7 KiB of launch parameters (copied by value at launch)
   memset(&batch, 0, sizeof(batch));
   int tiles = 0, ctrs = 0;
+  bool any_fused = false;
   const bool pair = use_pair_kernel(precision);
   const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
   const MnEncoding mn = mn_encoding();
@@ -1187,6 +1194,7 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
     ctrs += p.row_blocks;
     p.split_ws = nullptr; p.ldp = 0; p.tctr_base = 0;
     if (fused && s > 1) {
+      any_fused = true;
       p.split_ws = d.split_ws;
       p.ldp = (d.N + 3) / 4 * 4;
       p.tctr_base = ctrs;
@@ -1264,18 +1272,24 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
     gemm_pair_kernel<<<2 * clusters, Cfg<true, true>::kThreads, Cfg<true, true>::kSmemBytes, st>>>(batch);
   } else if (precision == MVAE_PREC_3XTF32) {
     if (!attr_set[1]) {
-      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<true>::kSmemBytes));
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<true>::kSmemBytes));
       attr_set[1] = true;
     }
-    gemm_kernel<true><<<grid, Cfg<true>::kThreads, Cfg<true>::kSmemBytes, st>>>(batch);
+    if (any_fused) gemm_kernel<true, true><<<grid, Cfg<true>::kThreads, Cfg<true>::kSmemBytes, st>>>(batch);
+    else gemm_kernel<true, false><<<grid, Cfg<true>::kThreads, Cfg<true>::kSmemBytes, st>>>(batch);
   } else {
     if (!attr_set[0]) {
-      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg<false>::kSmemBytes));
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg<false>::kSmemBytes));
       attr_set[0] = true;
     }
-    gemm_kernel<false><<<grid, Cfg<false>::kThreads, Cfg<false>::kSmemBytes, st>>>(batch);
+    if (any_fused) gemm_kernel<false, true><<<grid, Cfg<false>::kThreads, Cfg<false>::kSmemBytes, st>>>(batch);
+    else gemm_kernel<false, false><<<grid, Cfg<false>::kThreads, Cfg<false>::kSmemBytes, st>>>(batch);
   }
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());

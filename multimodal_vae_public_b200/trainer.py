@@ -283,8 +283,11 @@ class MnistMVAETrainer:
             tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
             kb = (K + 31) // 32
             budget = max(1, self._sms // max(share, 1))
-            if 2 * tiles <= budget and kb >= 8:
-                split = min(budget // tiles, kb // 4, 16)
+            # measured (profiles/r02_fused_split_ab.txt): worth it for LONG reductions only -- the K = 6272 classifier layers
+            # at 512 rows/GPU gain 5 % of the FashionMNIST step, while splitting the K = 512 / 784 MNIST layers costs 6 %
+            # (pipeline fill + the scratch round trip outweigh the shorter k loop): keep >= 16 k-blocks per split
+            if 2 * tiles <= budget and kb >= 48:
+                split = min(budget // tiles, kb // 16, 16)
                 if split > 1:
                     ws = self._split_ws.get(key)
                     if ws is None or ws.numel() < M * ((N + 3) // 4 * 4):
