@@ -32,10 +32,50 @@ __device__ __forceinline__ float dswish_m(float x) {
   return s * (1.0f + x * (1.0f - s));
 }
 
+// Stage the filter taps of `npx` consecutive output pixels [p0, p0 + npx) in shared memory: s_tap[pixel][K = 16 CIN], k =
+// (kh, kw, ci), zero at the padding and beyond the last pixel.  4 tasks per pixel (one per kh): the (image, row, column)
+// decomposition and the bounds tests are done ONCE per 4 CIN taps instead of once per multiply (the first version
+// recomputed them per FMA operand and was instruction-bound: 155 M warp instructions for 411 MB of output).
+template <int CIN>
+__device__ __forceinline__ void stage_taps(const float* __restrict__ x, float* s_tap, int64_t p0, int npx, int64_t npix,
+                                           int H, int W, int OH, int OW) {
+  constexpr int K = 16 * CIN;
+  for (int task = threadIdx.x; task < npx * 4; task += blockDim.x) {
+    const int pi = task >> 2, kh = task & 3;
+    const int64_t p = p0 + pi;
+    float v[4 * CIN];
+#pragma unroll
+    for (int j = 0; j < 4 * CIN; ++j) v[j] = 0.f;
+    if (p < npix) {
+      const int b = static_cast<int>(p / (OH * OW));
+      const int r = static_cast<int>(p - static_cast<int64_t>(b) * OH * OW);
+      const int oh = r / OW, ow = r - oh * OW;
+      const int iy = 2 * oh - 1 + kh;
+      if (iy >= 0 && iy < H) {
+        const float* row = x + (static_cast<int64_t>(b) * H + iy) * W * CIN;
+        const int ix0 = 2 * ow - 1;
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw) {
+          const int ix = ix0 + kw;
+          if (ix >= 0 && ix < W) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) v[kw * CIN + ci] = __ldg(row + ix * CIN + ci);
+          }
+        }
+      }
+    }
+    float* dst = s_tap + pi * K + kh * 4 * CIN;
+#pragma unroll
+    for (int j = 0; j < 4 * CIN; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Conv2d(CIN -> Cout), forward: a[p][co] = sum_{kh,kw,ci} x[b, 2oh-1+kh, 2ow-1+kw, ci] * Wc[co][(kh,kw,ci)], h = swish(a)
-// One thread = 4 consecutive output channels of kPix output pixels (weights read once per tap for the kPix pixels);
-// the Cout/4 threads of a pixel are adjacent lanes: 128-bit stores cover whole rows of a / h.
+// A block walks chunks of kPix * (256 / (Cout/4)) output pixels: taps staged in shared memory, then one thread = 4
+// consecutive output channels of kPix pixels (every weight float4 is reused for kPix pixels; taps and weights come from
+// shared memory as 128-bit broadcasts); the Cout/4 threads of a pixel are adjacent lanes, so the 128-bit stores cover
+// whole rows of a / h.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kPix = 4;
 template <int CIN>
@@ -43,75 +83,71 @@ __global__ void __launch_bounds__(256) conv_cin_fwd_kernel(const float* __restri
                                                            float* __restrict__ a, float* __restrict__ h, int B, int H, int W,
                                                            int Cout) {
   constexpr int K = 16 * CIN;
-  extern __shared__ __align__(16) float s_w[];      // [K][Cout] (transposed: the threads of a pixel read consecutive co)
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;                                  // [K][Cout] (transposed: the threads of a pixel read consecutive co)
+  float* s_tap = smem + K * Cout;                     // [chunk pixels][K]
   for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
     const int co = i / K, k = i - co * K;
     s_w[k * Cout + co] = wc[i];
   }
-  __syncthreads();
   const int OH = H >> 1, OW = W >> 1;
-  const int cg = Cout >> 2;                          // threads per pixel
-  const int ppb = blockDim.x / cg;                   // pixels per block pass
+  const int cg = Cout >> 2;                           // threads per pixel
+  const int ppb = blockDim.x / cg;                    // pixels per pass
+  const int chunk = ppb * kPix;
   const int64_t npix = static_cast<int64_t>(B) * OH * OW;
   const int c4 = (threadIdx.x % cg) * 4;
   const int pl = threadIdx.x / cg;
-  for (int64_t base = static_cast<int64_t>(blockIdx.x) * ppb * kPix; base < npix;
-       base += static_cast<int64_t>(gridDim.x) * ppb * kPix) {
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * chunk; base < npix; base += static_cast<int64_t>(gridDim.x) * chunk) {
+    __syncthreads();                                  // s_w ready / previous chunk's taps consumed
+    stage_taps<CIN>(x, s_tap, base, chunk, npix, H, W, OH, OW);
+    __syncthreads();
     float acc[kPix][4];
-    const float* xb[kPix];
-    int oh[kPix], ow[kPix];
-    bool ok[kPix];
 #pragma unroll
-    for (int j = 0; j < kPix; ++j) {
-      const int64_t p = base + pl + static_cast<int64_t>(j) * ppb;
-      ok[j] = p < npix;
-      const int64_t pp = ok[j] ? p : 0;
-      const int b = static_cast<int>(pp / (OH * OW));
-      const int r = static_cast<int>(pp - static_cast<int64_t>(b) * OH * OW);
-      oh[j] = r / OW; ow[j] = r - oh[j] * OW;
-      xb[j] = x + static_cast<int64_t>(b) * H * W * CIN;
+    for (int j = 0; j < kPix; ++j)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
-    }
+#pragma unroll 4
+    for (int k4 = 0; k4 < K / 4; ++k4) {
+      float4 w[4];
 #pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
+      for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(s_w + (4 * k4 + i) * Cout + c4);
 #pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-#pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-          const float4 w4 = *reinterpret_cast<const float4*>(s_w + ((kh * 4 + kw) * CIN + ci) * Cout + c4);
-#pragma unroll
-          for (int j = 0; j < kPix; ++j) {
-            const int iy = 2 * oh[j] - 1 + kh, ix = 2 * ow[j] - 1 + kw;
-            const float v = (ok[j] && iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(xb[j] + (iy * W + ix) * CIN + ci) : 0.f;
-            acc[j][0] += v * w4.x; acc[j][1] += v * w4.y; acc[j][2] += v * w4.z; acc[j][3] += v * w4.w;
-          }
-        }
+      for (int j = 0; j < kPix; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(s_tap + (pl + j * ppb) * K + 4 * k4);
+        acc[j][0] += t.x * w[0].x + t.y * w[1].x + t.z * w[2].x + t.w * w[3].x;
+        acc[j][1] += t.x * w[0].y + t.y * w[1].y + t.z * w[2].y + t.w * w[3].y;
+        acc[j][2] += t.x * w[0].z + t.y * w[1].z + t.z * w[2].z + t.w * w[3].z;
+        acc[j][3] += t.x * w[0].w + t.y * w[1].w + t.z * w[2].w + t.w * w[3].w;
       }
     }
 #pragma unroll
     for (int j = 0; j < kPix; ++j) {
-      if (!ok[j]) continue;
       const int64_t p = base + pl + static_cast<int64_t>(j) * ppb;
-      *reinterpret_cast<float4*>(a + p * Cout + c4) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-      *reinterpret_cast<float4*>(h + p * Cout + c4) =
-          make_float4(swish_m(acc[j][0]), swish_m(acc[j][1]), swish_m(acc[j][2]), swish_m(acc[j][3]));
+      if (p >= npix) continue;
+      __stcs(reinterpret_cast<float4*>(a + p * Cout + c4), make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]));
+      __stcs(reinterpret_cast<float4*>(h + p * Cout + c4),
+             make_float4(swish_m(acc[j][0]), swish_m(acc[j][1]), swish_m(acc[j][2]), swish_m(acc[j][3])));
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // Conv2d(CIN -> Cout), weight gradient: dWc[co][k] += sum_p da[p][co] * xcol[p][k]   (k = (kh,kw,ci); no data gradient:
-// the image is an input).  A thread owns a 4 (co) x 4 (k) patch of dWc and walks the pixels of its pixel lane; the block
-// walks a contiguous range of pixels; partial patches are summed over the lanes in shared memory and added to dWc with
-// one red.add.v4 per patch row per block.  da is read exactly once (128-bit, coalesced over the co threads).
+// the image is an input).  A thread owns a 4 (co) x 4 (k) patch of dWc; the block walks a contiguous pixel range in chunks
+// of kWgChunk pixels whose taps are staged in shared memory; the pixel lanes of the block take alternate pixels.  Per
+// pixel a thread issues one 128-bit load of da (coalesced over the co threads, read exactly once), one 128-bit shared
+// load of taps and 16 FMAs.  Partial patches are summed over the lanes in shared memory and added to dWc with one
+// red.add.v4 per patch row per block.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kWgChunk = 64;
 template <int CIN>
 __global__ void __launch_bounds__(256) conv_cin_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ da,
                                                              float* __restrict__ dwc, int B, int H, int W, int Cout,
                                                              int pix_per_block) {
-  constexpr int K = 16 * CIN, KG = K / 4;            // k groups of 4 consecutive k (same kh: 4 * CIN % 4 == 0)
-  extern __shared__ __align__(16) float s_red[];     // [lanes][Cout * K] partial patches
+  constexpr int K = 16 * CIN, KG = K / 4;            // k groups of 4 consecutive k
+  extern __shared__ __align__(16) float smem[];
+  float* s_tap = smem;                                // [kWgChunk][K]
+  float* s_red = smem + kWgChunk * K;                 // [lanes][Cout * K] partial patches
   const int OH = H >> 1, OW = W >> 1;
   const int cg = Cout >> 2;
   const int tpl = cg * KG;                           // threads per pixel lane
@@ -119,8 +155,6 @@ __global__ void __launch_bounds__(256) conv_cin_wgrad_kernel(const float* __rest
   const int lane_id = threadIdx.x / tpl, t = threadIdx.x - lane_id * tpl;
   const bool active = lane_id < lanes;
   const int c4 = (t % cg) * 4, kq = t / cg;          // my patch: co [c4, c4+4) x k [4 kq, 4 kq + 4)
-  const int kh = (4 * kq) / (4 * CIN);               // all four k share kh
-  const int r0 = (4 * kq) - kh * 4 * CIN;            // offset inside the (kw, ci) row segment of 4 * CIN floats
   const int64_t npix = static_cast<int64_t>(B) * OH * OW;
   const int64_t p_begin = static_cast<int64_t>(blockIdx.x) * pix_per_block;
   const int64_t p_end = p_begin + pix_per_block < npix ? p_begin + pix_per_block : npix;
@@ -129,26 +163,24 @@ __global__ void __launch_bounds__(256) conv_cin_wgrad_kernel(const float* __rest
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
-  if (active) {
-    for (int64_t p = p_begin + lane_id; p < p_end; p += lanes) {
-      const int b = static_cast<int>(p / (OH * OW));
-      const int r = static_cast<int>(p - static_cast<int64_t>(b) * OH * OW);
-      const int oh = r / OW, ow = r - oh * OW;
-      const float4 d4 = __ldcs(reinterpret_cast<const float4*>(da + p * Cout + c4));
-      const int iy = 2 * oh - 1 + kh;
-      float xv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = r0 + i;                        // (kw, ci) flat
-        const int ix = 2 * ow - 1 + rr / CIN;
-        xv[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W)
-                    ? __ldg(x + ((static_cast<int64_t>(b) * H + iy) * W + ix) * CIN + (rr % CIN)) : 0.f;
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[i][0] += xv[i] * d4.x; acc[i][1] += xv[i] * d4.y; acc[i][2] += xv[i] * d4.z; acc[i][3] += xv[i] * d4.w;
+  for (int64_t c0 = p_begin; c0 < p_end; c0 += kWgChunk) {
+    const int n = static_cast<int>(p_end - c0 < kWgChunk ? p_end - c0 : kWgChunk);
+    __syncthreads();
+    stage_taps<CIN>(x, s_tap, c0, n, npix, H, W, OH, OW);
+    __syncthreads();
+    if (active) {
+#pragma unroll 4
+      for (int pi = lane_id; pi < n; pi += lanes) {
+        const float4 d4 = __ldcs(reinterpret_cast<const float4*>(da + (c0 + pi) * Cout + c4));
+        const float4 x4 = *reinterpret_cast<const float4*>(s_tap + pi * K + 4 * kq);
+        acc[0][0] += x4.x * d4.x; acc[0][1] += x4.x * d4.y; acc[0][2] += x4.x * d4.z; acc[0][3] += x4.x * d4.w;
+        acc[1][0] += x4.y * d4.x; acc[1][1] += x4.y * d4.y; acc[1][2] += x4.y * d4.z; acc[1][3] += x4.y * d4.w;
+        acc[2][0] += x4.z * d4.x; acc[2][1] += x4.z * d4.y; acc[2][2] += x4.z * d4.z; acc[2][3] += x4.z * d4.w;
+        acc[3][0] += x4.w * d4.x; acc[3][1] += x4.w * d4.y; acc[3][2] += x4.w * d4.z; acc[3][3] += x4.w * d4.w;
       }
     }
+  }
+  if (active) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)   // s_red[lane][co][k]
 #pragma unroll
@@ -156,70 +188,107 @@ __global__ void __launch_bounds__(256) conv_cin_wgrad_kernel(const float* __rest
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < Cout * KG; idx += blockDim.x) {   // one float4 of dWc[co][4 kq ..]
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int l = 0; l < lanes; ++l) {
       const float4 v = *reinterpret_cast<const float4*>(s_red + static_cast<size_t>(l) * Cout * K + idx * 4);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
     }
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dwc + idx * 4), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dwc + idx * 4), "f"(s4.x), "f"(s4.y), "f"(s4.z), "f"(s4.w)
                  : "memory");
+  }
+}
+
+// Cooperative, fully coalesced copy of `rows` activation rows of Cin floats (global, contiguous) into shared memory with
+// a row stride of Cin + 4 floats (conflict-free 128-bit row reads by one thread per row), up to 8 loads per thread in
+// flight.  rows_valid < rows: the remaining rows are zero-filled.
+__device__ __forceinline__ void stage_rows_padded(const float* __restrict__ src, float* dst, int rows, int rows_valid, int Cin,
+                                                  int ld) {
+  const int c4n = Cin >> 2, ld4 = ld >> 2;
+  const int total = rows * c4n;
+  for (int i0 = 0; i0 < total; i0 += 8 * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x + threadIdx.x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < total && i / c4n < rows_valid) v[u] = __ldcs(reinterpret_cast<const float4*>(src) + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int i = i0 + u * blockDim.x + threadIdx.x;
+      if (i < total) {
+        const int r = i / c4n, c = i - r * c4n;
+        reinterpret_cast<float4*>(dst)[r * ld4 + c] = v[u];
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // ConvTranspose2d(Cin -> COUT), forward: out[b, oy, ox, co] = sum over the <= 2 x 2 taps (iy, kh), (ix, kw) with
 // oy = 2 iy - 1 + kh, ox = 2 ix - 1 + kw of  sum_ci hin[b, iy, ix, ci] * Wt[(kh,kw,co)][ci].
-// A block takes `tr` input rows of one image (+ one halo row on each side): phase 1, one thread per input pixel, the
-// pixel's Cin channels streamed once (128-bit) against the 16 * COUT weight rows held in shared memory -> the pixel's
-// "cols" vector in shared memory; phase 2 gathers the <= 4 contributions of every output pixel of the tile and writes
-// whole output rows.  The wide activation is read once (the halo rows twice); nothing else touches HBM.
+// A block takes `tr` input rows of one image (+ one halo row on each side): the rows are copied to shared memory fully
+// coalesced (the first version let every thread stream its own 256-byte row from global memory: 16 bytes per lane per
+// request, L1-bound at 85 %); phase 1, one thread per (pixel pair, half of the 16 * COUT weight rows): a weight float4
+// read from shared memory serves two pixels; the pixels' "cols" vectors go to shared memory; phase 2 gathers the <= 4
+// contributions of every output pixel of the tile and writes whole output rows.
 // ------------------------------------------------------------------------------------------------------------------
 template <int COUT>
 __global__ void __launch_bounds__(256) convT_cout_fwd_kernel(const float* __restrict__ hin, const float* __restrict__ wt,
                                                              float* __restrict__ out, int B, int IH, int IW, int Cin,
                                                              int tr, int tiles_per_img) {
-  constexpr int KC = 16 * COUT;
+  constexpr int KC = 16 * COUT, KH = KC / 2;          // a task computes KH of the KC cols values of two pixels
   extern __shared__ __align__(16) float smem[];
+  const int c4n = Cin >> 2, ldh = Cin + 4;
+  const int npx_max = (tr + 2) * IW;
   float* s_w = smem;                                  // [KC][Cin]
-  float* s_cols = smem + KC * Cin;                    // [(tr + 2) * IW][KC + 1]  (+1: conflict-free column gathers)
+  float* s_cols = s_w + KC * Cin;                     // [npx_max][KC + 1]  (+1: conflict-free column gathers)
+  float* s_h = s_cols + ((npx_max * (KC + 1) + 3) & ~3);   // [npx_max][Cin + 4]
   for (int i = threadIdx.x; i < KC * Cin / 4; i += blockDim.x)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
-  const int c4n = Cin >> 2;
   const int OW = 2 * IW;
   for (int tile = blockIdx.x; tile < B * tiles_per_img; tile += gridDim.x) {
     const int b = tile / tiles_per_img;
     const int row0 = (tile - b * tiles_per_img) * tr;          // first owned input row
     const int rows = min(tr, IH - row0);
-    const int lo = row0 - 1;                                    // first staged input row (may be -1: zero)
+    const int lo = row0 - 1;                                    // first staged input row (may be -1)
+    const int r_first = lo < 0 ? 0 : lo;                        // staged rows that exist: [r_first, r_last)
+    const int r_last = min(IH, row0 + rows + 1);
     const int npx = (rows + 2) * IW;
-    __syncthreads();                                            // s_w ready / previous tile's s_cols consumed
-    // ---- phase 1: cols of the staged pixels
-    for (int px = threadIdx.x; px < npx; px += blockDim.x) {
-      const int ry = px / IW, ix = px - ry * IW;
-      const int iy = lo + ry;
-      float cols[KC];
+    __syncthreads();                                            // s_w ready / previous tile consumed
+    stage_rows_padded(hin + ((static_cast<int64_t>(b) * IH + r_first) * IW) * Cin, s_h + (r_first - lo) * IW * ldh,
+                      (r_last - r_first) * IW, (r_last - r_first) * IW, Cin, ldh);
+    __syncthreads();
+    // ---- phase 1: cols of the staged pixels; task = (pixel pair, half of the weight rows)
+    const int npair = (npx + 1) >> 1;
+    for (int task = threadIdx.x; task < 2 * npair; task += blockDim.x) {
+      const int pair = task >> 1, khalf = task & 1;
+      const int px0 = 2 * pair, px1 = px0 + 1;
+      const int iy0 = lo + px0 / IW, iy1 = lo + px1 / IW;
+      const bool ok0 = iy0 >= 0 && iy0 < IH, ok1 = px1 < npx && iy1 >= 0 && iy1 < IH;
+      float c0[KH], c1[KH];
 #pragma unroll
-      for (int k = 0; k < KC; ++k) cols[k] = 0.f;
-      if (iy >= 0 && iy < IH) {
-        const float4* src = reinterpret_cast<const float4*>(hin + ((static_cast<int64_t>(b) * IH + iy) * IW + ix) * Cin);
-        for (int c = 0; c < c4n; c += 4) {                     // 4 x 128-bit loads in flight
-          float4 v[4];
+      for (int k = 0; k < KH; ++k) { c0[k] = 0.f; c1[k] = 0.f; }
+      if (ok0 || ok1) {
+        const float* h0 = s_h + px0 * ldh;
+        const float* h1 = s_h + (ok1 ? px1 : px0) * ldh;
+        const float* wb = s_w + khalf * KH * Cin;
+        for (int c = 0; c < c4n; ++c) {
+          const float4 v0 = *reinterpret_cast<const float4*>(h0 + 4 * c);
+          const float4 v1 = *reinterpret_cast<const float4*>(h1 + 4 * c);
 #pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = (c + u < c4n) ? __ldcs(src + c + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (c + u < c4n) {
-#pragma unroll
-              for (int k = 0; k < KC; ++k) {
-                const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cin + (c + u) * 4);   // warp-uniform: broadcast
-                cols[k] += v[u].x * w4.x + v[u].y * w4.y + v[u].z * w4.z + v[u].w * w4.w;
-              }
-            }
+          for (int k = 0; k < KH; ++k) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wb + k * Cin + 4 * c);
+            c0[k] += v0.x * w4.x + v0.y * w4.y + v0.z * w4.z + v0.w * w4.w;
+            c1[k] += v1.x * w4.x + v1.y * w4.y + v1.z * w4.z + v1.w * w4.w;
           }
         }
       }
 #pragma unroll
-      for (int k = 0; k < KC; ++k) s_cols[px * (KC + 1) + k] = cols[k];
+      for (int k = 0; k < KH; ++k) {
+        s_cols[px0 * (KC + 1) + khalf * KH + k] = ok0 ? c0[k] : 0.f;
+        if (px1 < npx) s_cols[px1 * (KC + 1) + khalf * KH + k] = ok1 ? c1[k] : 0.f;
+      }
     }
     __syncthreads();
     // ---- phase 2: output rows [2 row0, 2 (row0 + rows)) of image b
@@ -229,7 +298,7 @@ __global__ void __launch_bounds__(256) convT_cout_fwd_kernel(const float* __rest
       const int rem = o - oyl * (OW * COUT);
       const int ox = rem / COUT, co = rem - ox * COUT;
       const int oy = 2 * row0 + oyl;
-      float s = 0.f;
+      float sum = 0.f;
 #pragma unroll
       for (int a2 = 0; a2 < 2; ++a2) {
         const int kh = ((oy + 1) & 1) + 2 * a2;                 // kh = (oy + 1) mod 2, + 2
@@ -240,10 +309,10 @@ __global__ void __launch_bounds__(256) convT_cout_fwd_kernel(const float* __rest
           const int kw = ((ox + 1) & 1) + 2 * b2;
           const int ix = (ox + 1 - kw) >> 1;
           if (ix < 0 || ix >= IW) continue;
-          s += s_cols[((iy - lo) * IW + ix) * (KC + 1) + (kh * 4 + kw) * COUT + co];
+          sum += s_cols[((iy - lo) * IW + ix) * (KC + 1) + (kh * 4 + kw) * COUT + co];
         }
       }
-      out[((static_cast<int64_t>(b) * 2 * IH + oy) * OW) * COUT + rem] = s;
+      out[((static_cast<int64_t>(b) * 2 * IH + oy) * OW) * COUT + rem] = sum;
     }
   }
 }
@@ -253,27 +322,29 @@ __global__ void __launch_bounds__(256) convT_cout_fwd_kernel(const float* __rest
 //   dcols[p][(kh,kw,co)] = dout[b, 2iy-1+kh, 2ix-1+kw, co]               (a gather: never materialised in HBM)
 //   d hin[p][ci] = (sum_k dcols[p][k] Wt[k][ci]) * swish'(ain[p][ci])    (ain = pre-activation of the layer below)
 //   dWt[k][ci]  += sum_p dcols[p][k] * hin[p][ci]
-// Persistent blocks: a block walks tiles of `tr` input rows; phase 1 (one thread per input pixel) gathers dcols into
-// registers + shared memory and writes d hin; phase 2 (a thread owns a 4 (k) x 4 (ci) patch of dWt, pixel lanes in
-// parallel) accumulates the weight gradient in REGISTERS across all tiles of the block; one red.add.v4 per patch row per
-// block at the end.  hin, ain are read once, d hin written once.
+// Persistent blocks walk tiles of `tr` input rows.  The tile's ain rows are copied to shared memory coalesced; phase 1 (one
+// thread per (pixel, half of the channels)) gathers dcols, overwrites the staged ain rows with d hin IN PLACE, and the
+// block then streams them out coalesced; phase 2 (a thread owns a 4 (k) x 4 (ci) patch of dWt, pixel lanes in parallel,
+// hin read coalesced from global memory exactly once) accumulates the weight gradient in REGISTERS across all tiles of
+// the block; one red.add.v4 per patch row per block at the end.
 // ------------------------------------------------------------------------------------------------------------------
 template <int COUT>
-__global__ void __launch_bounds__(256) convT_cout_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ hin,
+__global__ void __launch_bounds__(256, COUT == 1 ? 3 : 2) convT_cout_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ hin,
                                                              const float* __restrict__ ain, const float* __restrict__ wt,
                                                              float* __restrict__ dhin, float* __restrict__ dwt, int B, int IH,
                                                              int IW, int Cin, int tr, int tiles_per_img) {
   constexpr int KC = 16 * COUT, KG = KC / 4;
   extern __shared__ __align__(16) float smem[];
+  const int c4n = Cin >> 2, ldh = Cin + 8;            // (+8: two threads per row, alternate float4s: conflict-free)
+  const int npx_max = tr * IW;
+  const int OW = 2 * IW, OH = 2 * IH;
   float* s_w = smem;                                  // [KC][Cin]
-  float* s_dc = smem + KC * Cin;                      // [KC][tr * IW]   dcols of the tile, k-major: conflict-free
-  const int npx_max = tr * IW;                        //                 writes (lane = pixel), broadcast reads in phase 2
-  float* s_do = s_dc + tr * IW * KC;                  // [(2 tr + 2) * 2 IW * COUT]  dout rows 2 row0 - 1 .. 2 (row0 + rows)
-  float* s_red = s_do;                                // (reused at the end) [lanes][KC * Cin]
+  float* s_dc = s_w + KC * Cin;                       // [KC][npx_max]  dcols of the tile, k-major
+  float* s_do = s_dc + KC * npx_max;                  // [(2 tr + 2) * OW * COUT]  dout rows 2 row0 - 1 .. 2 (row0 + rows)
+  float* s_a = s_do + (((2 * tr + 2) * OW * COUT + 3) & ~3);   // [npx_max][Cin + 4]  ain rows -> d hin rows (in place)
+  float* s_red = s_a;                                 // (reused at the very end) [lanes][KC * Cin]
   for (int i = threadIdx.x; i < KC * Cin / 4; i += blockDim.x)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
-  const int c4n = Cin >> 2;
-  const int OW = 2 * IW, OH = 2 * IH;
   const int tpl = c4n * KG;                           // threads per pixel lane in phase 2
   const int lanes = blockDim.x / tpl;
   const int lane_id = threadIdx.x / tpl, t2 = threadIdx.x - lane_id * tpl;
@@ -290,15 +361,18 @@ __global__ void __launch_bounds__(256) convT_cout_bwd_kernel(const float* __rest
     const int npx = rows * IW;
     const int oy_lo = 2 * row0 - 1;                   // first staged dout row
     const int nrows_o = 2 * rows + 2;
-    __syncthreads();                                  // previous tile fully consumed (s_dc, s_do)
+    const int64_t p0 = (static_cast<int64_t>(b) * IH + row0) * IW;   // first pixel (row of hin / ain / dhin) of the tile
+    __syncthreads();                                  // previous tile fully consumed
     for (int i = threadIdx.x; i < nrows_o * OW * COUT; i += blockDim.x) {
       const int ry = i / (OW * COUT);
       const int oy = oy_lo + ry;
       s_do[i] = (oy >= 0 && oy < OH) ? __ldg(dout + (static_cast<int64_t>(b) * OH + oy) * OW * COUT + (i - ry * OW * COUT)) : 0.f;
     }
+    stage_rows_padded(ain + p0 * Cin, s_a, npx, npx, Cin, ldh);
     __syncthreads();
-    // ---- phase 1: per input pixel, dcols gather, d hin
-    for (int px = threadIdx.x; px < npx; px += blockDim.x) {
+    // ---- phase 1: task = (pixel, half of the channels): dcols gather (+ publish to s_dc), d hin in place
+    for (int task = threadIdx.x; task < 2 * npx; task += blockDim.x) {
+      const int px = task >> 1, chalf = task & 1;
       const int ryl = px / IW, ix = px - ryl * IW;
       float dc[KC];
 #pragma unroll
@@ -312,34 +386,37 @@ __global__ void __launch_bounds__(256) convT_cout_bwd_kernel(const float* __rest
             dc[(kh * 4 + kw) * COUT + co] = (ox >= 0 && ox < OW) ? s_do[(ry * OW + ox) * COUT + co] : 0.f;
         }
       }
+      if (chalf == 0) {
 #pragma unroll
-      for (int k = 0; k < KC; ++k) s_dc[k * npx_max + px] = dc[k];
-      const int64_t p = (static_cast<int64_t>(b) * IH + row0 + ryl) * IW + ix;
-      const float4* asrc = reinterpret_cast<const float4*>(ain + p * Cin);
-      float4* dst = reinterpret_cast<float4*>(dhin + p * Cin);
-      for (int c = 0; c < c4n; c += 4) {
-        float4 av[4];
+        for (int k = 0; k < KC; ++k) s_dc[k * npx_max + px] = dc[k];
+      }
+      float* arow = s_a + px * ldh;
+      for (int c = chalf; c < c4n; c += 2) {          // alternate float4s of the row
+        const float4 av = *reinterpret_cast<const float4*>(arow + 4 * c);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) av[u] = (c + u < c4n) ? __ldcs(asrc + c + u) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (c + u < c4n) {
-            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-              const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cin + (c + u) * 4);     // broadcast
-              g.x += dc[k] * w4.x; g.y += dc[k] * w4.y; g.z += dc[k] * w4.z; g.w += dc[k] * w4.w;
-            }
-            g.x *= dswish_m(av[u].x); g.y *= dswish_m(av[u].y); g.z *= dswish_m(av[u].z); g.w *= dswish_m(av[u].w);
-            __stcs(dst + c + u, g);
-          }
+        for (int k = 0; k < KC; ++k) {
+          const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cin + 4 * c);     // (2 addresses per warp)
+          g.x += dc[k] * w4.x; g.y += dc[k] * w4.y; g.z += dc[k] * w4.z; g.w += dc[k] * w4.w;
         }
+        g.x *= dswish_m(av.x); g.y *= dswish_m(av.y); g.z *= dswish_m(av.z); g.w *= dswish_m(av.w);
+        *reinterpret_cast<float4*>(arow + 4 * c) = g;
       }
     }
     __syncthreads();
+    // ---- d hin rows out, coalesced
+    {
+      const int total = npx * c4n, ld4 = ldh >> 2;
+      float4* dst = reinterpret_cast<float4*>(dhin + p0 * Cin);
+      for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = i / c4n, c = i - r * c4n;
+        __stcs(dst + i, reinterpret_cast<const float4*>(s_a)[r * ld4 + c]);
+      }
+    }
     // ---- phase 2: dWt patch += sum over the tile's pixels of dcols[p][k] * hin[p][ci]
     if (lane_id < lanes) {
-      const float* hb = hin + ((static_cast<int64_t>(b) * IH + row0) * IW) * Cin + ci4;
+      const float* hb = hin + p0 * Cin + ci4;
+#pragma unroll 4
       for (int px = lane_id; px < npx; px += lanes) {
         const float4 h4 = __ldcs(reinterpret_cast<const float4*>(hb + static_cast<int64_t>(px) * Cin));
         const float4 d4 = make_float4(s_dc[(4 * kq) * npx_max + px], s_dc[(4 * kq + 1) * npx_max + px],
@@ -361,12 +438,12 @@ __global__ void __launch_bounds__(256) convT_cout_bwd_kernel(const float* __rest
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < KC * c4n; idx += blockDim.x) {
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int l = 0; l < lanes; ++l) {
       const float4 v = *reinterpret_cast<const float4*>(s_red + static_cast<size_t>(l) * KC * Cin + idx * 4);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      s4.x += v.x; s4.y += v.y; s4.z += v.z; s4.w += v.w;
     }
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dwt + idx * 4), "f"(s.x), "f"(s.y), "f"(s.z), "f"(s.w)
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dwt + idx * 4), "f"(s4.x), "f"(s4.y), "f"(s4.z), "f"(s4.w)
                  : "memory");
   }
 }
@@ -408,7 +485,7 @@ extern "C" int mvae_conv_k4s2p1_cin_fwd(const float* x, const float* wc, float* 
   int64_t blocks = (npix + ppb - 1) / ppb;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  const size_t smem = static_cast<size_t>(16) * Cin * Cout * sizeof(float);
+  const size_t smem = static_cast<size_t>(16) * Cin * (Cout + ppb) * sizeof(float);    // weights + one chunk of taps
   if (Cin == 1) conv_cin_fwd_kernel<1><<<static_cast<unsigned>(blocks), 256, smem, st>>>(x, wc, a, h, B, H, W, Cout);
   else conv_cin_fwd_kernel<3><<<static_cast<unsigned>(blocks), 256, smem, st>>>(x, wc, a, h, B, H, W, Cout);
   count_launch();
@@ -431,7 +508,7 @@ extern "C" int mvae_conv_k4s2p1_cin_wgrad(const float* x, const float* da, float
   if (per < 64) per = 64;
   blocks = (npix + per - 1) / per;
   const int lanes = 256 / tpl;
-  const size_t smem = static_cast<size_t>(lanes) * Cout * 16 * Cin * sizeof(float);
+  const size_t smem = (static_cast<size_t>(lanes) * Cout + kWgChunk) * 16 * Cin * sizeof(float);
   int rc;
   if (Cin == 1) {
     if ((rc = set_smem(conv_cin_wgrad_kernel<1>, smem, "conv_k4s2p1_cin_wgrad"))) return rc;
@@ -455,7 +532,8 @@ extern "C" int mvae_convt_k4s2p1_cout_fwd(const float* hin, const float* wt, flo
   const int tr = tile_rows(IH, IW);
   const int tiles_per_img = (IH + tr - 1) / tr;
   const int KC = 16 * Cout;
-  const size_t smem = (static_cast<size_t>(KC) * Cin + static_cast<size_t>(tr + 2) * IW * (KC + 1)) * sizeof(float);
+  const size_t npx_max = static_cast<size_t>(tr + 2) * IW;
+  const size_t smem = (static_cast<size_t>(KC) * Cin + ((npx_max * (KC + 1) + 3) & ~size_t(3)) + npx_max * (Cin + 4)) * sizeof(float);
   int64_t blocks = static_cast<int64_t>(B) * tiles_per_img;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
@@ -487,10 +565,11 @@ extern "C" int mvae_convt_k4s2p1_cout_bwd(const float* dout, const float* hin, c
   const int tr = tile_rows(IH, IW);
   const int tiles_per_img = (IH + tr - 1) / tr;
   const int lanes = 256 / tpl;
-  size_t tail = static_cast<size_t>(2 * tr + 2) * 2 * IW * Cout;               // staged dout rows ...
+  const size_t s_do = (static_cast<size_t>(2 * tr + 2) * 2 * IW * Cout + 3) & ~size_t(3);      // staged dout rows
+  size_t tail = static_cast<size_t>(tr) * IW * (Cin + 8);                       // staged ain rows -> d hin rows ...
   const size_t red = static_cast<size_t>(lanes) * KC * Cin;                   // ... reused for the final lane reduction
   if (red > tail) tail = red;
-  const size_t smem = (static_cast<size_t>(KC) * Cin + static_cast<size_t>(tr) * IW * KC + tail) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(KC) * Cin + static_cast<size_t>(tr) * IW * KC + s_do + tail) * sizeof(float);
   int64_t blocks = static_cast<int64_t>(B) * tiles_per_img;
   int rc;
   if (Cout == 1) { if ((rc = set_smem(convT_cout_bwd_kernel<1>, smem, "convT_k4s2p1_cout_bwd"))) return rc; }

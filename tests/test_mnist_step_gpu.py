@@ -103,8 +103,10 @@ def test_graph_replay_equals_eager_and_philox_noise_changes():
         la = a.step(image, text, annealing_factor=0.1 * (it + 1), noise=noise)
         lb = b.step(image, text, annealing_factor=0.1 * (it + 1), noise=noise)
         assert abs(la - lb) <= 1e-6 * abs(la), (it, la, lb)      # same kernels; only atomics order differs
+    # (Adam turns rounding-level differences of near-zero gradients -- the order of the fp32 atomics differs between the
+    # two runs -- into differences of a fraction of lr = 1e-3 per step; 3 steps here)
     for k in a.params:
-        assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-5, k
+        assert (a.params[k] - b.params[k]).abs().max().item() <= 5e-5, k
     # Philox path under graph replay: fresh noise every step, loss finite and decreasing over a few steps
     l0 = b.step(image, text, annealing_factor=1.0)
     n0 = b.noise.clone()
