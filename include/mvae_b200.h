@@ -45,6 +45,23 @@ const char* mvae_last_error(void);
 uint64_t mvae_launch_count(void);
 int mvae_device_sm_count(void);
 
+/* Implicit-GEMM convolution operand: instead of a matrix, operand A (or B) of mvae_gemm_desc may be the im2col VIEW of an
+ * NHWC activation tensor [N, H, W, C] -- rows = output pixels (n, p, q) in raster order, columns k = (th, tw, c) =
+ * filter tap x input channel -- fetched tile by tile with TMA im2col-mode loads (zero fill at the padding), never
+ * materialised in HBM.  Replaces the im2col buffers in front of the conv GEMMs (Conv2d forward / weight gradient,
+ * ConvTranspose2d data / weight gradient: fashionmnist/model.py:80-82,112-113; celeba/model.py:78-87,117-125).
+ *   output pixel (p, q) reads input (lower_h + p*stride + th, lower_w + q*stride + tw);  k4 s2 p1: lower = -1, taps 4x4
+ *   OH = (H + upper_h - lower_h - 1) / stride + 1 with upper = pad - (taps - 1)    (k4 s2 p1: upper = -2)
+ *   C % 32 == 0; C == 0 means "plain matrix operand".  The operand pointer (A / B) is the tensor's base address.
+ * As K-major A: M = N*OH*OW, K = taps_h*taps_w*C.  As MN-major operand (weight gradients: a_mn_major / b_mn_major = 1):
+ * the reduction runs over the pixels, the M (or N) index is (th, tw, c).                                              */
+typedef struct {
+  int32_t N, H, W, C;
+  int32_t lower_h, lower_w, upper_h, upper_w;
+  int32_t stride;
+  int32_t taps_h, taps_w;
+} mvae_conv_view;
+
 /* One GEMM problem  C[M,N] = A[M,K] * B[N,K]^T  with a fused epilogue.
  *   a_mn_major = 0: A stored [M][K] (K contiguous, lda = row stride)
  *   a_mn_major = 1: A stored [K][M] (M contiguous, lda = row stride)   -- same for B with N.
@@ -69,6 +86,8 @@ typedef struct {
                                   /* the full epilogue (bias / Swish / Swish' / colsum) -- for layers with fewer output tiles  */
                                   /* than SMs (small per-GPU batches, K = 6272 classifier layers).  mvae_gemm_chain only;     */
                                   /* N % 4 == 0; one scratch per problem of a launch.                                          */
+  mvae_conv_view a_view;          /* a_view.C > 0: A is the im2col view of the NHWC tensor at `A` (lda ignored)                */
+  mvae_conv_view b_view;          /* b_view.C > 0: B likewise (MN-major only: the weight-gradient form)                       */
 } mvae_gemm_desc;
 
 /* Launch up to MVAE_GEMM_MAX_BATCH independent problems in ONE persistent kernel. */

@@ -23,6 +23,12 @@ class MvaeError(RuntimeError):
     pass
 
 
+class ConvView(C.Structure):
+    _fields_ = [("N", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32),
+                ("lower_h", C.c_int32), ("lower_w", C.c_int32), ("upper_h", C.c_int32), ("upper_w", C.c_int32),
+                ("stride", C.c_int32), ("taps_h", C.c_int32), ("taps_w", C.c_int32)]
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("lda", C.c_int64), ("a_mn_major", C.c_int32),
@@ -35,6 +41,7 @@ class GemmDesc(C.Structure):
         ("colsum", C.c_void_p),
         ("epilogue", C.c_int32), ("split_k", C.c_int32), ("accumulate", C.c_int32),
         ("split_ws", C.c_void_p),
+        ("a_view", ConvView), ("b_view", ConvView),
     ]
 
 

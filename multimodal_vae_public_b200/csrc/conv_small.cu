@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) conv_cin_fwd_kernel(const float* __restri
 // load of taps and 16 FMAs.  Partial patches are summed over the lanes in shared memory and added to dWc with one
 // red.add.v4 per patch row per block.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kWgChunk = 64;
+constexpr int kWgChunk = 256;
 template <int CIN>
 __global__ void __launch_bounds__(256) conv_cin_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ da,
                                                              float* __restrict__ dwc, int B, int H, int W, int Cout,
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) conv_cin_wgrad_kernel(const float* __rest
     stage_taps<CIN>(x, s_tap, c0, n, npix, H, W, OH, OW);
     __syncthreads();
     if (active) {
-#pragma unroll 4
+#pragma unroll 8
       for (int pi = lane_id; pi < n; pi += lanes) {
         const float4 d4 = __ldcs(reinterpret_cast<const float4*>(da + (c0 + pi) * Cout + c4));
         const float4 x4 = *reinterpret_cast<const float4*>(s_tap + pi * K + 4 * kq);
@@ -227,68 +227,60 @@ __device__ __forceinline__ void stage_rows_padded(const float* __restrict__ src,
 // ------------------------------------------------------------------------------------------------------------------
 // ConvTranspose2d(Cin -> COUT), forward: out[b, oy, ox, co] = sum over the <= 2 x 2 taps (iy, kh), (ix, kw) with
 // oy = 2 iy - 1 + kh, ox = 2 ix - 1 + kw of  sum_ci hin[b, iy, ix, ci] * Wt[(kh,kw,co)][ci].
-// A block takes `tr` input rows of one image (+ one halo row on each side): the rows are copied to shared memory fully
-// coalesced (the first version let every thread stream its own 256-byte row from global memory: 16 bytes per lane per
-// request, L1-bound at 85 %); phase 1, one thread per (pixel pair, half of the 16 * COUT weight rows): a weight float4
-// read from shared memory serves two pixels; the pixels' "cols" vectors go to shared memory; phase 2 gathers the <= 4
-// contributions of every output pixel of the tile and writes whole output rows.
+// A block takes `tr` input rows of one image (+ one halo row on each side): phase 1, one thread per input pixel, the
+// pixel's Cin channels streamed once (128-bit) against the 16 * COUT weight rows held in shared memory -> the pixel's
+// "cols" vector in shared memory; phase 2 gathers the <= 4 contributions of every output pixel of the tile and writes
+// whole output rows.  The wide activation is read once (the halo rows twice); nothing else touches HBM.
+// (Measured, FashionMNIST B = 4096: 235 us, L1-bound (every lane streams its own 256-byte row).  A variant that staged the
+// rows coalesced through shared memory and register-blocked over pixel pairs issued 45 % more instructions and took
+// 304 us; the im2col-free tensor-core route it replaces took 322 us.  profiles/r02_conv_small_ncu.txt)
 // ------------------------------------------------------------------------------------------------------------------
 template <int COUT>
 __global__ void __launch_bounds__(256) convT_cout_fwd_kernel(const float* __restrict__ hin, const float* __restrict__ wt,
                                                              float* __restrict__ out, int B, int IH, int IW, int Cin,
                                                              int tr, int tiles_per_img) {
-  constexpr int KC = 16 * COUT, KH = KC / 2;          // a task computes KH of the KC cols values of two pixels
+  constexpr int KC = 16 * COUT;
   extern __shared__ __align__(16) float smem[];
-  const int c4n = Cin >> 2, ldh = Cin + 4;
-  const int npx_max = (tr + 2) * IW;
   float* s_w = smem;                                  // [KC][Cin]
-  float* s_cols = s_w + KC * Cin;                     // [npx_max][KC + 1]  (+1: conflict-free column gathers)
-  float* s_h = s_cols + ((npx_max * (KC + 1) + 3) & ~3);   // [npx_max][Cin + 4]
+  float* s_cols = smem + KC * Cin;                    // [(tr + 2) * IW][KC + 1]  (+1: conflict-free column gathers)
   for (int i = threadIdx.x; i < KC * Cin / 4; i += blockDim.x)
     reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(wt) + i);
+  const int c4n = Cin >> 2;
   const int OW = 2 * IW;
   for (int tile = blockIdx.x; tile < B * tiles_per_img; tile += gridDim.x) {
     const int b = tile / tiles_per_img;
     const int row0 = (tile - b * tiles_per_img) * tr;          // first owned input row
     const int rows = min(tr, IH - row0);
-    const int lo = row0 - 1;                                    // first staged input row (may be -1)
-    const int r_first = lo < 0 ? 0 : lo;                        // staged rows that exist: [r_first, r_last)
-    const int r_last = min(IH, row0 + rows + 1);
+    const int lo = row0 - 1;                                    // first staged input row (may be -1: zero)
     const int npx = (rows + 2) * IW;
-    __syncthreads();                                            // s_w ready / previous tile consumed
-    stage_rows_padded(hin + ((static_cast<int64_t>(b) * IH + r_first) * IW) * Cin, s_h + (r_first - lo) * IW * ldh,
-                      (r_last - r_first) * IW, (r_last - r_first) * IW, Cin, ldh);
-    __syncthreads();
-    // ---- phase 1: cols of the staged pixels; task = (pixel pair, half of the weight rows)
-    const int npair = (npx + 1) >> 1;
-    for (int task = threadIdx.x; task < 2 * npair; task += blockDim.x) {
-      const int pair = task >> 1, khalf = task & 1;
-      const int px0 = 2 * pair, px1 = px0 + 1;
-      const int iy0 = lo + px0 / IW, iy1 = lo + px1 / IW;
-      const bool ok0 = iy0 >= 0 && iy0 < IH, ok1 = px1 < npx && iy1 >= 0 && iy1 < IH;
-      float c0[KH], c1[KH];
+    __syncthreads();                                            // s_w ready / previous tile's s_cols consumed
+    // ---- phase 1: cols of the staged pixels
+    for (int px = threadIdx.x; px < npx; px += blockDim.x) {
+      const int ry = px / IW, ix = px - ry * IW;
+      const int iy = lo + ry;
+      float cols[KC];
 #pragma unroll
-      for (int k = 0; k < KH; ++k) { c0[k] = 0.f; c1[k] = 0.f; }
-      if (ok0 || ok1) {
-        const float* h0 = s_h + px0 * ldh;
-        const float* h1 = s_h + (ok1 ? px1 : px0) * ldh;
-        const float* wb = s_w + khalf * KH * Cin;
-        for (int c = 0; c < c4n; ++c) {
-          const float4 v0 = *reinterpret_cast<const float4*>(h0 + 4 * c);
-          const float4 v1 = *reinterpret_cast<const float4*>(h1 + 4 * c);
+      for (int k = 0; k < KC; ++k) cols[k] = 0.f;
+      if (iy >= 0 && iy < IH) {
+        const float4* src = reinterpret_cast<const float4*>(hin + ((static_cast<int64_t>(b) * IH + iy) * IW + ix) * Cin);
+        for (int c = 0; c < c4n; c += 4) {                     // 4 x 128-bit loads in flight
+          float4 v[4];
 #pragma unroll
-          for (int k = 0; k < KH; ++k) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wb + k * Cin + 4 * c);
-            c0[k] += v0.x * w4.x + v0.y * w4.y + v0.z * w4.z + v0.w * w4.w;
-            c1[k] += v1.x * w4.x + v1.y * w4.y + v1.z * w4.z + v1.w * w4.w;
+          for (int u = 0; u < 4; ++u) v[u] = (c + u < c4n) ? __ldcs(src + c + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c + u < c4n) {
+#pragma unroll
+              for (int k = 0; k < KC; ++k) {
+                const float4 w4 = *reinterpret_cast<const float4*>(s_w + k * Cin + (c + u) * 4);   // warp-uniform: broadcast
+                cols[k] += v[u].x * w4.x + v[u].y * w4.y + v[u].z * w4.z + v[u].w * w4.w;
+              }
+            }
           }
         }
       }
 #pragma unroll
-      for (int k = 0; k < KH; ++k) {
-        s_cols[px0 * (KC + 1) + khalf * KH + k] = ok0 ? c0[k] : 0.f;
-        if (px1 < npx) s_cols[px1 * (KC + 1) + khalf * KH + k] = ok1 ? c1[k] : 0.f;
-      }
+      for (int k = 0; k < KC; ++k) s_cols[px * (KC + 1) + k] = cols[k];
     }
     __syncthreads();
     // ---- phase 2: output rows [2 row0, 2 (row0 + rows)) of image b
@@ -298,7 +290,7 @@ __global__ void __launch_bounds__(256) convT_cout_fwd_kernel(const float* __rest
       const int rem = o - oyl * (OW * COUT);
       const int ox = rem / COUT, co = rem - ox * COUT;
       const int oy = 2 * row0 + oyl;
-      float sum = 0.f;
+      float s = 0.f;
 #pragma unroll
       for (int a2 = 0; a2 < 2; ++a2) {
         const int kh = ((oy + 1) & 1) + 2 * a2;                 // kh = (oy + 1) mod 2, + 2
@@ -309,10 +301,10 @@ __global__ void __launch_bounds__(256) convT_cout_fwd_kernel(const float* __rest
           const int kw = ((ox + 1) & 1) + 2 * b2;
           const int ix = (ox + 1 - kw) >> 1;
           if (ix < 0 || ix >= IW) continue;
-          sum += s_cols[((iy - lo) * IW + ix) * (KC + 1) + (kh * 4 + kw) * COUT + co];
+          s += s_cols[((iy - lo) * IW + ix) * (KC + 1) + (kh * 4 + kw) * COUT + co];
         }
       }
-      out[((static_cast<int64_t>(b) * 2 * IH + oy) * OW) * COUT + rem] = sum;
+      out[((static_cast<int64_t>(b) * 2 * IH + oy) * OW) * COUT + rem] = s;
     }
   }
 }
@@ -503,7 +495,7 @@ extern "C" int mvae_conv_k4s2p1_cin_wgrad(const float* x, const float* da, float
     return set_error(MVAE_ERR_BAD_ARG, "conv_k4s2p1_cin_wgrad: da / dwc must be 16-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t npix = static_cast<int64_t>(B) * (H / 2) * (W / 2);
-  int64_t blocks = static_cast<int64_t>(sm_count()) * 4;
+  int64_t blocks = static_cast<int64_t>(sm_count()) * 8;
   int64_t per = (npix + blocks - 1) / blocks;
   if (per < 64) per = 64;
   blocks = (npix + per - 1) / per;
@@ -532,8 +524,7 @@ extern "C" int mvae_convt_k4s2p1_cout_fwd(const float* hin, const float* wt, flo
   const int tr = tile_rows(IH, IW);
   const int tiles_per_img = (IH + tr - 1) / tr;
   const int KC = 16 * Cout;
-  const size_t npx_max = static_cast<size_t>(tr + 2) * IW;
-  const size_t smem = (static_cast<size_t>(KC) * Cin + ((npx_max * (KC + 1) + 3) & ~size_t(3)) + npx_max * (Cin + 4)) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(KC) * Cin + static_cast<size_t>(tr + 2) * IW * (KC + 1)) * sizeof(float);
   int64_t blocks = static_cast<int64_t>(B) * tiles_per_img;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
   if (blocks > cap) blocks = cap;

@@ -102,10 +102,26 @@ struct alignas(64) GemmProblem {
   // accumulators are red.add'ed into a zeroed fp32 scratch matrix; per (tile, epilogue warp) an arrival counter tells the
   // last of them that its 32-row slab is complete -- it reads the sums back, applies the real epilogue (bias / Swish /
   // Swish' / column sums), stores C / out2, re-zeroes the scratch and publishes the row block to the chain.
+  // ---- implicit-GEMM convolution operands (mvae_conv_view): the operand is fetched with TMA im2col-mode loads from the
+  // NHWC activation itself.  Per operand: cblocks = C / 32 (k-blocks, or 32-wide boxes, per filter tap; 0 = plain matrix),
+  // output raster OW / OH*OW, position of the first filter tap of output pixel (p, q): (lower + p*stride, lower + q*stride).
+  struct ConvGeom { int cblocks, C, OW, OHW, lower_h, lower_w, stride, taps_w; } a_cv, b_cv;
   float* split_ws;        // [M][ldp] scratch or nullptr (plain split-K: partial sums red.add'ed straight into C)
   int64_t ldp;
   int tctr_base;          // first arrival counter of this problem (tiles_m * tiles_n * 8 counters)
 };
+
+// TMA base coordinates (w, h, n) of output pixel `pix` (raster index over n, p, q) of an implicit conv operand
+struct ConvPos { int w, h, n; };
+__device__ __forceinline__ ConvPos conv_pos(const GemmProblem::ConvGeom& g, int pix) {
+  ConvPos r;
+  r.n = pix / g.OHW;
+  const int rem = pix - r.n * g.OHW;
+  const int pp = rem / g.OW;
+  r.h = g.lower_h + pp * g.stride;
+  r.w = g.lower_w + (rem - pp * g.OW) * g.stride;
+  return r;
+}
 
 struct GemmBatch {
   GemmProblem p[MAX_PROBLEMS];
@@ -644,24 +660,61 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           }
         }
         if (batch.tilelog != nullptr) tilelog(batch, tl, 2, globaltimer_ns());
+        int acw = 0, ach = 0, acn = 0;     // implicit K-major A: base position of the tile's first output pixel
+        if (p.a_cv.cblocks != 0 && !a_mn) {
+          const ConvPos tp = conv_pos(p.a_cv, m0);
+          acw = tp.w; ach = tp.h; acn = tp.n;
+        }
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + OPERAND_BYTES;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
           const int k0 = kb * BLOCK_K;
-          if (!a_mn) {
-            ptx::tma_load_2d(sa, map_a, &full_bar[stage], k0, m0);  // box {32 k, 128 rows}
-          } else {
+          if (p.a_cv.cblocks == 0) {
+            if (!a_mn) {
+              ptx::tma_load_2d(sa, map_a, &full_bar[stage], k0, m0);  // box {32 k, 128 rows}
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 32; ++j)                    // 4 boxes {32 m, 32 k-rows}
-              ptx::tma_load_2d(sa + j * 4096, map_a, &full_bar[stage], m0 + 32 * j, k0);
-          }
-          if (!b_mn) {
-            ptx::tma_load_2d(sb, map_b, &full_bar[stage], k0, n0);  // box {32 k, block_n rows}
+              for (int j = 0; j < BLOCK_M / 32; ++j)                    // 4 boxes {32 m, 32 k-rows}
+                ptx::tma_load_2d(sa + j * 4096, map_a, &full_bar[stage], m0 + 32 * j, k0);
+            }
+          } else if (!a_mn) {
+            // implicit K-major A: 128 output pixels from (acw, ach, acn) x the 32 channels [c0, c0 + 32) of filter tap kb / cblocks
+            const int tap = kb / p.a_cv.cblocks, c0 = (kb - tap * p.a_cv.cblocks) * 32;
+            const int th = tap / p.a_cv.taps_w, tw = tap - th * p.a_cv.taps_w;
+            ptx::tma_load_im2col_4d(sa, map_a, &full_bar[stage], c0, acw, ach, acn, static_cast<uint16_t>(tw),
+                                    static_cast<uint16_t>(th));
           } else {
-            for (int j = 0; j < n_mine / 32; ++j)
-              ptx::tma_load_2d(sb + j * 4096, map_b, &full_bar[stage], n0 + 32 * j, k0);
+            // implicit MN-major A (weight-gradient form): the reduction runs over the pixels [k0, k0 + 32); the tile's 128 m
+            // values are (tap, channel) pairs, 32 channels of one tap per box
+            const ConvPos kp = conv_pos(p.a_cv, k0);
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 32; ++j) {
+              const int m = m0 + 32 * j;
+              const int tap = m / p.a_cv.C, c0 = m - tap * p.a_cv.C;
+              const int th = tap / p.a_cv.taps_w, tw = tap - th * p.a_cv.taps_w;
+              ptx::tma_load_im2col_4d(sa + j * 4096, map_a, &full_bar[stage], c0, kp.w, kp.h, kp.n, static_cast<uint16_t>(tw),
+                                      static_cast<uint16_t>(th));
+            }
+          }
+          if (p.b_cv.cblocks == 0) {
+            if (!b_mn) {
+              ptx::tma_load_2d(sb, map_b, &full_bar[stage], k0, n0);  // box {32 k, block_n rows}
+            } else {
+              for (int j = 0; j < n_mine / 32; ++j)
+                ptx::tma_load_2d(sb + j * 4096, map_b, &full_bar[stage], n0 + 32 * j, k0);
+            }
+          } else {
+            // implicit MN-major B (Conv2d weight gradient: dW = dy^T im2col(x)): boxes of 32 pixels x 32 channels of one tap
+            const ConvPos kp = conv_pos(p.b_cv, k0);
+            for (int j = 0; j < n_mine / 32; ++j) {
+              const int n = n0 + 32 * j;
+              const int tap = n / p.b_cv.C, c0 = n - tap * p.b_cv.C;
+              const int th = tap / p.b_cv.taps_w, tw = tap - th * p.b_cv.taps_w;
+              ptx::tma_load_im2col_4d(sb + j * 4096, map_b, &full_bar[stage], c0, kp.w, kp.h, kp.n, static_cast<uint16_t>(tw),
+                                      static_cast<uint16_t>(th));
+            }
           }
           dbg_stamp(batch, 0, dn);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -1079,6 +1132,48 @@ int make_map(CUtensorMap* m, const float* base, int64_t inner, int64_t rows, int
   return MVAE_OK;
 }
 
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeIm2col get_encode_im2col() {
+  static PFN_encodeIm2col fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_encodeIm2col>(p);
+  return fn;
+}
+
+// im2col-mode map over an NHWC fp32 tensor: `pixels` output pixels x 32 channels per load
+int make_im2col_map(CUtensorMap* m, const float* base, const mvae_conv_view& v, int pixels, CUtensorMapSwizzle swizzle) {
+  PFN_encodeIm2col enc = get_encode_im2col();
+  if (!enc) return set_error(MVAE_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not available");
+  if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(MVAE_ERR_BAD_ARG, "conv operand must be 16-byte aligned");
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(v.C), static_cast<cuuint64_t>(v.W), static_cast<cuuint64_t>(v.H),
+                        static_cast<cuuint64_t>(v.N)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(v.C) * 4, static_cast<cuuint64_t>(v.W) * v.C * 4,
+                        static_cast<cuuint64_t>(v.H) * v.W * v.C * 4};
+  int lo[2] = {v.lower_w, v.lower_h}, up[2] = {v.upper_w, v.upper_h};
+  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(v.stride), static_cast<cuuint32_t>(v.stride), 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, lo, up, 32,
+                   static_cast<cuuint32_t>(pixels), estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MVAE_ERR_CUDA, "cuTensorMapEncodeIm2col failed (%d)", (int)r);
+  return MVAE_OK;
+}
+
+// geometry of a conv view; returns the number of output pixels (0 on inconsistent parameters)
+int64_t conv_geom(const mvae_conv_view& v, GemmProblem::ConvGeom* g) {
+  if (v.C <= 0 || (v.C & 31) || v.N < 1 || v.H < 1 || v.W < 1 || v.stride < 1 || v.taps_h < 1 || v.taps_w < 1) return 0;
+  const int oh = (v.H + v.upper_h - v.lower_h - 1) / v.stride + 1, ow = (v.W + v.upper_w - v.lower_w - 1) / v.stride + 1;
+  if (oh < 1 || ow < 1) return 0;
+  g->cblocks = v.C / 32; g->C = v.C; g->OW = ow; g->OHW = oh * ow;
+  g->lower_h = v.lower_h; g->lower_w = v.lower_w; g->stride = v.stride; g->taps_w = v.taps_w;
+  return static_cast<int64_t>(v.N) * oh * ow;
+}
+
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // Debug knobs (environment) for the MN-major operand encoding; unset in normal operation.
@@ -1237,10 +1332,25 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
       p.dep_target = NUM_EPI_WARPS * pq.tiles_n * (pq.split_ws != nullptr ? 1 : pq.split_k);
     }
     int rc;
-    if (!p.a_mn) rc = make_map(&p.map_a, d.A, d.K, d.M, d.lda, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
+    memset(&p.a_cv, 0, sizeof(p.a_cv)); memset(&p.b_cv, 0, sizeof(p.b_cv));
+    if (d.a_view.C > 0) {
+      // implicit-GEMM A: rows (K-major) or the reduction index (MN-major) are the output pixels of the view
+      const int64_t pixels = conv_geom(d.a_view, &p.a_cv);
+      const int64_t kk = static_cast<int64_t>(d.a_view.taps_h) * d.a_view.taps_w * d.a_view.C;
+      if (pixels == 0 || pair || p.dep >= 0 || (!p.a_mn && (pixels != d.M || kk != d.K)) || (p.a_mn && (pixels != d.K || kk != d.M)))
+        return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: a_view does not match M/K (pixels %lld, taps*C %lld; C %% 32 == 0; no "
+                         "chain dependency, no pair kernel)", who, i, (long long)pixels, (long long)kk);
+      rc = make_im2col_map(&p.map_a, d.A, d.a_view, p.a_mn ? 32 : BLOCK_M, p.a_mn ? mn.swizzle : CU_TENSOR_MAP_SWIZZLE_128B);
+    } else if (!p.a_mn) rc = make_map(&p.map_a, d.A, d.K, d.M, d.lda, BLOCK_K, BLOCK_M, CU_TENSOR_MAP_SWIZZLE_128B);
     else         rc = make_map(&p.map_a, d.A, d.M, d.K, d.lda, 32, BLOCK_K, mn.swizzle);
     if (rc) return rc;
-    if (!p.b_mn) rc = make_map(&p.map_b, d.B, d.K, d.N, d.ldb, BLOCK_K, pair ? block_n / 2 : block_n, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (d.b_view.C > 0) {
+      const int64_t pixels = conv_geom(d.b_view, &p.b_cv);
+      const int64_t kk = static_cast<int64_t>(d.b_view.taps_h) * d.b_view.taps_w * d.b_view.C;
+      if (pixels == 0 || pair || !p.b_mn || pixels != d.K || kk != d.N || (d.N % 32) != 0)
+        return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: b_view must be MN-major with pixels == K and taps*C == N", who, i);
+      rc = make_im2col_map(&p.map_b, d.B, d.b_view, 32, mn.swizzle);
+    } else if (!p.b_mn) rc = make_map(&p.map_b, d.B, d.K, d.N, d.ldb, BLOCK_K, pair ? block_n / 2 : block_n, CU_TENSOR_MAP_SWIZZLE_128B);
     else         rc = make_map(&p.map_b, d.B, d.N, d.K, d.ldb, 32, BLOCK_K, mn.swizzle);
     if (rc) return rc;
   }

@@ -111,6 +111,19 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 4-D im2col-mode load (NHWC activation, dims {C, W, H, N}): `pixels` consecutive OUTPUT pixels of a convolution starting
+// at base position (w, h, n) -- walking W, then H, then N by the map's traversal stride inside its bounding box -- times
+// `channels` input channels from c, each read at (w + off_w, h + off_h): one operand tile of an implicit GEMM, zero-filled
+// at the padding and past the last image.  Semantics verified on B200 against a CPU im2col (tools/micro/im2col_probe.cu).
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c, int32_t w,
+                                                   int32_t h, int32_t n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+        "h"(off_w), "h"(off_h)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),

@@ -28,11 +28,27 @@ def _chk2d(t: torch.Tensor, name: str):
                              f"{tuple(t.shape)} {t.dtype} strides={t.stride()} device={t.device}")
 
 
+def conv_view(N, H, W, Cch, taps=4, stride=2, pad=1, lower=None, upper=None) -> _lib.ConvView:
+    """im2col view of an NHWC tensor [N,H,W,C] for mvae_gemm_desc.a_view / b_view (include/mvae_b200.h): a taps x taps
+    filter walking with `stride`; by default the padding is symmetric (`pad`), `lower` / `upper` (h, w) override it."""
+    v = _lib.ConvView()
+    v.N, v.H, v.W, v.C = N, H, W, Cch
+    lo = (-pad, -pad) if lower is None else lower
+    up = (pad - (taps - 1), pad - (taps - 1)) if upper is None else upper
+    v.lower_h, v.lower_w, v.upper_h, v.upper_w = lo[0], lo[1], up[0], up[1]
+    v.stride, v.taps_h, v.taps_w = stride, taps, taps
+    return v
+
+
 def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, out2=None, epilogue=EPI_STORE,
-              split_k=1, accumulate=False, colsum=None, split_ws=None) -> GemmDesc:
+              split_k=1, accumulate=False, colsum=None, split_ws=None, a_view=None, b_view=None) -> GemmDesc:
     d = GemmDesc()
-    d.A, d.lda, d.a_mn_major = A.data_ptr(), A.stride(0), int(a_mn)
-    d.B, d.ldb, d.b_mn_major = B.data_ptr(), B.stride(0), int(b_mn)
+    d.A, d.lda, d.a_mn_major = A.data_ptr(), (A.stride(0) if a_view is None else 0), int(a_mn)
+    d.B, d.ldb, d.b_mn_major = B.data_ptr(), (B.stride(0) if b_view is None else 0), int(b_mn)
+    if a_view is not None:
+        d.a_view = a_view
+    if b_view is not None:
+        d.b_view = b_view
     d.M, d.N, d.K = M, N, K
     d.C, d.ldc = Cmat.data_ptr(), Cmat.stride(0)
     d.bias = _p(bias)

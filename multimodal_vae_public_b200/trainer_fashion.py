@@ -110,10 +110,17 @@ class FashionMVAETrainer(MnistMVAETrainer):
         B = self.B
         # direct kernels for the 1-channel conv layers (default); MVAE_DIRECT_C1=0 restores im2col + tensor-core GEMM
         self.direct_c1 = os.environ.get("MVAE_DIRECT_C1", "1") != "0"
+        # ... of which the last transposed conv's BACKWARD only on request (MVAE_DIRECT_C1_BWD=1): measured at B = 4096 the
+        # direct forward kernels win (conv1 133 vs 217 us, last transposed conv 235 vs 322 us) but the CUDA-core backward of the
+        # transposed conv does not (741 vs 562 us: 2,048 FMAs per pixel are too many for the FMA pipes;
+        # profiles/r02_conv_small_ncu.txt)
+        self.direct_c1_bwd = self.direct_c1 and os.environ.get("MVAE_DIRECT_C1_BWD", "0") == "1"
+        # implicit-GEMM operands for the 64-channel conv layers (default); MVAE_IMPLICIT_CONV=0 materialises im2col in HBM
+        self.implicit_conv = os.environ.get("MVAE_IMPLICIT_CONV", "1") != "0"
         # image encoder (B rows), NHWC
-        self.cols1 = f(B * 196, 16)
+        self.cols1 = f(B * 196, 16) if not self.direct_c1 else None
         self.c1_a, self.c1_h = f(B * 196, 64), f(B * 196, 64)
-        self.cols2 = f(B * 49, 1024)
+        self.cols2 = f(B * 49, 1024) if not self.implicit_conv else None
         self.c2_a, self.c2_h = f(B * 49, 128), f(B * 49, 128)           # == [B, 6272] in (h,w,c) order
         self.fc_a, self.fc_h = f(B, 512), f(B, 512)
         # text encoder
@@ -123,13 +130,13 @@ class FashionMVAETrainer(MnistMVAETrainer):
         self.u2_a, self.u2_h = f(2 * B, 6272), f(2 * B, 6272)           # == [2B*49, 128]
         self.colsT1 = f(2 * B * 49, 1024)
         self.t1_a, self.t1_h = f(2 * B * 196, 64), f(2 * B * 196, 64)
-        self.colsT2 = f(2 * B * 196, 16)
+        self.colsT2 = f(2 * B * 196, 16) if not self.direct_c1 else None
         # text decoder (2B rows)
         self.td_a = [f(2 * B, 512) for _ in range(3)]; self.td_h = [f(2 * B, 512) for _ in range(3)]
         # backward scratch
-        self.dcolsT2 = f(2 * B * 196, 16)
+        self.dcolsT2 = f(2 * B * 196, 16) if not self.direct_c1_bwd else None
         self.d_t1 = f(2 * B * 196, 64)
-        self.dcolsT1 = f(2 * B * 49, 1024)
+        self.dcolsT1 = f(2 * B * 49, 1024) if not self.implicit_conv else None
         self.d_u2 = f(2 * B, 6272)
         self.d_u1 = f(2 * B, 512)
         self.td_dA = [f(2 * B, 512) for _ in range(2)]
@@ -182,7 +189,10 @@ class FashionMVAETrainer(MnistMVAETrainer):
             ops.im2col_k4s2p1(self.x, self.cols1, B, 28, 28, 1)
             ops.gemm_batch([ops.gemm_desc(self.cols1, p["image_encoder.features.0.weight"], self.c1_a, B * 196, 64, 16,
                                           out2=self.c1_h, epilogue=ops.EPI_BIAS_SWISH)], P)
-        ops.im2col_k4s2p1(self.c1_h, self.cols2, B, 14, 14, 64)
+        imp = self.implicit_conv     # conv GEMM operands fetched by TMA im2col loads: no cols buffers in HBM
+        v_c1 = ops.conv_view(B, 14, 14, 64) if imp else None
+        if not imp:
+            ops.im2col_k4s2p1(self.c1_h, self.cols2, B, 14, 14, 64)
         lt = self.label_table
         if lt:   # label encoder once per class (csrc/label_table.cu); the PoE kernels gather row text[b]
             emb, w2, b2, w3, b3 = self._label_encoder(0)
@@ -190,8 +200,8 @@ class FashionMVAETrainer(MnistMVAETrainer):
         else:
             ops.embedding_swish_fwd(p["text_encoder.net.0.weight"], self.text, None, self.te_h1)
         ops.gemm_batch([
-            ops.gemm_desc(self.cols2, p["image_encoder.features.2.weight"], self.c2_a, B * 49, 128, 1024,
-                          out2=self.c2_h, epilogue=ops.EPI_BIAS_SWISH)] + ([] if lt else [
+            ops.gemm_desc(self.c1_h if imp else self.cols2, p["image_encoder.features.2.weight"], self.c2_a, B * 49, 128, 1024,
+                          out2=self.c2_h, epilogue=ops.EPI_BIAS_SWISH, a_view=v_c1)] + ([] if lt else [
             ops.gemm_desc(self.te_h1, p["text_encoder.net.2.weight"], self.te_a2, B, 512, 512,
                           bias=p["text_encoder.net.2.bias"], out2=self.te_h2, epilogue=ops.EPI_BIAS_SWISH)]), P)
         # (classifier.0 has K = 6272 but only B/128 x 4 output tiles: fused split-K when that leaves SMs idle)
@@ -248,7 +258,7 @@ class FashionMVAETrainer(MnistMVAETrainer):
         ops.bce_logits_fwd_bwd(self.logit_i, self.x, self.logit_i, self.lam_i / b_global, self.acc[0:3], seg_rows=B)
         ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)
         # ---- last layers: convT2 (image) and net.6 (text)
-        direct = self.direct_c1
+        direct = self.direct_c1_bwd
         ops.colsum_accumulate(self.logit_t, g["text_decoder.net.6.bias"])
         txt_last = [
             ops.gemm_desc(self.logit_t, self.td_h[2], g["text_decoder.net.6.weight"], 10, 512, 2 * B, a_mn=True, b_mn=True,
@@ -266,13 +276,17 @@ class FashionMVAETrainer(MnistMVAETrainer):
                               a_mn=True, b_mn=True, split_k=split_for(2 * B * 196), accumulate=True),
                 ops.gemm_desc(self.dcolsT2, p["image_decoder.hallucinate.2.weight"], self.d_t1, 2 * B * 196, 64, 16, b_mn=True,
                               aux=self.t1_a, epilogue=ops.EPI_MUL_DSWISH)] + txt_last, P)
-        # ---- convT1 (image) and net.4 (text)
-        ops.im2col_k4s2p1(self.d_t1, self.dcolsT1, 2 * B, 14, 14, 64)
+        # ---- convT1 (image) and net.4 (text): d cols = im2col(d_t1), implicit (TMA im2col) unless MVAE_IMPLICIT_CONV=0
+        imp = self.implicit_conv
+        v_t1 = ops.conv_view(2 * B, 14, 14, 64) if imp else None
+        if not imp:
+            ops.im2col_k4s2p1(self.d_t1, self.dcolsT1, 2 * B, 14, 14, 64)
+        dcols = self.d_t1 if imp else self.dcolsT1
         ops.gemm_batch([
-            ops.gemm_desc(self.dcolsT1, self.u2_h.view(2 * B * 49, 128), g["image_decoder.hallucinate.0.weight"], 1024, 128,
-                          2 * B * 49, a_mn=True, b_mn=True, split_k=split_for(2 * B * 49), accumulate=True),
-            ops.gemm_desc(self.dcolsT1, p["image_decoder.hallucinate.0.weight"], self.d_u2.view(2 * B * 49, 128), 2 * B * 49,
-                          128, 1024, b_mn=True, aux=self.u2_a.view(2 * B * 49, 128), epilogue=ops.EPI_MUL_DSWISH),
+            ops.gemm_desc(dcols, self.u2_h.view(2 * B * 49, 128), g["image_decoder.hallucinate.0.weight"], 1024, 128,
+                          2 * B * 49, a_mn=True, b_mn=True, split_k=split_for(2 * B * 49), accumulate=True, a_view=v_t1),
+            ops.gemm_desc(dcols, p["image_decoder.hallucinate.0.weight"], self.d_u2.view(2 * B * 49, 128), 2 * B * 49,
+                          128, 1024, b_mn=True, aux=self.u2_a.view(2 * B * 49, 128), epilogue=ops.EPI_MUL_DSWISH, a_view=v_t1),
             ops.gemm_desc(self.td_dA[0], self.td_h[1], g["text_decoder.net.4.weight"], 512, 512, 2 * B, a_mn=True, b_mn=True,
                           split_k=split_for(2 * B), accumulate=True),
             ops.gemm_desc(self.td_dA[0], p["text_decoder.net.4.weight"], self.td_dA[1], 2 * B, 512, 512, b_mn=True,
@@ -333,12 +347,13 @@ class FashionMVAETrainer(MnistMVAETrainer):
             ops.embedding_swish_bwd(p["text_encoder.net.0.weight"], self.text, self.te_dA[1], g["text_encoder.net.0.weight"])
         # ---- conv2
         ops.gemm_batch([
-            ops.gemm_desc(self.d_c2, self.cols2, g["image_encoder.features.2.weight"], 128, 1024, B * 49, a_mn=True,
-                          b_mn=True, split_k=split_for(B * 49), accumulate=True),
+            ops.gemm_desc(self.d_c2, self.c1_h if imp else self.cols2, g["image_encoder.features.2.weight"], 128, 1024, B * 49,
+                          a_mn=True, b_mn=True, split_k=split_for(B * 49), accumulate=True,
+                          b_view=ops.conv_view(B, 14, 14, 64) if imp else None),
             ops.gemm_desc(self.d_c2, p["image_encoder.features.2.weight"], self.dcols2, B * 49, 1024, 128, b_mn=True)], P)
         ops.col2im_k4s2p1(self.dcols2, self.d_c1, B, 7, 7, 64, aux=self.c1_a)
-        # ---- conv1 (no data gradient: the image is an input)
-        if direct:
+        # ---- conv1 (no data gradient: the image is an input); direct whenever the forward was (no cols1 buffer then)
+        if self.direct_c1:
             ops.conv_cin_wgrad(self.x, self.d_c1, g["image_encoder.features.0.weight"], B, 28, 28, 1, 64)
         else:
             ops.gemm_batch([ops.gemm_desc(self.d_c1, self.cols1, g["image_encoder.features.0.weight"], 64, 16, B * 196,
