@@ -105,7 +105,10 @@ struct alignas(64) GemmProblem {
   // ---- implicit-GEMM convolution operands (mvae_conv_view): the operand is fetched with TMA im2col-mode loads from the
   // NHWC activation itself.  Per operand: cblocks = C / 32 (k-blocks, or 32-wide boxes, per filter tap; 0 = plain matrix),
   // output raster OW / OH*OW, position of the first filter tap of output pixel (p, q): (lower + p*stride, lower + q*stride).
-  struct ConvGeom { int cblocks, C, OW, OHW, lower_h, lower_w, stride, taps_w; } a_cv, b_cv;
+  // Divisions by OW, OH*OW, C, cblocks, taps_w run on the single TMA-producer thread once per k-block: they use
+  // host-computed reciprocals (x / d = (x * mul) >> 40, exact for x < 2^28, d < 2^12).
+  struct ConvGeom { int cblocks, C, OW, OHW, lower_h, lower_w, stride, taps_w;
+                    unsigned long long m_OW, m_OHW, m_C, m_cb, m_tw; } a_cv, b_cv;
   float* split_ws;        // [M][ldp] scratch or nullptr (plain split-K: partial sums red.add'ed straight into C)
   int64_t ldp;
   int tctr_base;          // first arrival counter of this problem (tiles_m * tiles_n * 8 counters)
@@ -113,14 +116,28 @@ struct alignas(64) GemmProblem {
 
 // TMA base coordinates (w, h, n) of output pixel `pix` (raster index over n, p, q) of an implicit conv operand
 struct ConvPos { int w, h, n; };
+__device__ __forceinline__ int fdiv(int x, unsigned long long mul) {
+  return static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(x)) * mul) >> 40);
+}
 __device__ __forceinline__ ConvPos conv_pos(const GemmProblem::ConvGeom& g, int pix) {
   ConvPos r;
-  r.n = pix / g.OHW;
+  r.n = fdiv(pix, g.m_OHW);
   const int rem = pix - r.n * g.OHW;
-  const int pp = rem / g.OW;
+  const int pp = fdiv(rem, g.m_OW);
   r.h = g.lower_h + pp * g.stride;
   r.w = g.lower_w + (rem - pp * g.OW) * g.stride;
   return r;
+}
+// (channel offset, tap column, tap row) of index `idx` = (tap, channel) of an implicit operand's (tap, channel) axis
+struct ConvTap { int c0; uint16_t tw, th; };
+__device__ __forceinline__ ConvTap conv_tap(const GemmProblem::ConvGeom& g, int idx) {
+  ConvTap t;
+  const int tap = fdiv(idx, g.m_C);
+  t.c0 = idx - tap * g.C;
+  const int th = fdiv(tap, g.m_tw);
+  t.th = static_cast<uint16_t>(th);
+  t.tw = static_cast<uint16_t>(tap - th * g.taps_w);
+  return t;
 }
 
 struct GemmBatch {
@@ -661,9 +678,19 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
         }
         if (batch.tilelog != nullptr) tilelog(batch, tl, 2, globaltimer_ns());
         int acw = 0, ach = 0, acn = 0;     // implicit K-major A: base position of the tile's first output pixel
-        if (p.a_cv.cblocks != 0 && !a_mn) {
-          const ConvPos tp = conv_pos(p.a_cv, m0);
-          acw = tp.w; ach = tp.h; acn = tp.n;
+        ConvTap abox[BLOCK_M / 32], bbox[BLOCK_N_MAX / 32];   // implicit MN-major operands: (tap, channels) of the tile's 32-wide boxes
+        if (p.a_cv.cblocks != 0) {
+          if (!a_mn) {
+            const ConvPos tp = conv_pos(p.a_cv, m0);
+            acw = tp.w; ach = tp.h; acn = tp.n;
+          } else {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 32; ++j) abox[j] = conv_tap(p.a_cv, m0 + 32 * j);
+          }
+        }
+        if (p.b_cv.cblocks != 0) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N_MAX / 32; ++j) bbox[j] = conv_tap(p.b_cv, n0 + 32 * j);
         }
         for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -681,22 +708,17 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
             }
           } else if (!a_mn) {
             // implicit K-major A: 128 output pixels from (acw, ach, acn) x the 32 channels [c0, c0 + 32) of filter tap kb / cblocks
-            const int tap = kb / p.a_cv.cblocks, c0 = (kb - tap * p.a_cv.cblocks) * 32;
-            const int th = tap / p.a_cv.taps_w, tw = tap - th * p.a_cv.taps_w;
+            const int tap = fdiv(kb, p.a_cv.m_cb), c0 = (kb - tap * p.a_cv.cblocks) * 32;
+            const int th = fdiv(tap, p.a_cv.m_tw), tw = tap - th * p.a_cv.taps_w;
             ptx::tma_load_im2col_4d(sa, map_a, &full_bar[stage], c0, acw, ach, acn, static_cast<uint16_t>(tw),
                                     static_cast<uint16_t>(th));
           } else {
             // implicit MN-major A (weight-gradient form): the reduction runs over the pixels [k0, k0 + 32); the tile's 128 m
-            // values are (tap, channel) pairs, 32 channels of one tap per box
+            // values are (tap, channel) pairs, 32 channels of one tap per box (abox: computed once per tile)
             const ConvPos kp = conv_pos(p.a_cv, k0);
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 32; ++j) {
-              const int m = m0 + 32 * j;
-              const int tap = m / p.a_cv.C, c0 = m - tap * p.a_cv.C;
-              const int th = tap / p.a_cv.taps_w, tw = tap - th * p.a_cv.taps_w;
-              ptx::tma_load_im2col_4d(sa + j * 4096, map_a, &full_bar[stage], c0, kp.w, kp.h, kp.n, static_cast<uint16_t>(tw),
-                                      static_cast<uint16_t>(th));
-            }
+            for (int j = 0; j < BLOCK_M / 32; ++j)
+              ptx::tma_load_im2col_4d(sa + j * 4096, map_a, &full_bar[stage], abox[j].c0, kp.w, kp.h, kp.n, abox[j].tw, abox[j].th);
           }
           if (p.b_cv.cblocks == 0) {
             if (!b_mn) {
@@ -708,13 +730,10 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           } else {
             // implicit MN-major B (Conv2d weight gradient: dW = dy^T im2col(x)): boxes of 32 pixels x 32 channels of one tap
             const ConvPos kp = conv_pos(p.b_cv, k0);
-            for (int j = 0; j < n_mine / 32; ++j) {
-              const int n = n0 + 32 * j;
-              const int tap = n / p.b_cv.C, c0 = n - tap * p.b_cv.C;
-              const int th = tap / p.b_cv.taps_w, tw = tap - th * p.b_cv.taps_w;
-              ptx::tma_load_im2col_4d(sb + j * 4096, map_b, &full_bar[stage], c0, kp.w, kp.h, kp.n, static_cast<uint16_t>(tw),
-                                      static_cast<uint16_t>(th));
-            }
+#pragma unroll
+            for (int j = 0; j < BLOCK_N_MAX / 32; ++j)
+              if (j < n_mine / 32)
+                ptx::tma_load_im2col_4d(sb + j * 4096, map_b, &full_bar[stage], bbox[j].c0, kp.w, kp.h, kp.n, bbox[j].tw, bbox[j].th);
           }
           dbg_stamp(batch, 0, dn);
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -1171,6 +1190,10 @@ int64_t conv_geom(const mvae_conv_view& v, GemmProblem::ConvGeom* g) {
   if (oh < 1 || ow < 1) return 0;
   g->cblocks = v.C / 32; g->C = v.C; g->OW = ow; g->OHW = oh * ow;
   g->lower_h = v.lower_h; g->lower_w = v.lower_w; g->stride = v.stride; g->taps_w = v.taps_w;
+  auto recip = [](int d) { return ((1ULL << 40) + static_cast<unsigned long long>(d) - 1) / static_cast<unsigned long long>(d); };
+  if (ow >= 4096 || v.C >= 4096 || v.taps_w >= 4096 || static_cast<int64_t>(oh) * ow >= 4096 * 16) return 0;
+  g->m_OW = recip(ow); g->m_OHW = recip(oh * ow); g->m_C = recip(v.C); g->m_cb = recip(v.C / 32); g->m_tw = recip(v.taps_w);
+  if (static_cast<int64_t>(v.N) * oh * ow >= (1LL << 28)) return 0;     // (exactness range of the reciprocal divisions)
   return static_cast<int64_t>(v.N) * oh * ow;
 }
 

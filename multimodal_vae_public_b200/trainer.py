@@ -169,9 +169,10 @@ class MnistMVAETrainer:
         # Adam on the rank's slice -> parameter all-gather, csrc/dp_p2p.cu); "nccl" = ncclAllReduce + flat Adam.
         self.dp_mode = "none"
         if world_size > 1:
-            # default "nccl"; MVAE_DP=p2p (or dp_mode="p2p") selects the fused peer-memory kernel: verified bit-for-bit
-            # against NCCL at 2 GPUs (+3.4 % step throughput), not yet validated at 4 and 8
-            self.dp_mode = os.environ.get("MVAE_DP", "nccl") if dp_mode is None else dp_mode
+            # default "auto": the fused peer-memory kernel when every rank has NVLink peer access to every other rank (agreed
+            # collectively), else NCCL.  Validated against NCCL and the single-process trajectory at 2, 4 and 8 GPUs
+            # (tests/test_dp_p2p_gpu.py, profiles/r02_multi_gpu_*.txt); MVAE_DP=nccl / dp_mode="nccl" forces the collective.
+            self.dp_mode = os.environ.get("MVAE_DP", "auto") if dp_mode is None else dp_mode
             if self.dp_mode not in ("nccl", "p2p", "auto"):
                 raise _lib.MvaeError(f"dp_mode must be 'nccl', 'p2p' or 'auto', got {self.dp_mode!r}")
             if self.dp_mode in ("p2p", "auto"):

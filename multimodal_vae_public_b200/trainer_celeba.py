@@ -125,6 +125,8 @@ class CelebAMVAETrainer(MnistMVAETrainer):
                  lambda_attrs: float = 10.0, **kw):
         kw.pop("lambda_text", None)
         kw["label_table"] = False        # the attribute encoder takes 2^18 distinct inputs: no class table here
+        import os
+        self.implicit_conv = os.environ.get("MVAE_IMPLICIT_CONV", "1") != "0"
         super().__init__(n_latents=n_latents, batch_size=batch_size, lr=lr, lambda_image=lambda_image,
                          lambda_text=lambda_attrs, **kw)
 
@@ -297,6 +299,15 @@ class CelebAMVAETrainer(MnistMVAETrainer):
         return super()._warmup_state() + [self.buffers[k] for k in sorted(self.buffers)]
 
     # ------------------------------------------------------------------ helpers
+    def _cols(self, x, buf, n, H, W, Cch, stride, pad):
+        """Operand of a conv GEMM over the NHWC activation x [n,H,W,C]: (tensor, view).  Implicit (default, C % 32 == 0):
+        the activation itself + its im2col view, fetched by TMA im2col loads inside the GEMM -- nothing is written to HBM.
+        Otherwise the im2col matrix is materialised in `buf` (the 3-channel layers; MVAE_IMPLICIT_CONV=0)."""
+        if self.implicit_conv and Cch % 32 == 0:
+            return x, ops.conv_view(n, H, W, Cch, taps=4, stride=stride, pad=pad)
+        ops.im2col_k4(x, buf, n, H, W, Cch, stride, pad)
+        return buf, None
+
     def _bn_f(self, x, h, S, seg_rows, prefix, order, training, act=True):
         p = self.params
         ops.bn_forward(x, h, S, seg_rows, p[prefix + ".weight"], p[prefix + ".bias"], self.bn_mean[prefix],
@@ -326,18 +337,18 @@ class CelebAMVAETrainer(MnistMVAETrainer):
         # ---- image encoder (evaluated once; its BN running stats are updated twice: joint + image-only call)
         ops.im2col_k4(self.x, self.cols1, B, 64, 64, 3, 2, 1)
         G([D(self.cols1, p[f"{e}.0.weight"], self.c1_a, B * 1024, 32, 48, out2=self.c1_h, epilogue=SW)], P)
-        ops.im2col_k4(self.c1_h, self.cols2, B, 32, 32, 32, 2, 1)
-        G([D(self.cols2, p[f"{e}.2.weight"], self.c2_x, B * 256, 64, 512),
+        c2, v2 = self._cols(self.c1_h, self.cols2, B, 32, 32, 32, 2, 1)
+        G([D(c2, p[f"{e}.2.weight"], self.c2_x, B * 256, 64, 512, a_view=v2),
            D(self.a_in, p["attrs_encoder.net.0.weight"], self.ae1_x, B, 512, 20, bias=p["attrs_encoder.net.0.bias"])], P)
         self._bn_f(self.c2_x, self.c2_h, 1, B * 256, f"{e}.3", (0, 0), training)
         self._bn_f(self.ae1_x, self.ae1_h, 1, B, "attrs_encoder.net.1", (0, 0), training)
-        ops.im2col_k4(self.c2_h, self.cols3, B, 16, 16, 64, 2, 1)
-        G([D(self.cols3, p[f"{e}.5.weight"], self.c3_x, B * 64, 128, 1024),
+        c3, v3 = self._cols(self.c2_h, self.cols3, B, 16, 16, 64, 2, 1)
+        G([D(c3, p[f"{e}.5.weight"], self.c3_x, B * 64, 128, 1024, a_view=v3),
            D(self.ae1_h, p["attrs_encoder.net.3.weight"], self.ae2_x, B, 512, 512, bias=p["attrs_encoder.net.3.bias"])], P)
         self._bn_f(self.c3_x, self.c3_h, 1, B * 64, f"{e}.6", (0, 0), training)
         self._bn_f(self.ae2_x, self.ae2_h, 1, B, "attrs_encoder.net.4", (0, 0), training)
-        ops.im2col_k4(self.c3_h, self.cols4, B, 8, 8, 128, 1, 0)
-        G([D(self.cols4, p[f"{e}.8.weight"], self.c4_x, B * 25, 256, 2048),
+        c4, v4 = self._cols(self.c3_h, self.cols4, B, 8, 8, 128, 1, 0)
+        G([D(c4, p[f"{e}.8.weight"], self.c4_x, B * 25, 256, 2048, a_view=v4),
            D(self.ae2_h, p["attrs_encoder.net.6.weight"], self.enc_t, B, 2 * L, 512, bias=p["attrs_encoder.net.6.bias"])], P)
         self._bn_f(self.c4_x, self.c4_h, 1, B * 25, f"{e}.9", (0, 0), training)
         G([D(self.c4_h.view(B, 6400), p["image_encoder.classifier.0.weight"], self.fc_a, B, 512, 6400,
@@ -405,32 +416,32 @@ class CelebAMVAETrainer(MnistMVAETrainer):
         self._bn_b(self.t3_x, self.d_t3h, self.d_t3x, 3, B * 1024, 0, 2, f"{d}.7")
         # d_t3h/d_t3x hold live rows [0, 2B*1024): bn_bwd indexes rows globally from segment 0 -> consistent
         self._bn_b(self.ad_x[2], self.d_adh, self.d_adx, 3, B, 1, 2, "attrs_decoder.net.7")
-        ops.im2col_k4(self.d_t3x, self.dcolsT3, R, 32, 32, 32, 2, 1)
+        dc3, w3 = self._cols(self.d_t3x, self.dcolsT3, R, 32, 32, 32, 2, 1)
         ops.colsum_accumulate(self.d_adx[B:], g["attrs_decoder.net.6.bias"])
-        G([D(self.dcolsT3, self.t2_h[: R * 256], g[f"{d}.6.weight"], 512, 64, R * 256, a_mn=True, b_mn=True,
-             split_k=sp(R * 256), accumulate=True),
-           D(self.dcolsT3, p[f"{d}.6.weight"], self.d_t2h, R * 256, 64, 512, b_mn=True),
+        G([D(dc3, self.t2_h[: R * 256], g[f"{d}.6.weight"], 512, 64, R * 256, a_mn=True, b_mn=True,
+             split_k=sp(R * 256), accumulate=True, a_view=w3),
+           D(dc3, p[f"{d}.6.weight"], self.d_t2h, R * 256, 64, 512, b_mn=True, a_view=w3),
            D(self.d_adx[B:], self.ad_h[1][B:], g["attrs_decoder.net.6.weight"], 512, 512, R, a_mn=True, b_mn=True,
              split_k=sp(R), accumulate=True),
            D(self.d_adx[B:], p["attrs_decoder.net.6.weight"], self.d_adh[B:], R, 512, 512, b_mn=True)], P)
         self._bn_b(self.t2_x, self.d_t2h, self.d_t2x, 3, B * 256, 0, 2, f"{d}.4")
         self._bn_b(self.ad_x[1], self.d_adh, self.d_adx, 3, B, 1, 2, "attrs_decoder.net.4")
-        ops.im2col_k4(self.d_t2x, self.dcolsT2, R, 16, 16, 64, 2, 1)
+        dc2, w2 = self._cols(self.d_t2x, self.dcolsT2, R, 16, 16, 64, 2, 1)
         ops.colsum_accumulate(self.d_adx[B:], g["attrs_decoder.net.3.bias"])
-        G([D(self.dcolsT2, self.t1_h[: R * 64], g[f"{d}.3.weight"], 1024, 128, R * 64, a_mn=True, b_mn=True,
-             split_k=sp(R * 64), accumulate=True),
-           D(self.dcolsT2, p[f"{d}.3.weight"], self.d_t1h, R * 64, 128, 1024, b_mn=True),
+        G([D(dc2, self.t1_h[: R * 64], g[f"{d}.3.weight"], 1024, 128, R * 64, a_mn=True, b_mn=True,
+             split_k=sp(R * 64), accumulate=True, a_view=w2),
+           D(dc2, p[f"{d}.3.weight"], self.d_t1h, R * 64, 128, 1024, b_mn=True, a_view=w2),
            D(self.d_adx[B:], self.ad_h[0][B:], g["attrs_decoder.net.3.weight"], 512, 512, R, a_mn=True, b_mn=True,
              split_k=sp(R), accumulate=True),
            D(self.d_adx[B:], p["attrs_decoder.net.3.weight"], self.d_adh[B:], R, 512, 512, b_mn=True)], P)
         self._bn_b(self.t1_x, self.d_t1h, self.d_t1x, 3, B * 64, 0, 2, f"{d}.1")
         self._bn_b(self.ad_x[0], self.d_adh, self.d_adx, 3, B, 1, 2, "attrs_decoder.net.1")
-        ops.im2col_k4(self.d_t1x, self.dcolsT1, R, 8, 8, 128, 1, 0)
+        dc1, w1 = self._cols(self.d_t1x, self.dcolsT1, R, 8, 8, 128, 1, 0)
         ops.colsum_accumulate(self.d_adx[B:], g["attrs_decoder.net.0.bias"])
-        G([D(self.dcolsT1, self.d0_h.view(3 * B * 25, 256)[: R * 25], g[f"{d}.0.weight"], 2048, 256, R * 25, a_mn=True,
-             b_mn=True, split_k=sp(R * 25), accumulate=True),
-           D(self.dcolsT1, p[f"{d}.0.weight"], self.d_d0.view(R * 25, 256), R * 25, 256, 2048, b_mn=True,
-             aux=self.d0_a.view(3 * B * 25, 256)[: R * 25], epilogue=ops.EPI_MUL_DSWISH),
+        G([D(dc1, self.d0_h.view(3 * B * 25, 256)[: R * 25], g[f"{d}.0.weight"], 2048, 256, R * 25, a_mn=True,
+             b_mn=True, split_k=sp(R * 25), accumulate=True, a_view=w1),
+           D(dc1, p[f"{d}.0.weight"], self.d_d0.view(R * 25, 256), R * 25, 256, 2048, b_mn=True,
+             aux=self.d0_a.view(3 * B * 25, 256)[: R * 25], epilogue=ops.EPI_MUL_DSWISH, a_view=w1),
            D(self.d_adx[B:], self.Z[B:], g["attrs_decoder.net.0.weight"], 512, L, R, a_mn=True, b_mn=True,
              split_k=sp(R), accumulate=True),
            D(self.d_adx[B:], p["attrs_decoder.net.0.weight"], self.dZ[B:], R, L, 512, b_mn=True, accumulate=True)], P)
@@ -471,20 +482,22 @@ class CelebAMVAETrainer(MnistMVAETrainer):
         self._bn_b(self.c4_x, self.d_c4h, self.d_c4x, 1, B * 25, 0, 1, f"{e}.9")
         self._bn_b(self.ae1_x, self.d_aeh, self.d_aex, 1, B, 0, 1, "attrs_encoder.net.1")
         ops.colsum_accumulate(self.d_aex, g["attrs_encoder.net.0.bias"])
-        G([D(self.d_c4x, self.cols4, g[f"{e}.8.weight"], 256, 2048, B * 25, a_mn=True, b_mn=True, split_k=sp(B * 25),
-             accumulate=True),
+        imp = self.implicit_conv
+        V = ops.conv_view
+        G([D(self.d_c4x, self.c3_h if imp else self.cols4, g[f"{e}.8.weight"], 256, 2048, B * 25, a_mn=True, b_mn=True,
+             split_k=sp(B * 25), accumulate=True, b_view=V(B, 8, 8, 128, stride=1, pad=0) if imp else None),
            D(self.d_c4x, p[f"{e}.8.weight"], self.dcols4, B * 25, 2048, 256, b_mn=True),
            D(self.d_aex, self.a_in, g["attrs_encoder.net.0.weight"], 512, 20, B, a_mn=True, b_mn=True, split_k=sp(B),
              accumulate=True)], P)
         ops.col2im_k4(self.dcols4, self.d_c3h, B, 5, 5, 128, 1, 0)
         self._bn_b(self.c3_x, self.d_c3h, self.d_c3x, 1, B * 64, 0, 1, f"{e}.6")
-        G([D(self.d_c3x, self.cols3, g[f"{e}.5.weight"], 128, 1024, B * 64, a_mn=True, b_mn=True, split_k=sp(B * 64),
-             accumulate=True),
+        G([D(self.d_c3x, self.c2_h if imp else self.cols3, g[f"{e}.5.weight"], 128, 1024, B * 64, a_mn=True, b_mn=True,
+             split_k=sp(B * 64), accumulate=True, b_view=V(B, 16, 16, 64) if imp else None),
            D(self.d_c3x, p[f"{e}.5.weight"], self.dcols3, B * 64, 1024, 128, b_mn=True)], P)
         ops.col2im_k4(self.dcols3, self.d_c2h, B, 8, 8, 64, 2, 1)
         self._bn_b(self.c2_x, self.d_c2h, self.d_c2x, 1, B * 256, 0, 1, f"{e}.3")
-        G([D(self.d_c2x, self.cols2, g[f"{e}.2.weight"], 64, 512, B * 256, a_mn=True, b_mn=True, split_k=sp(B * 256),
-             accumulate=True),
+        G([D(self.d_c2x, self.c1_h if imp else self.cols2, g[f"{e}.2.weight"], 64, 512, B * 256, a_mn=True, b_mn=True,
+             split_k=sp(B * 256), accumulate=True, b_view=V(B, 32, 32, 32) if imp else None),
            D(self.d_c2x, p[f"{e}.2.weight"], self.dcols2, B * 256, 512, 64, b_mn=True)], P)
         ops.col2im_k4(self.dcols2, self.d_c1a, B, 16, 16, 32, 2, 1, aux=self.c1_a)
         G([D(self.d_c1a, self.cols1, g[f"{e}.0.weight"], 32, 48, B * 1024, a_mn=True, b_mn=True, split_k=sp(B * 1024),

@@ -325,14 +325,14 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         # ---- image encoder (once; BN running stats updated once per image-containing pass)
         ops.im2col_k4(self.x, self.cols1, B, 64, 64, 3, 2, 1)
         G([D(self.cols1, p[f"{e}.0.weight"], self.c1_a, B * 1024, 32, 48, out2=self.c1_h, epilogue=SW)], Pp)
-        ops.im2col_k4(self.c1_h, self.cols2, B, 32, 32, 32, 2, 1)
-        G([D(self.cols2, p[f"{e}.2.weight"], self.c2_x, B * 256, 64, 512)], Pp)
+        c2, v2 = self._cols(self.c1_h, self.cols2, B, 32, 32, 32, 2, 1)
+        G([D(c2, p[f"{e}.2.weight"], self.c2_x, B * 256, 64, 512, a_view=v2)], Pp)
         self._bn_f(self.c2_x, self.c2_h, 1, B * 256, f"{e}.3", (0,) * NI, training)
-        ops.im2col_k4(self.c2_h, self.cols3, B, 16, 16, 64, 2, 1)
-        G([D(self.cols3, p[f"{e}.5.weight"], self.c3_x, B * 64, 128, 1024)], Pp)
+        c3, v3 = self._cols(self.c2_h, self.cols3, B, 16, 16, 64, 2, 1)
+        G([D(c3, p[f"{e}.5.weight"], self.c3_x, B * 64, 128, 1024, a_view=v3)], Pp)
         self._bn_f(self.c3_x, self.c3_h, 1, B * 64, f"{e}.6", (0,) * NI, training)
-        ops.im2col_k4(self.c3_h, self.cols4, B, 8, 8, 128, 1, 0)
-        G([D(self.cols4, p[f"{e}.8.weight"], self.c4_x, B * 25, 256, 2048)], Pp)
+        c4, v4 = self._cols(self.c3_h, self.cols4, B, 8, 8, 128, 1, 0)
+        G([D(c4, p[f"{e}.8.weight"], self.c4_x, B * 25, 256, 2048, a_view=v4)], Pp)
         self._bn_f(self.c4_x, self.c4_h, 1, B * 25, f"{e}.9", (0,) * NI, training)
         G([D(self.c4_h.view(B, 6400), p["image_encoder.classifier.0.weight"], self.fc_a, B, 512, 6400,
              bias=p["image_encoder.classifier.0.bias"], out2=self.fc_h, epilogue=SW)], Pp)
@@ -445,22 +445,24 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
              split_k=sp(R * 1024), accumulate=True),
            D(self.dcolsT4[: R * 1024], p[f"{d}.9.weight"], self.d_t3h[: R * 1024], R * 1024, 32, 48, b_mn=True)], Pp)
         self._bn_b(self.t3_x, self.d_t3h, self.d_t3x, P, B * 1024, 0, NI, f"{d}.7")
-        ops.im2col_k4(self.d_t3x, self.dcolsT3, R, 32, 32, 32, 2, 1)
-        G([D(self.dcolsT3[: R * 256], self.t2_h[: R * 256], g[f"{d}.6.weight"], 512, 64, R * 256, a_mn=True, b_mn=True,
-             split_k=sp(R * 256), accumulate=True),
-           D(self.dcolsT3[: R * 256], p[f"{d}.6.weight"], self.d_t2h[: R * 256], R * 256, 64, 512, b_mn=True)], Pp)
+        dc3, w3 = self._cols(self.d_t3x, self.dcolsT3, R, 32, 32, 32, 2, 1)
+        G([D(dc3[: R * (256 if w3 is None else 1024)], self.t2_h[: R * 256], g[f"{d}.6.weight"], 512, 64, R * 256, a_mn=True, b_mn=True,
+             split_k=sp(R * 256), accumulate=True, a_view=w3),
+           D(dc3[: R * (256 if w3 is None else 1024)], p[f"{d}.6.weight"], self.d_t2h[: R * 256], R * 256, 64, 512, b_mn=True,
+             a_view=w3)], Pp)
         self._bn_b(self.t2_x, self.d_t2h, self.d_t2x, P, B * 256, 0, NI, f"{d}.4")
-        ops.im2col_k4(self.d_t2x, self.dcolsT2, R, 16, 16, 64, 2, 1)
-        G([D(self.dcolsT2[: R * 64], self.t1_h[: R * 64], g[f"{d}.3.weight"], 1024, 128, R * 64, a_mn=True, b_mn=True,
-             split_k=sp(R * 64), accumulate=True),
-           D(self.dcolsT2[: R * 64], p[f"{d}.3.weight"], self.d_t1h[: R * 64], R * 64, 128, 1024, b_mn=True)], Pp)
+        dc2, w2 = self._cols(self.d_t2x, self.dcolsT2, R, 16, 16, 64, 2, 1)
+        G([D(dc2[: R * (64 if w2 is None else 256)], self.t1_h[: R * 64], g[f"{d}.3.weight"], 1024, 128, R * 64, a_mn=True, b_mn=True,
+             split_k=sp(R * 64), accumulate=True, a_view=w2),
+           D(dc2[: R * (64 if w2 is None else 256)], p[f"{d}.3.weight"], self.d_t1h[: R * 64], R * 64, 128, 1024, b_mn=True,
+             a_view=w2)], Pp)
         self._bn_b(self.t1_x, self.d_t1h, self.d_t1x, P, B * 64, 0, NI, f"{d}.1")
-        ops.im2col_k4(self.d_t1x, self.dcolsT1, R, 8, 8, 128, 1, 0)
+        dc1, w1 = self._cols(self.d_t1x, self.dcolsT1, R, 8, 8, 128, 1, 0)
         d_d0 = self.d_d0[:R]
-        G([D(self.dcolsT1[: R * 25], self.d0_h.view(-1, 256)[: R * 25], g[f"{d}.0.weight"], 2048, 256, R * 25, a_mn=True,
-             b_mn=True, split_k=sp(R * 25), accumulate=True),
-           D(self.dcolsT1[: R * 25], p[f"{d}.0.weight"], d_d0.view(R * 25, 256), R * 25, 256, 2048, b_mn=True,
-             aux=self.d0_a.view(-1, 256)[: R * 25], epilogue=DS)], Pp)
+        G([D(dc1[: R * (25 if w1 is None else 64)], self.d0_h.view(-1, 256)[: R * 25], g[f"{d}.0.weight"], 2048, 256, R * 25, a_mn=True,
+             b_mn=True, split_k=sp(R * 25), accumulate=True, a_view=w1),
+           D(dc1[: R * (25 if w1 is None else 64)], p[f"{d}.0.weight"], d_d0.view(R * 25, 256), R * 25, 256, 2048, b_mn=True,
+             aux=self.d0_a.view(-1, 256)[: R * 25], epilogue=DS, a_view=w1)], Pp)
         ops.colsum_accumulate(d_d0, g["image_decoder.upsample.0.bias"])
         G([D(d_d0, Z[:R], g["image_decoder.upsample.0.weight"], 6400, L, R, a_mn=True, b_mn=True, split_k=sp(R), accumulate=True),
            D(d_d0, p["image_decoder.upsample.0.weight"], self.dZ[:R], R, L, 6400, b_mn=True, accumulate=True)], Pp)
@@ -505,15 +507,20 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
              split_k=sp(B), accumulate=True),
            D(self.d_fca, p["image_encoder.classifier.0.weight"], self.d_c4h.view(B, 6400), B, 6400, 512, b_mn=True)], Pp)
         self._bn_b(self.c4_x, self.d_c4h, self.d_c4x, 1, B * 25, 0, 1, f"{e}.9")
-        G([D(self.d_c4x, self.cols4, g[f"{e}.8.weight"], 256, 2048, B * 25, a_mn=True, b_mn=True, split_k=sp(B * 25), accumulate=True),
+        imp = self.implicit_conv
+        V = ops.conv_view
+        G([D(self.d_c4x, self.c3_h if imp else self.cols4, g[f"{e}.8.weight"], 256, 2048, B * 25, a_mn=True, b_mn=True,
+             split_k=sp(B * 25), accumulate=True, b_view=V(B, 8, 8, 128, stride=1, pad=0) if imp else None),
            D(self.d_c4x, p[f"{e}.8.weight"], self.dcols4, B * 25, 2048, 256, b_mn=True)], Pp)
         ops.col2im_k4(self.dcols4, self.d_c3h, B, 5, 5, 128, 1, 0)
         self._bn_b(self.c3_x, self.d_c3h, self.d_c3x, 1, B * 64, 0, 1, f"{e}.6")
-        G([D(self.d_c3x, self.cols3, g[f"{e}.5.weight"], 128, 1024, B * 64, a_mn=True, b_mn=True, split_k=sp(B * 64), accumulate=True),
+        G([D(self.d_c3x, self.c2_h if imp else self.cols3, g[f"{e}.5.weight"], 128, 1024, B * 64, a_mn=True, b_mn=True,
+             split_k=sp(B * 64), accumulate=True, b_view=V(B, 16, 16, 64) if imp else None),
            D(self.d_c3x, p[f"{e}.5.weight"], self.dcols3, B * 64, 1024, 128, b_mn=True)], Pp)
         ops.col2im_k4(self.dcols3, self.d_c2h, B, 8, 8, 64, 2, 1)
         self._bn_b(self.c2_x, self.d_c2h, self.d_c2x, 1, B * 256, 0, 1, f"{e}.3")
-        G([D(self.d_c2x, self.cols2, g[f"{e}.2.weight"], 64, 512, B * 256, a_mn=True, b_mn=True, split_k=sp(B * 256), accumulate=True),
+        G([D(self.d_c2x, self.c1_h if imp else self.cols2, g[f"{e}.2.weight"], 64, 512, B * 256, a_mn=True, b_mn=True,
+             split_k=sp(B * 256), accumulate=True, b_view=V(B, 32, 32, 32) if imp else None),
            D(self.d_c2x, p[f"{e}.2.weight"], self.dcols2, B * 256, 512, 64, b_mn=True)], Pp)
         ops.col2im_k4(self.dcols2, self.d_c1a, B, 16, 16, 32, 2, 1, aux=self.c1_a)
         G([D(self.d_c1a, self.cols1, g[f"{e}.0.weight"], 32, 48, B * 1024, a_mn=True, b_mn=True, split_k=sp(B * 1024),

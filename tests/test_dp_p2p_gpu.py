@@ -73,7 +73,10 @@ def test_p2p_exchange_matches_single_process_and_nccl(tmp_path, use_graph, world
         for k, v in ref.params.items():
             for r in res[mode][1:]:
                 assert torch.equal(r0["params"][k], r["params"][k]), k       # replicas stay bit-identical
-            assert (v.cpu() - r0["params"][k]).abs().max().item() <= 1e-4, (mode, k)
+            # (4 Adam steps at lr = 1e-3: elements whose gradient is rounding noise move by +-lr per step in a direction that
+            # depends on the summation order -- sum over 2..8 partial gradients vs one full-batch sum -- so the bound is a
+            # fraction of lr per step; the losses above agree to 2e-6 and the replicas bit for bit)
+            assert (v.cpu() - r0["params"][k]).abs().max().item() <= 5e-4, (mode, k)
 
 
 def _worker_desync(rank, world, port, out):
