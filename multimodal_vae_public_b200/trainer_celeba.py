@@ -265,8 +265,48 @@ class CelebAMVAETrainer(MnistMVAETrainer):
             return float(self.loss_host[0])
         return None
 
-    def attach_dataset(self, *a, **k):  # pragma: no cover
-        raise _lib.MvaeError("the device-resident dataset path is implemented for the MNIST-shape trainers")
+    # ---- device-resident dataset (celeba/datasets.py:38-135 + the DataLoader / H2D of celeba/train.py:163-186 replaced)
+    def attach_dataset(self, images_u8: torch.Tensor, attrs: torch.Tensor) -> None:
+        """Keep the whole uint8 dataset in HBM: ``images_u8`` [N,64,64,3] (HWC, as the image files decode) or [N,3,64,64]
+        (CHW; converted once), ``attrs`` [N,18] in {0,1}.  A batch is then two gather launches: rows idx of the HWC bytes
+        / 255 land directly in the NHWC activation layout the conv kernels read (ToTensor's /255 and the NCHW->NHWC staging
+        of the host path both disappear), and the attribute rows become {0,1} floats."""
+        if images_u8.dtype != torch.uint8 or images_u8.dim() != 4:
+            raise _lib.MvaeError("attach_dataset: images must be a uint8 [N,64,64,3] or [N,3,64,64] tensor")
+        if images_u8.shape[1] == 3 and images_u8.shape[-1] != 3:
+            images_u8 = images_u8.permute(0, 2, 3, 1)
+        n = images_u8.shape[0]
+        if tuple(images_u8.shape[1:]) != (64, 64, 3) or tuple(attrs.shape) != (n, N_ATTRS):
+            raise _lib.MvaeError("attach_dataset: expected images [N,64,64,3] and attrs [N,18]")
+        self.ds_images = images_u8.contiguous().reshape(n, 64 * 64 * 3).to(self.dev)
+        a = torch.zeros(n, 20, dtype=torch.uint8)                      # rows padded to 20 bytes (the a_in layout); 255 -> 1.0
+        a[:, :N_ATTRS] = (attrs != 0).to(torch.uint8) * 255
+        self.ds_attrs = a.to(self.dev)
+
+    def epoch_permutation(self, seed: int) -> torch.Tensor:
+        g = torch.Generator(device=self.dev).manual_seed(seed)
+        return torch.randperm(self.ds_images.shape[0], generator=g, device=self.dev)
+
+    def step_from_dataset(self, idx: torch.Tensor, annealing_factor: float = 1.0, training: bool = True,
+                          update: bool = True, sync: bool = True):
+        """One training iteration on rows ``idx`` (int64 [B], on the device) of the attached dataset."""
+        if idx.numel() != self.B or idx.dtype != torch.int64 or not idx.is_cuda:
+            raise _lib.MvaeError(f"step_from_dataset: idx must be a CUDA int64 tensor of {self.B} row indices")
+        idx = idx.contiguous()
+        with torch.cuda.stream(self._stream):
+            ops.gather_batch_u8(self.ds_images, None, idx, self.x.view(self.B, 64 * 64 * 3), None)
+            ops.gather_batch_u8(self.ds_attrs, None, idx, self.a_in, None)
+            self._stage_beta(annealing_factor)
+            self._masks_given = False
+        self.run(training=training, noise_given=False, update=update)
+        self._pipe_after_run(training, update)
+        with torch.cuda.stream(self._stream):
+            self.loss_host.copy_(self.loss_out, non_blocking=True)
+        if sync:
+            self._stream.synchronize()
+            self.check_device_errors()
+            return float(self.loss_host[0])
+        return None
 
     # ---- pipelined host path (base class step_pipelined): one staged batch = NCHW image + [B,18] attrs
     def _pipe_slot_tensors(self):

@@ -141,3 +141,25 @@ def test_pipelined_host_fed_steps_equal_synchronous_steps():
         assert abs(x - y) <= 2e-6 * abs(x)
     for k in a.params:   # (several Adam steps on atomically-summed gradients: equal up to a small fraction of lr per step)
         assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-4, k
+
+
+def test_device_resident_dataset_equals_host_fed_step():
+    """attach_dataset + step_from_dataset (uint8 HWC dataset in HBM, /255 and the attribute lookup fused into the gather; no
+    NCHW staging) == step() on the same rows converted the way the reference's loader does (ToTensor: CHW float / 255)."""
+    from multimodal_vae_public_b200.trainer_celeba import CelebAMVAETrainer
+    B, N = 8, 40
+    rs = np.random.RandomState(21)
+    data = torch.from_numpy(rs.randint(0, 256, (N, 64, 64, 3)).astype(np.uint8))           # HWC, as decoded image files
+    attrs = torch.from_numpy(rs.randint(0, 2, (N, 18)).astype(np.int64))
+    a = CelebAMVAETrainer(n_latents=L, batch_size=B, use_graph=False)
+    b = CelebAMVAETrainer(n_latents=L, batch_size=B, use_graph=False)
+    b.load_state_dict(a.state_dict())
+    b.attach_dataset(data, attrs)
+    idx = torch.from_numpy(rs.permutation(N)[:B].astype(np.int64)).cuda()
+    img = (data[idx.cpu()].permute(0, 3, 1, 2).float() / 255.0).contiguous()                # ToTensor()
+    la = a.step(img, attrs[idx.cpu()].float(), annealing_factor=0.5, training=False, update=False)
+    lb = b.step_from_dataset(idx, annealing_factor=0.5, training=False, update=False)
+    assert abs(la - lb) <= 1e-6 * abs(la), (la, lb)
+    assert torch.equal(a.x, b.x) and torch.equal(a.a_in, b.a_in)
+    for k in a.grads:
+        assert (a.grads[k] - b.grads[k]).abs().max().item() <= 1e-5 * max(a.grads[k].abs().max().item(), 1e-12), k

@@ -242,3 +242,30 @@ def test_celeba19_modules_match_oracle():
     np.random.seed(21); a = T19.sample_combinations(T19.enumerate_combinations(19), 3)
     np.random.seed(21); b = O19.sample_combinations_fast(19, 3, np.random)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["prior", "image", "text", "both"])
+def test_generate_matches_oracle(mode):
+    """mnist/sample.py:66-112 as a function: the latent Gaussian of the four modes, n samples decoded by both decoders,
+    sigmoid / log_softmax outputs -- against the fp64 oracle with the same noise."""
+    from multimodal_vae_public_b200.mnist.sample import generate
+    m, image, text, p32 = _setup(B=4)
+    L, n = 64, 12
+    rs = np.random.RandomState(9)
+    noise = torch.from_numpy(rs.standard_normal((n, L)).astype(np.float32))
+    img = image[1:2] if mode in ("image", "both") else None
+    txt = int(text[1]) if mode in ("text", "both") else None
+    m.train()                                     # generate() must switch to eval itself and restore the mode
+    img_recon, txt_logp, z = generate(m, n, image=img, text=txt, noise=noise)
+    assert m.training and img_recon.shape == (n, 1, 28, 28) and txt_logp.shape == (n, 10)
+    p64 = {k: v.double() for k, v in p32.items()}
+    if mode == "prior":
+        mu, std = torch.zeros(1, L, dtype=torch.float64), torch.ones(1, L, dtype=torch.float64)
+    else:
+        mu, lv = O.mnist_infer(p64, None if img is None else img.double(), None if txt is None else torch.tensor([txt]), L)
+        std = (0.5 * lv).exp()
+    zr = noise.double() * std + mu
+    np.testing.assert_allclose(z.cpu().numpy(), zr.numpy(), rtol=1e-4, atol=2e-5)
+    ri = torch.sigmoid(O.mnist_decoder(p64, "image_decoder", zr)); rt = torch.log_softmax(O.mnist_decoder(p64, "text_decoder", zr), 1)
+    np.testing.assert_allclose(img_recon.reshape(n, 784).cpu().numpy(), ri.numpy(), rtol=1e-3, atol=5e-5)
+    np.testing.assert_allclose(txt_logp.cpu().numpy(), rt.numpy(), rtol=1e-3, atol=1e-4)
