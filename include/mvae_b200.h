@@ -86,8 +86,21 @@ typedef struct {
                                   /* the full epilogue (bias / Swish / Swish' / colsum) -- for layers with fewer output tiles  */
                                   /* than SMs (small per-GPU batches, K = 6272 classifier layers).  mvae_gemm_chain only;     */
                                   /* N % 4 == 0; one scratch per problem of a launch.                                          */
+  const float* B_lo;              /* optional, MVAE_PREC_3XTF32 only: B - trunc_tf32(B), same shape / ldb as B (mvae_split_lo).  */
+                                  /* B = weights are constant over a step, so their low halves are computed once per step      */
+                                  /* and fetched by TMA next to B instead of being recomputed per tile in the GEMM main loop.  */
   mvae_conv_view a_view;          /* a_view.C > 0: A is the im2col view of the NHWC tensor at `A` (lda ignored)                */
   mvae_conv_view b_view;          /* b_view.C > 0: B likewise (MN-major only: the weight-gradient form)                       */
+  /* Sub-pixel form of a stride-s transposed convolution (ConvTranspose2d forward, Conv2d data gradient: no cols buffer, no     */
+  /* col2im pass): the s*s output parity classes are separate problems whose A is a (k/s x k/s)-tap stride-1 view, whose B      */
+  /* picks the filter taps of the class out of the full weight matrix, and whose rows land on the class's output pixels.        */
+  /*   tap-split B : K = b_tap_slots * b_tap_k; slot t of the reduction uses B rows (K-major) / columns (MN-major)              */
+  /*                 [b_tap_table[t] * b_tap_mn, + N) and k in [0, b_tap_k).  b_tap_slots = 0: plain B.                         */
+  /*   row map     : GEMM row (n, j, i) of rowmap_IH x rowmap_IW grids is stored at pixel (n, s j + py, s i + px) of an          */
+  /*                 (s IH) x (s IW) NHWC image -- C, out2 and aux alike.  rowmap_IW = 0: identity.                              */
+  int32_t b_tap_slots, b_tap_k, b_tap_mn;
+  int32_t b_tap_table[16];
+  int32_t rowmap_IH, rowmap_IW, rowmap_s, rowmap_py, rowmap_px;
 } mvae_gemm_desc;
 
 /* Launch up to MVAE_GEMM_MAX_BATCH independent problems in ONE persistent kernel. */
@@ -113,6 +126,10 @@ int mvae_gemm_batch(const mvae_gemm_desc* descs, int n, int precision, void* str
 #define MVAE_GEMM_CHAIN_WS_HEADER 2
 int mvae_gemm_chain(const mvae_gemm_desc* descs, const int32_t* deps, int n, int32_t* ws, int64_t ws_ints,
                     int precision, void* stream);
+
+/* lo[i] = x[i] - trunc_tf32(x[i]) (low 13 mantissa bits cleared): the low halves of 3xTF32 operands, for mvae_gemm_desc.B_lo.
+ * n % 4 == 0, 16-byte aligned. */
+int mvae_split_lo(const float* x, float* lo, int64_t n, void* stream);
 
 /* y = x W^T + b (optionally also h = swish(y)):  nn.Linear.forward + Swish, mnist/model.py:81-84. */
 int mvae_linear_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,

@@ -41,7 +41,12 @@ class GemmDesc(C.Structure):
         ("colsum", C.c_void_p),
         ("epilogue", C.c_int32), ("split_k", C.c_int32), ("accumulate", C.c_int32),
         ("split_ws", C.c_void_p),
+        ("B_lo", C.c_void_p),
         ("a_view", ConvView), ("b_view", ConvView),
+        ("b_tap_slots", C.c_int32), ("b_tap_k", C.c_int32), ("b_tap_mn", C.c_int32),
+        ("b_tap_table", C.c_int32 * 16),
+        ("rowmap_IH", C.c_int32), ("rowmap_IW", C.c_int32), ("rowmap_s", C.c_int32), ("rowmap_py", C.c_int32),
+        ("rowmap_px", C.c_int32),
     ]
 
 
@@ -51,6 +56,7 @@ _P, _I, _L, _F, _U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
 SIGNATURES = {
     "mvae_gemm_batch": [C.POINTER(GemmDesc), _I, _I, _P],
     "mvae_gemm_chain": [C.POINTER(GemmDesc), C.POINTER(C.c_int32), _I, _P, _L, _I, _P],
+    "mvae_split_lo": [_P, _P, _L, _P],
     "mvae_linear_fwd": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _I, _I, _I, _I, _P],
     "mvae_linear_dgrad": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P],
     "mvae_linear_wgrad": [_P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _P],

@@ -1205,6 +1205,33 @@ extern "C" int mvae_adam_flat(float* p, const float* g, float* m, float* v, int6
   return MVAE_OK;
 }
 
+namespace mvae {
+namespace {
+__global__ void __launch_bounds__(256) split_lo_kernel(const float4* __restrict__ x, float4* __restrict__ lo, int64_t n4) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i];
+  float4 l;
+  l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+  l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+  l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  lo[i] = l;
+}
+}  // namespace
+}  // namespace mvae
+
+extern "C" int mvae_split_lo(const float* x, float* lo, int64_t n, void* stream) {
+  if (!x || !lo || n < 4 || (n & 3) || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(lo)) & 15))
+    return set_error(MVAE_ERR_BAD_ARG, "split_lo: n %% 4 == 0 and 16-byte aligned buffers required");
+  const int64_t n4 = n / 4;
+  split_lo_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(lo), n4);
+  count_launch();
+  MVAE_CUDA_CHECK(cudaGetLastError());
+  return MVAE_OK;
+}
+
 extern "C" int mvae_elbo_finalize(const double* recon_img, const double* recon_txt, const double* kl, int P,
                                   float lambda_image, float lambda_text, float beta, const float* beta_dev,
                                   float inv_batch, float* out, void* stream) {

@@ -72,6 +72,8 @@ struct Cfg {
 struct alignas(64) GemmProblem {
   CUtensorMap map_a;
   CUtensorMap map_b;
+  CUtensorMap map_b_lo;   // 3xTF32 with a pre-split B (weights): the lo tile arrives by TMA instead of being computed in the loop
+  int has_b_lo;
   float* C;
   const float* bias;
   const float* aux;
@@ -109,6 +111,15 @@ struct alignas(64) GemmProblem {
   // host-computed reciprocals (x / d = (x * mul) >> 40, exact for x < 2^28, d < 2^12).
   struct ConvGeom { int cblocks, C, OW, OHW, lower_h, lower_w, stride, taps_w;
                     unsigned long long m_OW, m_OHW, m_C, m_cb, m_tw; } a_cv, b_cv;
+  // ---- tap-split B (sub-pixel transposed convolutions): the K axis of the problem is (tap slot t, 32 r), the matching
+  // B rows (K-major) / columns (MN-major) of slot t start at bt_table[t] * bt_mn; bt_cb = k-blocks per slot (0 = off)
+  int bt_cb, bt_mn;
+  unsigned long long bt_m_cb;
+  unsigned char bt_table[16];
+  // ---- output row map (the same): GEMM row (n, j, i) of an IH x IW grid is stored at NHWC pixel (n, sy j + py, sx i + px)
+  // of an OH x OW image: row' = (n OH + s j + py) OW + s i + px.  Applies to C, out2 and aux.  rm_IW = 0: identity.
+  int rm_IW, rm_IHW, rm_OW, rm_OHW, rm_s, rm_py, rm_px;
+  unsigned long long rm_m_IW, rm_m_IHW;
   float* split_ws;        // [M][ldp] scratch or nullptr (plain split-K: partial sums red.add'ed straight into C)
   int64_t ldp;
   int tctr_base;          // first arrival counter of this problem (tiles_m * tiles_n * 8 counters)
@@ -281,10 +292,26 @@ struct EpiParams {
   int epilogue, atomic;
 };
 
-__device__ __forceinline__ float4 load_aux4(const EpiParams& e, int row, int col, int nvalid) {
+// Output row map of the sub-pixel transposed-convolution problems (GemmProblem::rm_*): only the general epilogue path of
+// the kExtra kernel instantiation uses it.
+struct RowMap {
+  int IW, IHW, OW, OHW, s, py, px;
+  unsigned long long m_IW, m_IHW;
+};
+__device__ __forceinline__ int64_t map_row(const RowMap& m, int row) {
+  if (m.IW == 0) return row;
+  const int n = static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(row)) * m.m_IHW) >> 40);
+  const int rem = row - n * m.IHW;
+  const int j = static_cast<int>((static_cast<unsigned long long>(static_cast<unsigned>(rem)) * m.m_IW) >> 40);
+  const int i = rem - j * m.IW;
+  return static_cast<int64_t>(n) * m.OHW + static_cast<int64_t>(m.s * j + m.py) * m.OW + m.s * i + m.px;
+}
+
+template <bool kMap = false>
+__device__ __forceinline__ float4 load_aux4(const EpiParams& e, int row, int col, int nvalid, const RowMap* rm = nullptr) {
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (row < e.M && nvalid > 0) {
-    const float* arow = e.aux + static_cast<int64_t>(row) * e.ldaux + col;
+    const float* arow = e.aux + (kMap ? map_row(*rm, row) : static_cast<int64_t>(row)) * e.ldaux + col;
     if (nvalid == 4) a = *reinterpret_cast<const float4*>(arow);
     else {
       a.x = arow[0];
@@ -299,9 +326,10 @@ __device__ __forceinline__ float4 load_aux4(const EpiParams& e, int row, int col
 // float4 index XOR-swizzled with (row & 7): conflict-free for the row-wise writes and the transposed reads).
 // The row loop is deliberately NOT unrolled: the fully unrolled version was instruction-fetch bound (the epilogue
 // is executed once per tile, ~25 KiB of straight-line code per pass, see profiles/r01_epilogue_ablation.txt).
+template <bool kMap = false>
 __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float4* st4, const uint32_t (&r)[32], int ncols,
                                                int lane, int row_base, int col0, const float (&bv)[4], float4 a_next,
-                                               int dbg_flags) {
+                                               int dbg_flags, const RowMap* rm = nullptr) {
   const int sub = lane >> 3, cq = lane & 7;
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -321,8 +349,9 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float4* st4, 
     const int rl = 4 * i + sub;
     const int row = row_base + rl;
     const float4 a_cur = a_next;
-    if (dsw && i < 7) a_next = load_aux4(e, row + 4, col, nvalid);   // one row group ahead
+    if (dsw && i < 7) a_next = load_aux4<kMap>(e, row + 4, col, nvalid, rm);   // one row group ahead
     if (nvalid == 0 || row >= e.M) continue;
+    const int64_t orow = kMap ? map_row(*rm, row) : static_cast<int64_t>(row);
     const float4 s4 = st4[rl * 8 + (cq ^ (rl & 7))];
     float v[4] = {s4.x + bv[0], s4.y + bv[1], s4.z + bv[2], s4.w + bv[3]};
     if (dsw && !(dbg_flags & 2)) {
@@ -337,7 +366,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float4* st4, 
 #pragma unroll
       for (int q = 0; q < 4; ++q) cs[q] += (q < nvalid) ? v[q] : 0.f;
     }
-    float* cptr = e.C + static_cast<int64_t>(row) * e.ldc + col;
+    float* cptr = e.C + orow * e.ldc + col;
     if (dbg_flags & 1) {
       if (v[0] == 123.456f) *cptr = v[1] + v[2] + v[3];
     } else if (e.atomic) {
@@ -356,7 +385,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float4* st4, 
       }
     }
     if (bsw) {
-      float* hptr = e.out2 + static_cast<int64_t>(row) * e.ldout2 + col;
+      float* hptr = e.out2 + orow * e.ldout2 + col;
       float h[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) h[q] = (dbg_flags & 2) ? v[q] * 0.5f : v[q] * sigmoidf_acc(v[q]);
@@ -575,6 +604,7 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
     for (int i = 0; i < batch.num_problems; ++i) {
       ptx::prefetch_tmap(&batch.p[i].map_a);
       ptx::prefetch_tmap(&batch.p[i].map_b);
+      if (batch.p[i].has_b_lo) ptx::prefetch_tmap(&batch.p[i].map_b_lo);
     }
     for (int s = 0; s < C::kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
@@ -696,7 +726,8 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + OPERAND_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          const bool b_lo_tma = kSplit && p.has_b_lo;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + (b_lo_tma ? 2 * b_bytes : b_bytes));
           const int k0 = kb * BLOCK_K;
           if (p.a_cv.cblocks == 0) {
             if (!a_mn) {
@@ -721,11 +752,23 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
               ptx::tma_load_im2col_4d(sa + j * 4096, map_a, &full_bar[stage], abox[j].c0, kp.w, kp.h, kp.n, abox[j].tw, abox[j].th);
           }
           if (p.b_cv.cblocks == 0) {
+            // tap-split B: k-block kb = (tap slot t, r); the slot's rows (K-major) / columns (MN-major) start at
+            // bt_table[t] * bt_mn and the k coordinate restarts at 32 r
+            int bk = k0, bn = n0;
+            if (p.bt_cb != 0) {
+              const int t = fdiv(kb, p.bt_m_cb);
+              bk = (kb - t * p.bt_cb) * BLOCK_K;
+              bn = n0 + static_cast<int>(p.bt_table[t]) * p.bt_mn;
+            }
             if (!b_mn) {
-              ptx::tma_load_2d(sb, map_b, &full_bar[stage], k0, n0);  // box {32 k, block_n rows}
+              ptx::tma_load_2d(sb, map_b, &full_bar[stage], bk, bn);  // box {32 k, block_n rows}
+              if (b_lo_tma) ptx::tma_load_2d(sb + C::kBBytes, &p.map_b_lo, &full_bar[stage], bk, bn);
             } else {
               for (int j = 0; j < n_mine / 32; ++j)
-                ptx::tma_load_2d(sb + j * 4096, map_b, &full_bar[stage], n0 + 32 * j, k0);
+                ptx::tma_load_2d(sb + j * 4096, map_b, &full_bar[stage], bn + 32 * j, bk);
+              if (b_lo_tma)
+                for (int j = 0; j < n_mine / 32; ++j)
+                  ptx::tma_load_2d(sb + C::kBBytes + j * 4096, &p.map_b_lo, &full_bar[stage], bn + 32 * j, bk);
             }
           } else {
             // implicit MN-major B (Conv2d weight gradient: dW = dy^T im2col(x)): boxes of 32 pixels x 32 channels of one tap
@@ -863,8 +906,16 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
         e.epilogue = MVAE_EPI_STORE; e.atomic = 1;
       }
       const bool dsw = e.epilogue == MVAE_EPI_MUL_DSWISH;
+      // output row map (sub-pixel transposed convolutions; kFused instantiation only): such problems take the general path
+      RowMap rm;
+      rm.IW = 0;
+      if (kFused && p.rm_IW != 0) {
+        rm.IW = p.rm_IW; rm.IHW = p.rm_IHW; rm.OW = p.rm_OW; rm.OHW = p.rm_OHW; rm.s = p.rm_s; rm.py = p.rm_py; rm.px = p.rm_px;
+        rm.m_IW = p.rm_m_IW; rm.m_IHW = p.rm_m_IHW;
+      }
+      const bool mapped = kFused && rm.IW != 0;
       // interior tiles (the common case) take the specialised epilogue; edge tiles / unusual combinations the general one
-      const bool rows_inside = row_base + 32 <= e.M && batch.dbg_flags == 0 &&
+      const bool rows_inside = row_base + 32 <= e.M && batch.dbg_flags == 0 && !mapped &&
                                !(e.colsum != nullptr && e.epilogue == MVAE_EPI_BIAS_SWISH) &&
                                !(e.colsum != nullptr && e.atomic);
       // ---- prefetch (independent of the accumulator): bias of my columns, aux rows of my chunk
@@ -882,6 +933,8 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
             const float* ap = e.aux + static_cast<int64_t>(row_base + sub) * e.ldaux + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i) auxv[i] = *reinterpret_cast<const float4*>(ap + static_cast<int64_t>(4 * i) * e.ldaux);
+          } else if (mapped) {
+            a0 = load_aux4<true>(e, row_base + sub, col, nvalid, &rm);
           } else {
             a0 = load_aux4(e, row_base + sub, col, nvalid);
           }
@@ -952,7 +1005,8 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           if (e.atomic) epilogue_chunk_fast16<true>(e, st_addr, r, lane, row_base, n0 + c0);
           else epilogue_chunk_fast16<false>(e, st_addr, r, lane, row_base, n0 + c0);
         } else {
-          epilogue_chunk(e, stage_buf, r, ncols, lane, row_base, n0 + c0, bv, a0, batch.dbg_flags);
+          if (mapped) epilogue_chunk<true>(e, stage_buf, r, ncols, lane, row_base, n0 + c0, bv, a0, batch.dbg_flags, &rm);
+          else epilogue_chunk(e, stage_buf, r, ncols, lane, row_base, n0 + c0, bv, a0, batch.dbg_flags);
         }
         if (ew == 0 && lane == 0) dbg_stamp(batch, 3, dn3);
       }
@@ -1005,6 +1059,7 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
     for (int t = tile0; t < batch.total_tiles; t += tile_step) {
       const TileInfo ti = decode_tile(batch, t);
       const int a_mn = batch.p[ti.prob].a_mn;
+      const bool b_presplit = batch.p[ti.prob].has_b_lo != 0;   // the lo tile of B came in by TMA (pre-split weights)
       for (int kb = ti.kb_begin; kb < ti.kb_end; ++kb) {
         if (tid == 0) dbg_stamp(batch, 4, dn4);
         ptx::mbar_wait(&full_bar[stage], phase);
@@ -1047,7 +1102,10 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
         ptx::tmem_st_32x32(ta, hi);
         ptx::tmem_st_32x32(ta + 32, lo);
         if (tid == 0) dbg_stamp(batch, 4, dn4);
-        // B: lo tile only
+        // B: lo tile only -- unless the caller supplied it pre-split (weights: x - trunc_tf32(x) is computed once per step
+        // by mvae_split_lo instead of once per tile and k-block here; this B pass was ~300 of the splitters' ~1,050 cycles
+        // per k-block, and the splitters are the critical path of the 3xTF32 main loop)
+        if (!b_presplit) {
         const uint32_t braw = sa + OPERAND_BYTES + (tid << 4);
         const uint32_t blo = braw + C::kBBytes;
         // all loads first, then all stores: interleaved, every load would wait for the previous store (the compiler
@@ -1064,6 +1122,7 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
           l.z = bx[i].z - __uint_as_float(__float_as_uint(bx[i].z) & 0xFFFFE000u);
           l.w = bx[i].w - __uint_as_float(__float_as_uint(bx[i].w) & 0xFFFFE000u);
           sts128(blo + i * (NUM_SPLIT_WARPS * 32 * 16), l.x, l.y, l.z, l.w);
+        }
         }
         if (tid == 0) dbg_stamp(batch, 4, dn4);
         ptx::tmem_st_wait();
@@ -1376,6 +1435,53 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
     } else if (!p.b_mn) rc = make_map(&p.map_b, d.B, d.K, d.N, d.ldb, BLOCK_K, pair ? block_n / 2 : block_n, CU_TENSOR_MAP_SWIZZLE_128B);
     else         rc = make_map(&p.map_b, d.B, d.N, d.K, d.ldb, 32, BLOCK_K, mn.swizzle);
     if (rc) return rc;
+    p.bt_cb = 0; p.bt_mn = 0; p.bt_m_cb = 0; memset(p.bt_table, 0, sizeof(p.bt_table));
+    p.rm_IW = 0;
+    if (d.b_tap_slots > 0) {
+      // K = slots * b_tap_k; B is a [rows][cols] matrix in which slot t occupies rows (K-major) / columns (MN-major)
+      // [b_tap_table[t] * b_tap_mn, + N) and k in [0, b_tap_k): the maps made above cover it if their extents say so
+      if (d.b_tap_slots > 16 || d.b_tap_k < 32 || (d.b_tap_k & 31) || static_cast<int64_t>(d.b_tap_slots) * d.b_tap_k != d.K ||
+          d.b_tap_mn < d.N || d.b_view.C > 0 || pair)
+        return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: tap-split B needs slots <= 16, b_tap_k %% 32 == 0, slots * b_tap_k == K, "
+                         "b_tap_mn >= N", who, i);
+      int max_t = 0;
+      for (int t = 0; t < d.b_tap_slots; ++t) {
+        p.bt_table[t] = static_cast<unsigned char>(d.b_tap_table[t]);
+        if (d.b_tap_table[t] > max_t) max_t = d.b_tap_table[t];
+      }
+      p.bt_cb = d.b_tap_k / 32; p.bt_mn = d.b_tap_mn;
+      p.bt_m_cb = ((1ULL << 40) + static_cast<unsigned long long>(p.bt_cb) - 1) / static_cast<unsigned long long>(p.bt_cb);
+      // re-encode the B map(s) over the whole tapped matrix: (max_t + 1) * b_tap_mn rows/cols, b_tap_k deep
+      const int64_t mn_extent = static_cast<int64_t>(max_t + 1) * d.b_tap_mn;
+      if (!p.b_mn) rc = make_map(&p.map_b, d.B, d.b_tap_k, mn_extent, d.ldb, BLOCK_K, block_n, CU_TENSOR_MAP_SWIZZLE_128B);
+      else         rc = make_map(&p.map_b, d.B, mn_extent, d.b_tap_k, d.ldb, 32, BLOCK_K, mn.swizzle);
+      if (rc) return rc;
+    }
+    if (d.rowmap_IW > 0) {
+      const int ihw = d.rowmap_IH * d.rowmap_IW;
+      if (d.rowmap_IH < 1 || d.rowmap_s < 1 || d.M % ihw != 0 || ihw >= 4096 * 16 || d.rowmap_IW >= 4096 || d.M >= (1 << 28) ||
+          d.rowmap_py < 0 || d.rowmap_py >= d.rowmap_s || d.rowmap_px < 0 || d.rowmap_px >= d.rowmap_s || atomic || fused || d.colsum)
+        return set_error(MVAE_ERR_BAD_ARG, "%s[%d]: bad output row map (M must be a whole number of IH x IW grids; plain "
+                         "store / activation epilogues only)", who, i);
+      p.rm_IW = d.rowmap_IW; p.rm_IHW = ihw; p.rm_s = d.rowmap_s; p.rm_OW = d.rowmap_s * d.rowmap_IW;
+      p.rm_OHW = d.rowmap_s * d.rowmap_s * ihw; p.rm_py = d.rowmap_py; p.rm_px = d.rowmap_px;
+      p.rm_m_IW = ((1ULL << 40) + static_cast<unsigned long long>(p.rm_IW) - 1) / static_cast<unsigned long long>(p.rm_IW);
+      p.rm_m_IHW = ((1ULL << 40) + static_cast<unsigned long long>(ihw) - 1) / static_cast<unsigned long long>(ihw);
+      any_fused = true;      // (the row map lives in the same kernel instantiation as fused split-K)
+    }
+    p.has_b_lo = 0;
+    if (d.B_lo != nullptr && precision == MVAE_PREC_3XTF32 && !pair && d.b_view.C == 0) {
+      int64_t bk_ext = d.K, bn_ext = d.N;
+      if (p.bt_cb != 0) {
+        int max_t = 0;
+        for (int t = 0; t < d.b_tap_slots; ++t) max_t = d.b_tap_table[t] > max_t ? d.b_tap_table[t] : max_t;
+        bk_ext = d.b_tap_k; bn_ext = static_cast<int64_t>(max_t + 1) * d.b_tap_mn;
+      }
+      if (!p.b_mn) rc = make_map(&p.map_b_lo, d.B_lo, bk_ext, bn_ext, d.ldb, BLOCK_K, block_n, CU_TENSOR_MAP_SWIZZLE_128B);
+      else         rc = make_map(&p.map_b_lo, d.B_lo, bn_ext, bk_ext, d.ldb, 32, BLOCK_K, mn.swizzle);
+      if (rc) return rc;
+      p.has_b_lo = 1;
+    }
   }
   batch.num_problems = n;
   batch.total_tiles = tiles;

@@ -40,9 +40,46 @@ def conv_view(N, H, W, Cch, taps=4, stride=2, pad=1, lower=None, upper=None) -> 
     return v
 
 
+# Pre-split weights (3xTF32): arenas registered here hold parameters whose low halves (x - trunc_tf32(x)) live at the same
+# offset in a twin buffer, refreshed once per step by split_lo(); gemm_desc() then hands the GEMM the twin of any B operand
+# that points into a registered arena (weights are the B operand of every forward / dgrad problem).
+_LO_ARENAS = []      # (base_ptr, end_ptr, lo_base_ptr)
+
+
+def register_lo_arena(params: torch.Tensor, lo: torch.Tensor) -> None:
+    if params.numel() != lo.numel() or params.dtype != torch.float32 or lo.dtype != torch.float32:
+        raise _lib.MvaeError("register_lo_arena: params / lo must be fp32 buffers of the same size")
+    _LO_ARENAS[:] = [a for a in _LO_ARENAS if a[0] != params.data_ptr()]
+    _LO_ARENAS.append((params.data_ptr(), params.data_ptr() + params.numel() * 4, lo.data_ptr()))
+
+
+def unregister_lo_arena(params: torch.Tensor) -> None:
+    _LO_ARENAS[:] = [a for a in _LO_ARENAS if a[0] != params.data_ptr()]
+
+
+def split_lo(x: torch.Tensor, lo: torch.Tensor) -> None:
+    """lo = x - trunc_tf32(x), element-wise (the low halves of 3xTF32 operands)."""
+    _lib.check(_lib.load().mvae_split_lo(x.data_ptr(), lo.data_ptr(), x.numel(), _stream()), "mvae_split_lo")
+
+
 def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, out2=None, epilogue=EPI_STORE,
-              split_k=1, accumulate=False, colsum=None, split_ws=None, a_view=None, b_view=None) -> GemmDesc:
+              split_k=1, accumulate=False, colsum=None, split_ws=None, a_view=None, b_view=None, b_taps=None,
+              rowmap=None) -> GemmDesc:
+    """b_taps = (table, k_per_slot, mn_per_slot): tap-split B; rowmap = (IH, IW, s, py, px): output row map (sub-pixel
+    transposed convolutions, see include/mvae_b200.h)."""
     d = GemmDesc()
+    if b_taps is not None:
+        table, k_per, mn_per = b_taps
+        d.b_tap_slots, d.b_tap_k, d.b_tap_mn = len(table), k_per, mn_per
+        for i, t in enumerate(table):
+            d.b_tap_table[i] = int(t)
+    if rowmap is not None:
+        d.rowmap_IH, d.rowmap_IW, d.rowmap_s, d.rowmap_py, d.rowmap_px = rowmap
+    bp = B.data_ptr()
+    for base, end, lo_base in _LO_ARENAS:
+        if base <= bp < end and b_view is None:
+            d.B_lo = lo_base + (bp - base)
+            break
     d.A, d.lda, d.a_mn_major = A.data_ptr(), (A.stride(0) if a_view is None else 0), int(a_mn)
     d.B, d.ldb, d.b_mn_major = B.data_ptr(), (B.stride(0) if b_view is None else 0), int(b_mn)
     if a_view is not None:
@@ -58,6 +95,30 @@ def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, 
     d.epilogue, d.split_k, d.accumulate = epilogue, split_k, int(accumulate)
     d.split_ws = _p(split_ws)      # fused split-K scratch [M, ceil4(N)] (zeroed once; see include/mvae_b200.h)
     return d
+
+
+def subpixel_k4s2p1(x, w, out, n, IH, IW, Cx, Cy, w_is_conv=False, out2=None, aux=None, epilogue=EPI_STORE):
+    """The four sub-pixel problems of a 4x4 / stride-2 / pad-1 TRANSPOSED convolution  y [n,2IH,2IW,Cy] = ConvT(x [n,IH,IW,Cx])
+    -- ConvTranspose2d forward (w = Wt [(kh,kw,cy)][cx], K-major B) or Conv2d data gradient (w_is_conv: w = Wc [cx][(kh,kw,cy)],
+    x = d out, y = d in; MN-major B) -- as implicit GEMMs: output pixel (2j+py, 2i+px) only ever sees the 2 x 2 taps
+    kh = 3-2a / 2-2a (py = 0 / 1), kw likewise, of input pixels (j+ly+a, i+lx+b), ly = -1 / 0.  No cols matrix, no col2im:
+    A = 2x2 stride-1 im2col view of x, B = the class's taps picked out of the full weight matrix (tap-split), rows stored
+    straight at their output pixels (row map); `out2` / `aux` ([n,2IH,2IW,Cy] like out) follow the same map."""
+    descs = []
+    M = n * IH * IW
+    for py in (0, 1):
+        for px in (0, 1):
+            ly, lx = (-1 if py == 0 else 0), (-1 if px == 0 else 0)
+            table = []
+            for a in (0, 1):
+                for b in (0, 1):
+                    kh = 3 - 2 * a if py == 0 else 2 - 2 * a
+                    kw = 3 - 2 * b if px == 0 else 2 - 2 * b
+                    table.append(kh * 4 + kw)
+            view = conv_view(n, IH, IW, Cx, taps=2, stride=1, lower=(ly, lx), upper=(ly, lx))
+            descs.append(gemm_desc(x, w, out, M, Cy, 4 * Cx, b_mn=w_is_conv, aux=aux, out2=out2, epilogue=epilogue, a_view=view,
+                                   b_taps=(table, Cx, Cy), rowmap=(IH, IW, 2, py, px)))
+    return descs
 
 
 def gemm_batch(descs: Sequence[GemmDesc], precision: int = PREC_3XTF32) -> None:

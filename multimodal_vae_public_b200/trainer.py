@@ -186,6 +186,12 @@ class MnistMVAETrainer:
         self.grads = {k: self.arena.view(1, k) for k, _ in self.layout}
         n = self.arena.numel
         self.flat_params, self.adam_m, self.adam_v = (self.arena.buffers[i][:n] for i in (0, 2, 3))
+        # pre-split weights (3xTF32): low halves of the parameters in a twin buffer, refreshed once per step and fetched
+        # by TMA as the GEMMs' B_lo operand (ops.register_lo_arena); MVAE_PRESPLIT=0 keeps the split inside the main loop
+        self.presplit = precision == PREC_3XTF32 and os.environ.get("MVAE_PRESPLIT", "1") != "0"
+        if self.presplit:
+            self.params_lo = torch.zeros(n, dtype=torch.float32, device=self.dev)
+            ops.register_lo_arena(self.flat_params, self.params_lo)
         self.grad_bucket = self.arena.buffers[1]          # gradients + 4 loss floats: the all-reduce payload
         self.flat_grads = self.grad_bucket[:n]
         B, L, dev = batch_size, n_latents, self.dev
@@ -283,7 +289,7 @@ class MnistMVAETrainer:
             bn = 128 if N >= 128 else (N + 31) // 32 * 32 if kw.get("b_mn") else (N + 15) // 16 * 16
             tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
             kb = (K + 31) // 32
-            budget = max(1, self._sms // max(share, 1))
+            budget = self._sms       # (siblings with short reductions drain quickly; a long one owns the machine's tail)
             # measured (profiles/r02_fused_split_ab.txt): worth it for LONG reductions only -- the K = 6272 classifier layers
             # at 512 rows/GPU gain 5 % of the FashionMNIST step, while splitting the K = 512 / 784 MNIST layers costs 6 %
             # (pipeline fill + the scratch round trip outweigh the shorter k loop): keep >= 16 k-blocks per split
@@ -545,6 +551,8 @@ class MnistMVAETrainer:
         b_global = self.B * self.world
         self.grad_bucket.zero_()
         self.zero_region.zero_()
+        if self.presplit:
+            ops.split_lo(self.flat_params, self.params_lo)
         self._enqueue_forward(training, use_noise_input)
         self._enqueue_loss_and_backward(training, b_global)
         ops.elbo_finalize(self.acc[0:3], self.acc[3:6], self.acc[6:9], 3, self.lam_i, self.lam_t, 1.0, 1.0 / b_global,

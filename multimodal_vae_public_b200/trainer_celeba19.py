@@ -316,6 +316,8 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         sp = self._split
         self._bn_training = training
         self.grad_bucket.zero_(); self.dZ.zero_(); self.acc19.zero_(); self.ad_dz.zero_()
+        if self.presplit:
+            ops.split_lo(self.flat_params, self.params_lo)
 
         def batched(descs):
             for i in range(0, len(descs), 4):

@@ -117,6 +117,9 @@ class FashionMVAETrainer(MnistMVAETrainer):
         self.direct_c1_bwd = self.direct_c1 and os.environ.get("MVAE_DIRECT_C1_BWD", "0") == "1"
         # implicit-GEMM operands for the 64-channel conv layers (default); MVAE_IMPLICIT_CONV=0 materialises im2col in HBM
         self.implicit_conv = os.environ.get("MVAE_IMPLICIT_CONV", "1") != "0"
+        # transposed convolutions (decoder forward, encoder data gradient) as four sub-pixel implicit GEMMs: no cols
+        # buffers, no col2im passes (ops.subpixel_k4s2p1); MVAE_SUBPIXEL=0 restores GEMM -> cols -> col2im
+        self.subpixel = self.implicit_conv and os.environ.get("MVAE_SUBPIXEL", "0") != "0"
         # image encoder (B rows), NHWC
         self.cols1 = f(B * 196, 16) if not self.direct_c1 else None
         self.c1_a, self.c1_h = f(B * 196, 64), f(B * 196, 64)
@@ -231,12 +234,17 @@ class FashionMVAETrainer(MnistMVAETrainer):
                           bias=p["image_decoder.upsampler.2.bias"], out2=self.u2_h, epilogue=ops.EPI_BIAS_SWISH),
             ops.gemm_desc(self.td_h[0], p["text_decoder.net.2.weight"], self.td_a[1], 2 * B, 512, 512,
                           bias=p["text_decoder.net.2.bias"], out2=self.td_h[1], epilogue=ops.EPI_BIAS_SWISH)], P)
-        ops.gemm_batch([
-            ops.gemm_desc(self.u2_h.view(2 * B * 49, 128), p["image_decoder.hallucinate.0.weight"], self.colsT1,
-                          2 * B * 49, 1024, 128),
-            ops.gemm_desc(self.td_h[1], p["text_decoder.net.4.weight"], self.td_a[2], 2 * B, 512, 512,
-                          bias=p["text_decoder.net.4.bias"], out2=self.td_h[2], epilogue=ops.EPI_BIAS_SWISH)], P)
-        ops.col2im_k4s2p1(self.colsT1, self.t1_a, 2 * B, 7, 7, 64, out_act=self.t1_h)
+        txt3 = ops.gemm_desc(self.td_h[1], p["text_decoder.net.4.weight"], self.td_a[2], 2 * B, 512, 512,
+                             bias=p["text_decoder.net.4.bias"], out2=self.td_h[2], epilogue=ops.EPI_BIAS_SWISH)
+        if self.subpixel:
+            descs = ops.subpixel_k4s2p1(self.u2_h, p["image_decoder.hallucinate.0.weight"], self.t1_a, 2 * B, 7, 7, 128, 64,
+                                        out2=self.t1_h, epilogue=ops.EPI_BIAS_SWISH)
+            ops.gemm_chain(descs + [txt3], [-1] * 5, self.chain_ws, P)
+        else:
+            ops.gemm_batch([
+                ops.gemm_desc(self.u2_h.view(2 * B * 49, 128), p["image_decoder.hallucinate.0.weight"], self.colsT1,
+                              2 * B * 49, 1024, 128), txt3], P)
+            ops.col2im_k4s2p1(self.colsT1, self.t1_a, 2 * B, 7, 7, 64, out_act=self.t1_h)
         txt_last = ops.gemm_desc(self.td_h[2], p["text_decoder.net.6.weight"], self.logit_t, 2 * B, 10, 512,
                                  bias=p["text_decoder.net.6.bias"])
         if direct:
@@ -350,8 +358,14 @@ class FashionMVAETrainer(MnistMVAETrainer):
             ops.gemm_desc(self.d_c2, self.c1_h if imp else self.cols2, g["image_encoder.features.2.weight"], 128, 1024, B * 49,
                           a_mn=True, b_mn=True, split_k=split_for(B * 49), accumulate=True,
                           b_view=ops.conv_view(B, 14, 14, 64) if imp else None),
-            ops.gemm_desc(self.d_c2, p["image_encoder.features.2.weight"], self.dcols2, B * 49, 1024, 128, b_mn=True)], P)
-        ops.col2im_k4s2p1(self.dcols2, self.d_c1, B, 7, 7, 64, aux=self.c1_a)
+            ] + ([] if self.subpixel else [
+            ops.gemm_desc(self.d_c2, p["image_encoder.features.2.weight"], self.dcols2, B * 49, 1024, 128, b_mn=True)]), P)
+        if self.subpixel:   # d c1 = ConvT(d c2; W2) * swish'(c1_a): four sub-pixel implicit GEMMs, rows stored in place
+            descs = ops.subpixel_k4s2p1(self.d_c2, p["image_encoder.features.2.weight"], self.d_c1, B, 7, 7, 128, 64,
+                                        w_is_conv=True, aux=self.c1_a, epilogue=ops.EPI_MUL_DSWISH)
+            ops.gemm_chain(descs, [-1] * 4, self.chain_ws, P)
+        else:
+            ops.col2im_k4s2p1(self.dcols2, self.d_c1, B, 7, 7, 64, aux=self.c1_a)
         # ---- conv1 (no data gradient: the image is an input); direct whenever the forward was (no cols1 buffer then)
         if self.direct_c1:
             ops.conv_cin_wgrad(self.x, self.d_c1, g["image_encoder.features.0.weight"], B, 28, 28, 1, 64)

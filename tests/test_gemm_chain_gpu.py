@@ -225,3 +225,40 @@ def test_fused_split_k_needs_scratch_and_chain(ops):
         ops.gemm_chain([ops.gemm_desc(x, w, y, 128, 64, 256, bias=b, split_k=2)], [-1], ops.chain_workspace("cuda"), 1)
     with pytest.raises(_lib.MvaeError):      # gemm_batch has no counter workspace
         ops.gemm_batch([ops.gemm_desc(x, w, y, 128, 64, 256, bias=b, split_k=2, split_ws=torch.zeros(128, 64, device="cuda"))], 1)
+
+
+@pytest.mark.parametrize("kind", ["fwd", "dgrad"])
+def test_presplit_b_lo_is_bit_identical_to_in_loop_split(ops, kind):
+    """3xTF32 with B_lo supplied (mvae_split_lo: weights split once per step, low halves fetched by TMA) computes exactly
+    what the in-loop split computes: same lo values, same MMAs."""
+    g = torch.Generator(device="cuda").manual_seed(17)
+    M, N, K = 1000, 512, 784
+    x = torch.randn(M, K, device="cuda", generator=g)
+    arena = torch.randn(N * K + 64, device="cuda", generator=g) / K ** 0.5        # a "parameter arena" holding W at offset 64
+    lo = torch.empty_like(arena)
+    if kind == "fwd":
+        w = arena[64:].view(N, K); b = torch.randn(N, device="cuda", generator=g)
+        mk = lambda y, h: ops.gemm_desc(x, w, y, M, N, K, bias=b, out2=h, epilogue=ops.EPI_BIAS_SWISH)   # noqa: E731
+    else:
+        w = arena[64:].view(K, N)                                                  # dx[M,N] = dy[M,K] W[K,N]: B MN-major
+        aux = torch.randn(M, N, device="cuda", generator=g)
+        mk = lambda y, h: ops.gemm_desc(x, w, y, M, N, K, b_mn=True, aux=aux, epilogue=ops.EPI_MUL_DSWISH)   # noqa: E731
+    y0 = torch.empty(M, N, device="cuda"); h0 = torch.empty(M, N, device="cuda")
+    d0 = mk(y0, h0)
+    assert not d0.B_lo
+    ops.gemm_batch([d0], 1)
+    ops.split_lo(arena, lo)
+    ops.register_lo_arena(arena, lo)
+    try:
+        y1 = torch.empty(M, N, device="cuda"); h1 = torch.empty(M, N, device="cuda")
+        d1 = mk(y1, h1)
+        assert d1.B_lo == lo.data_ptr() + 64 * 4
+        ops.gemm_batch([d1], 1)
+    finally:
+        ops.unregister_lo_arena(arena)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
+    if kind == "fwd":
+        assert torch.equal(h0, h1)
+    ref = arena.double()
+    assert torch.equal(lo.double(), ref - (arena.view(torch.int32) & -8192).view(torch.float32).double())

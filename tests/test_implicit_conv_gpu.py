@@ -110,3 +110,43 @@ def test_implicit_operands_equal_materialised_im2col(monkeypatch):
     for k in a.grads:
         err = (a.grads[k] - b.grads[k]).abs().max().item() / max(b.grads[k].abs().max().item(), 1e-12)
         assert err <= 1e-4, (k, err)
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("B,IH,Cin,Cout", [(3, 7, 128, 64), (40, 7, 128, 64), (2, 16, 64, 32), (300, 7, 128, 64)])
+def test_subpixel_conv_transpose_forward(ops, prec, B, IH, Cin, Cout):
+    """ConvTranspose2d(k4 s2 p1) + Swish as four sub-pixel implicit GEMMs (2x2 stride-1 views, tap-split B, row-mapped
+    stores of pre-activation and activation): no cols buffer, no col2im."""
+    rs = np.random.RandomState(B + IH + 1)
+    x = torch.from_numpy(rs.standard_normal((B, Cin, IH, IH)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((Cin, Cout, 4, 4)) / (4 * Cin) ** 0.5).astype(np.float32))
+    ref = F.conv_transpose2d(x.double(), w.double(), stride=2, padding=1).permute(0, 2, 3, 1)      # [B,2IH,2IH,Cout]
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wt = w.permute(2, 3, 1, 0).reshape(16 * Cout, Cin).contiguous().cuda()                       # [(kh,kw,co)][ci]
+    P_out = B * 4 * IH * IH
+    a = torch.full((P_out, Cout), float("nan"), device="cuda"); h = torch.full((P_out, Cout), float("nan"), device="cuda")
+    descs = ops.subpixel_k4s2p1(x_nhwc, wt, a, B, IH, IH, Cin, Cout, out2=h, epilogue=ops.EPI_BIAS_SWISH)
+    ops.gemm_chain(descs, [-1] * 4, ops.chain_workspace("cuda"), prec)
+    assert _rel(a, ref.reshape(P_out, Cout)) < TOL[prec]
+    assert _rel(h, (ref * torch.sigmoid(ref)).reshape(P_out, Cout)) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("B,H,C,Cout", [(3, 14, 64, 128), (33, 14, 64, 128), (2, 32, 32, 64), (280, 14, 64, 128)])
+def test_subpixel_conv_data_gradient(ops, prec, B, H, C, Cout):
+    """Conv2d(k4 s2 p1) data gradient through the Swish below: d x = ConvT(d y; W) * swish'(a) as four sub-pixel implicit
+    GEMMs (B = the conv weight [co][(kh,kw,ci)] read MN-major, tap-split), aux and C row-mapped."""
+    rs = np.random.RandomState(B + H + 2)
+    a = torch.from_numpy(rs.standard_normal((B, C, H, H)).astype(np.float32))                     # pre-activation of the layer below
+    w = torch.from_numpy((rs.standard_normal((Cout, C, 4, 4)) / (16 * C) ** 0.5).astype(np.float32))
+    a64 = a.double().requires_grad_(True)
+    y = F.conv2d(a64 * torch.sigmoid(a64), w.double(), stride=2, padding=1)                         # [B,Cout,H/2,H/2]
+    OH = H // 2
+    dy = torch.from_numpy(rs.standard_normal((B, OH, OH, Cout)).astype(np.float32))
+    (y.permute(0, 2, 3, 1) * dy.double()).sum().backward()
+    wc = w.permute(0, 2, 3, 1).reshape(Cout, 16 * C).contiguous().cuda()                           # [co][(kh,kw,ci)]
+    a_rows = a.permute(0, 2, 3, 1).reshape(B * H * H, C).contiguous().cuda()
+    dx = torch.full((B * H * H, C), float("nan"), device="cuda")
+    descs = ops.subpixel_k4s2p1(dy.cuda(), wc, dx, B, OH, OH, Cout, C, w_is_conv=True, aux=a_rows, epilogue=ops.EPI_MUL_DSWISH)
+    ops.gemm_chain(descs, [-1] * 4, ops.chain_workspace("cuda"), prec)
+    assert _rel(dx, a64.grad.permute(0, 2, 3, 1).reshape(B * H * H, C)) < TOL[prec] * 2
