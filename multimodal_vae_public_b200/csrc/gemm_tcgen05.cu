@@ -422,10 +422,12 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& e, float4* st4, 
 // instructions per element than the general path: the epilogue warps share their schedulers with the operand
 // splitters, so every instruction saved here is an issue slot for the main loop, and the tail of a launch (the last
 // tile's epilogue, which nothing overlaps) shrinks with it.
-template <int kEpi, bool kAtomic, bool kColsum>
+// kMap: the 8 rows of a lane go to the row-mapped pixels roff[i] (sub-pixel transposed convolutions) instead of to
+// row_base + sub + 4 i.
+template <int kEpi, bool kAtomic, bool kColsum, bool kMap = false>
 __device__ __forceinline__ void epilogue_chunk_fast(const EpiParams& e, uint32_t st_addr, const uint32_t (&r)[32],
                                                     int lane, int row_base, int col0, const float (&bv)[4],
-                                                    const float4 (&aux)[8]) {
+                                                    const float4 (&aux)[8], const int* roff = nullptr) {
   const int sub = lane >> 3, cq = lane & 7;
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -455,6 +457,10 @@ __device__ __forceinline__ void epilogue_chunk_fast(const EpiParams& e, uint32_t
     if (kColsum) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) cs[q] += v[q];
+    }
+    if (kMap) {
+      cptr = e.C + static_cast<int64_t>(roff[i]) * e.ldc + col;
+      if (kEpi == MVAE_EPI_BIAS_SWISH) hptr = e.out2 + static_cast<int64_t>(roff[i]) * e.ldout2 + col;
     }
     if (kAtomic) ptx::red_add_v4_f32(cptr, v[0], v[1], v[2], v[3]);
     else *reinterpret_cast<float4*>(cptr) = make_float4(v[0], v[1], v[2], v[3]);
@@ -577,11 +583,13 @@ __device__ __forceinline__ void epilogue_from_scratch(const EpiParams& e, float*
   }
 }
 
-// kFused: the launch contains fused split-K problems.  A separate instantiation: the phase-B code next to the main
-// epilogue costs registers (100-200 bytes of spills at the 128-register budget of the 14-warp CTA), which launches without
-// such problems -- all the large ones -- must not pay.
-template <bool kSplit, bool kPair, bool kFused = false>
+// kExtra: bit 0 = the launch contains fused split-K problems, bit 1 = row-mapped problems.  Separate instantiations: the
+// extra code next to the main epilogue costs registers (100-500 bytes of spills at the 128-register budget of the 14-warp
+// CTA), which launches without such problems -- all the large plain ones -- must not pay.
+template <bool kSplit, bool kPair, int kExtra = 0>
 __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
+  constexpr bool kFused = (kExtra & 1) != 0;     // fused split-K (last-arriver epilogue)
+  constexpr bool kRowMap = (kExtra & 2) != 0;    // row-mapped epilogue (sub-pixel transposed convolutions)
   using C = Cfg<kSplit, kPair>;
   static_assert(!kPair || kSplit, "the CTA-pair variant exists for the 3xTF32 mode only");
   extern __shared__ uint8_t smem_raw[];
@@ -909,15 +917,22 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
       // output row map (sub-pixel transposed convolutions; kFused instantiation only): such problems take the general path
       RowMap rm;
       rm.IW = 0;
-      if (kFused && p.rm_IW != 0) {
+      if (kRowMap && p.rm_IW != 0) {
         rm.IW = p.rm_IW; rm.IHW = p.rm_IHW; rm.OW = p.rm_OW; rm.OHW = p.rm_OHW; rm.s = p.rm_s; rm.py = p.rm_py; rm.px = p.rm_px;
         rm.m_IW = p.rm_m_IW; rm.m_IHW = p.rm_m_IHW;
       }
-      const bool mapped = kFused && rm.IW != 0;
+      const bool mapped = kRowMap && rm.IW != 0;
       // interior tiles (the common case) take the specialised epilogue; edge tiles / unusual combinations the general one
-      const bool rows_inside = row_base + 32 <= e.M && batch.dbg_flags == 0 && !mapped &&
-                               !(e.colsum != nullptr && e.epilogue == MVAE_EPI_BIAS_SWISH) &&
-                               !(e.colsum != nullptr && e.atomic);
+      const bool rows_inside0 = row_base + 32 <= e.M && batch.dbg_flags == 0 &&
+                                !(e.colsum != nullptr && e.epilogue == MVAE_EPI_BIAS_SWISH) &&
+                                !(e.colsum != nullptr && e.atomic);
+      const bool rows_inside = rows_inside0 && !mapped;
+      const bool mapped_fast = kRowMap && mapped && rows_inside0 && !e.atomic && e.colsum == nullptr;
+      int roff[8];                          // mapped rows of this lane (interior tiles of row-mapped problems)
+      if (kRowMap && mapped_fast) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) roff[i] = static_cast<int>(map_row(rm, row_base + sub + 4 * i));
+      }
       // ---- prefetch (independent of the accumulator): bias of my columns, aux rows of my chunk
       float bv[4];
       float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -933,6 +948,10 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
             const float* ap = e.aux + static_cast<int64_t>(row_base + sub) * e.ldaux + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i) auxv[i] = *reinterpret_cast<const float4*>(ap + static_cast<int64_t>(4 * i) * e.ldaux);
+          } else if (kRowMap && mapped_fast && n0 + 32 * c + 32 <= e.N && block_n - 32 * c >= 32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              auxv[i] = *reinterpret_cast<const float4*>(e.aux + static_cast<int64_t>(roff[i]) * e.ldaux + col);
           } else if (mapped) {
             a0 = load_aux4<true>(e, row_base + sub, col, nvalid, &rm);
           } else {
@@ -999,6 +1018,14 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
             epilogue_chunk_fast<MVAE_EPI_STORE, false, true>(e, st_addr, r, lane, row_base, n0 + c0, bv, auxv);
           else
             epilogue_chunk_fast<MVAE_EPI_STORE, false, false>(e, st_addr, r, lane, row_base, n0 + c0, bv, auxv);
+        } else if (kRowMap && mapped_fast && ncols == 32 && n0 + c0 + 32 <= e.N) {
+          const uint32_t st_addr = ptx::smem_u32(stage_buf);
+          if (e.epilogue == MVAE_EPI_BIAS_SWISH)
+            epilogue_chunk_fast<MVAE_EPI_BIAS_SWISH, false, false, true>(e, st_addr, r, lane, row_base, n0 + c0, bv, auxv, roff);
+          else if (dsw)
+            epilogue_chunk_fast<MVAE_EPI_MUL_DSWISH, false, false, true>(e, st_addr, r, lane, row_base, n0 + c0, bv, auxv, roff);
+          else
+            epilogue_chunk_fast<MVAE_EPI_STORE, false, false, true>(e, st_addr, r, lane, row_base, n0 + c0, bv, auxv, roff);
         } else if (rows_inside && ncols == 16 && n0 + c0 + 16 <= e.N && e.epilogue == MVAE_EPI_STORE &&
                    e.colsum == nullptr) {
           const uint32_t st_addr = ptx::smem_u32(stage_buf);
@@ -1164,9 +1191,9 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
   }
 }
 
-template <bool kSplit, bool kFused = false>
+template <bool kSplit, int kExtra = 0>
 __global__ void __launch_bounds__(Cfg<kSplit>::kThreads, 1) gemm_kernel(const __grid_constant__ GemmBatch batch) {
-  gemm_body<kSplit, false, kFused>(batch);
+  gemm_body<kSplit, false, kExtra>(batch);
 }
 
 // CTA-pair variant (3xTF32): launched as clusters of two CTAs (adjacent SMs of a TPC), tcgen05 cta_group::2.
@@ -1325,7 +1352,7 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
   GemmBatch batch;   // ~7 KiB of launch parameters (copied by value at launch)
   memset(&batch, 0, sizeof(batch));
   int tiles = 0, ctrs = 0;
-  bool any_fused = false;
+  bool any_fused = false, any_rowmap = false;
   const bool pair = use_pair_kernel(precision);
   const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
   const MnEncoding mn = mn_encoding();
@@ -1467,7 +1494,7 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
       p.rm_OHW = d.rowmap_s * d.rowmap_s * ihw; p.rm_py = d.rowmap_py; p.rm_px = d.rowmap_px;
       p.rm_m_IW = ((1ULL << 40) + static_cast<unsigned long long>(p.rm_IW) - 1) / static_cast<unsigned long long>(p.rm_IW);
       p.rm_m_IHW = ((1ULL << 40) + static_cast<unsigned long long>(ihw) - 1) / static_cast<unsigned long long>(ihw);
-      any_fused = true;      // (the row map lives in the same kernel instantiation as fused split-K)
+      any_rowmap = true;
     }
     p.has_b_lo = 0;
     if (d.B_lo != nullptr && precision == MVAE_PREC_3XTF32 && !pair && d.b_view.C == 0) {
@@ -1509,26 +1536,23 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
     }
     const int clusters = tiles < max_pair_clusters() ? tiles : max_pair_clusters();
     gemm_pair_kernel<<<2 * clusters, Cfg<true, true>::kThreads, Cfg<true, true>::kSmemBytes, st>>>(batch);
-  } else if (precision == MVAE_PREC_3XTF32) {
-    if (!attr_set[1]) {
-      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<true>::kSmemBytes));
-      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<true>::kSmemBytes));
-      attr_set[1] = true;
-    }
-    if (any_fused) gemm_kernel<true, true><<<grid, Cfg<true>::kThreads, Cfg<true>::kSmemBytes, st>>>(batch);
-    else gemm_kernel<true, false><<<grid, Cfg<true>::kThreads, Cfg<true>::kSmemBytes, st>>>(batch);
   } else {
-    if (!attr_set[0]) {
-      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<false>::kSmemBytes));
-      MVAE_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg<false>::kSmemBytes));
-      attr_set[0] = true;
+    const int extra = (any_fused ? 1 : 0) | (any_rowmap ? 2 : 0);
+    const bool split3 = precision == MVAE_PREC_3XTF32;
+    const int threads = split3 ? Cfg<true>::kThreads : Cfg<false>::kThreads;
+    const int smem = split3 ? Cfg<true>::kSmemBytes : Cfg<false>::kSmemBytes;
+    void (*kern)(const GemmBatch) = nullptr;
+    if (split3) {
+      kern = extra == 0 ? gemm_kernel<true, 0> : extra == 1 ? gemm_kernel<true, 1> : extra == 2 ? gemm_kernel<true, 2> : gemm_kernel<true, 3>;
+    } else {
+      kern = extra == 0 ? gemm_kernel<false, 0> : extra == 1 ? gemm_kernel<false, 1> : extra == 2 ? gemm_kernel<false, 2> : gemm_kernel<false, 3>;
     }
-    if (any_fused) gemm_kernel<false, true><<<grid, Cfg<false>::kThreads, Cfg<false>::kSmemBytes, st>>>(batch);
-    else gemm_kernel<false, false><<<grid, Cfg<false>::kThreads, Cfg<false>::kSmemBytes, st>>>(batch);
+    static bool attr_done[2][4] = {{false, false, false, false}, {false, false, false, false}};
+    if (!attr_done[split3 ? 1 : 0][extra]) {
+      MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr_done[split3 ? 1 : 0][extra] = true;
+    }
+    kern<<<grid, threads, smem, st>>>(batch);
   }
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());

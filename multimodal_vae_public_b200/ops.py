@@ -49,8 +49,14 @@ _LO_ARENAS = []      # (base_ptr, end_ptr, lo_base_ptr)
 def register_lo_arena(params: torch.Tensor, lo: torch.Tensor) -> None:
     if params.numel() != lo.numel() or params.dtype != torch.float32 or lo.dtype != torch.float32:
         raise _lib.MvaeError("register_lo_arena: params / lo must be fp32 buffers of the same size")
-    _LO_ARENAS[:] = [a for a in _LO_ARENAS if a[0] != params.data_ptr()]
-    _LO_ARENAS.append((params.data_ptr(), params.data_ptr() + params.numel() * 4, lo.data_ptr()))
+    b0, e0 = params.data_ptr(), params.data_ptr() + params.numel() * 4
+    l0, l1 = lo.data_ptr(), lo.data_ptr() + lo.numel() * 4
+    # drop every older entry that overlaps the new buffers: its owner is gone and the allocator reused the memory (a stale
+    # entry would hand a GEMM a B_lo pointer into somebody else's tensor)
+    _LO_ARENAS[:] = [a for a in _LO_ARENAS
+                     if not (a[0] < e0 and b0 < a[1]) and not (a[2] < l1 and l0 < a[2] + (a[1] - a[0]))
+                     and not (a[0] < l1 and l0 < a[1]) and not (a[2] < e0 and b0 < a[2] + (a[1] - a[0]))]
+    _LO_ARENAS.append((b0, e0, l0))
 
 
 def unregister_lo_arena(params: torch.Tensor) -> None:

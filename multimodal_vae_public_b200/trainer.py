@@ -186,9 +186,12 @@ class MnistMVAETrainer:
         self.grads = {k: self.arena.view(1, k) for k, _ in self.layout}
         n = self.arena.numel
         self.flat_params, self.adam_m, self.adam_v = (self.arena.buffers[i][:n] for i in (0, 2, 3))
-        # pre-split weights (3xTF32): low halves of the parameters in a twin buffer, refreshed once per step and fetched
-        # by TMA as the GEMMs' B_lo operand (ops.register_lo_arena); MVAE_PRESPLIT=0 keeps the split inside the main loop
-        self.presplit = precision == PREC_3XTF32 and os.environ.get("MVAE_PRESPLIT", "1") != "0"
+        # pre-split weights (3xTF32), OPT-IN (MVAE_PRESPLIT=1): low halves of the parameters in a twin buffer, refreshed once
+        # per step and fetched by TMA as the GEMMs' B_lo operand (ops.register_lo_arena) instead of being computed by the
+        # splitter warps per tile and k-block.  Bit-identical results, but measured SLOWER on the same box (MNIST 0.727 vs
+        # 0.713 ms/step, FashionMNIST 6.70 vs 6.49): the extra 16 KiB of L2 -> shared-memory traffic per k-block costs more
+        # than the 300 splitter cycles it removes (profiles/r02_ab_mnist_fashion.txt) -- the loop is L2-feed / smem bound.
+        self.presplit = precision == PREC_3XTF32 and os.environ.get("MVAE_PRESPLIT", "0") != "0"
         if self.presplit:
             self.params_lo = torch.zeros(n, dtype=torch.float32, device=self.dev)
             ops.register_lo_arena(self.flat_params, self.params_lo)
@@ -236,6 +239,13 @@ class MnistMVAETrainer:
         self._stream = torch.cuda.Stream(device=dev)
         self.launches_per_step = 0
         self.init_parameters(seed)
+
+    def __del__(self):
+        try:
+            if getattr(self, "presplit", False):
+                ops.unregister_lo_arena(self.flat_params)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
 
     # ------------------------------------------------------------------ flavour hooks
     def _make_layout(self, n_latents: int):
