@@ -127,6 +127,16 @@ def subpixel_k4s2p1(x, w, out, n, IH, IW, Cx, Cy, w_is_conv=False, out2=None, au
     return descs
 
 
+def full_k4s1p0(x, w, out, n, IH, IW, Cx, Cy, w_is_conv=False, out2=None, aux=None, epilogue=EPI_STORE):
+    """4x4 / stride-1 / pad-0 TRANSPOSED convolution y [n,IH+3,IW+3,Cy] = ConvT(x [n,IH,IW,Cx]) (celeba/model.py:117 forward,
+    :85 data gradient) as ONE implicit GEMM: output (oy, ox) sums x[oy - kh, ox - kw] W[kh, kw], i.e. a 4x4 stride-1 view
+    with lower corner -3 whose tap (th, tw) meets filter tap (3 - th, 3 - tw): tap-split B with the table reversed."""
+    view = conv_view(n, IH, IW, Cx, taps=4, stride=1, lower=(-3, -3), upper=(0, 0))
+    table = [15 - t for t in range(16)]
+    return [gemm_desc(x, w, out, n * (IH + 3) * (IW + 3), Cy, 16 * Cx, b_mn=w_is_conv, aux=aux, out2=out2, epilogue=epilogue,
+                      a_view=view, b_taps=(table, Cx, Cy))]
+
+
 def gemm_batch(descs: Sequence[GemmDesc], precision: int = PREC_3XTF32) -> None:
     arr = (GemmDesc * len(descs))(*descs)
     _lib.check(_lib.load().mvae_gemm_batch(arr, len(descs), precision, _stream()), "mvae_gemm_batch")

@@ -127,6 +127,8 @@ class CelebAMVAETrainer(MnistMVAETrainer):
         kw["label_table"] = False        # the attribute encoder takes 2^18 distinct inputs: no class table here
         import os
         self.implicit_conv = os.environ.get("MVAE_IMPLICIT_CONV", "1") != "0"
+        # transposed convolutions without cols / col2im (ops.subpixel_k4s2p1, ops.full_k4s1p0); see trainer_fashion
+        self.subpixel = self.implicit_conv and os.environ.get("MVAE_SUBPIXEL", "1") != "0"
         super().__init__(n_latents=n_latents, batch_size=batch_size, lr=lr, lambda_image=lambda_image,
                          lambda_text=lambda_attrs, **kw)
 
@@ -414,19 +416,30 @@ class CelebAMVAETrainer(MnistMVAETrainer):
              bias=p["image_decoder.upsample.0.bias"], out2=self.d0_h, epilogue=SW),
            D(self.Z, p["attrs_decoder.net.0.weight"], self.ad_x[0], 3 * B, 512, L, bias=p["attrs_decoder.net.0.bias"])], P)
         self._bn_f(self.ad_x[0], self.ad_h[0], 3, B, "attrs_decoder.net.1", _BN_ORDER3, training)
-        G([D(self.d0_h.view(3 * B * 25, 256), p[f"{d}.0.weight"], self.colsT1, 3 * B * 25, 2048, 256),
-           D(self.ad_h[0], p["attrs_decoder.net.3.weight"], self.ad_x[1], 3 * B, 512, 512, bias=p["attrs_decoder.net.3.bias"])], P)
-        ops.col2im_k4(self.colsT1, self.t1_x, 3 * B, 5, 5, 128, 1, 0)
+        sub = self.subpixel
+        GC = lambda descs: ops.gemm_chain(descs, [-1] * len(descs), self.chain_ws, P)   # noqa: E731  (> 4 problems / row maps)
+        ad1 = D(self.ad_h[0], p["attrs_decoder.net.3.weight"], self.ad_x[1], 3 * B, 512, 512, bias=p["attrs_decoder.net.3.bias"])
+        if sub:
+            GC(ops.full_k4s1p0(self.d0_h, p[f"{d}.0.weight"], self.t1_x, 3 * B, 5, 5, 256, 128) + [ad1])
+        else:
+            G([D(self.d0_h.view(3 * B * 25, 256), p[f"{d}.0.weight"], self.colsT1, 3 * B * 25, 2048, 256), ad1], P)
+            ops.col2im_k4(self.colsT1, self.t1_x, 3 * B, 5, 5, 128, 1, 0)
         self._bn_f(self.t1_x, self.t1_h, 3, B * 64, f"{d}.1", _BN_ORDER3, training)
         self._bn_f(self.ad_x[1], self.ad_h[1], 3, B, "attrs_decoder.net.4", _BN_ORDER3, training)
-        G([D(self.t1_h, p[f"{d}.3.weight"], self.colsT2, 3 * B * 64, 1024, 128),
-           D(self.ad_h[1], p["attrs_decoder.net.6.weight"], self.ad_x[2], 3 * B, 512, 512, bias=p["attrs_decoder.net.6.bias"])], P)
-        ops.col2im_k4(self.colsT2, self.t2_x, 3 * B, 8, 8, 64, 2, 1)
+        ad2 = D(self.ad_h[1], p["attrs_decoder.net.6.weight"], self.ad_x[2], 3 * B, 512, 512, bias=p["attrs_decoder.net.6.bias"])
+        if sub:
+            GC(ops.subpixel_k4s2p1(self.t1_h, p[f"{d}.3.weight"], self.t2_x, 3 * B, 8, 8, 128, 64) + [ad2])
+        else:
+            G([D(self.t1_h, p[f"{d}.3.weight"], self.colsT2, 3 * B * 64, 1024, 128), ad2], P)
+            ops.col2im_k4(self.colsT2, self.t2_x, 3 * B, 8, 8, 64, 2, 1)
         self._bn_f(self.t2_x, self.t2_h, 3, B * 256, f"{d}.4", _BN_ORDER3, training)
         self._bn_f(self.ad_x[2], self.ad_h[2], 3, B, "attrs_decoder.net.7", _BN_ORDER3, training)
-        G([D(self.t2_h, p[f"{d}.6.weight"], self.colsT3, 3 * B * 256, 512, 64),
-           D(self.ad_h[2], p["attrs_decoder.net.9.weight"], self.logit_a, 3 * B, N_ATTRS, 512, bias=p["attrs_decoder.net.9.bias"])], P)
-        ops.col2im_k4(self.colsT3, self.t3_x, 3 * B, 16, 16, 32, 2, 1)
+        ad3 = D(self.ad_h[2], p["attrs_decoder.net.9.weight"], self.logit_a, 3 * B, N_ATTRS, 512, bias=p["attrs_decoder.net.9.bias"])
+        if sub:
+            GC(ops.subpixel_k4s2p1(self.t2_h, p[f"{d}.6.weight"], self.t3_x, 3 * B, 16, 16, 64, 32) + [ad3])
+        else:
+            G([D(self.t2_h, p[f"{d}.6.weight"], self.colsT3, 3 * B * 256, 512, 64), ad3], P)
+            ops.col2im_k4(self.colsT3, self.t3_x, 3 * B, 16, 16, 32, 2, 1)
         self._bn_f(self.t3_x, self.t3_h, 3, B * 1024, f"{d}.7", _BN_ORDER3, training)
         G([D(self.t3_h, p[f"{d}.9.weight"], self.colsT4, 3 * B * 1024, 48, 32)], P)
         ops.col2im_k4(self.colsT4, self.logit_i, 3 * B, 32, 32, 3, 2, 1)
@@ -526,20 +539,31 @@ class CelebAMVAETrainer(MnistMVAETrainer):
         V = ops.conv_view
         G([D(self.d_c4x, self.c3_h if imp else self.cols4, g[f"{e}.8.weight"], 256, 2048, B * 25, a_mn=True, b_mn=True,
              split_k=sp(B * 25), accumulate=True, b_view=V(B, 8, 8, 128, stride=1, pad=0) if imp else None),
-           D(self.d_c4x, p[f"{e}.8.weight"], self.dcols4, B * 25, 2048, 256, b_mn=True),
+           ] + ([] if self.subpixel else [D(self.d_c4x, p[f"{e}.8.weight"], self.dcols4, B * 25, 2048, 256, b_mn=True)]) + [
            D(self.d_aex, self.a_in, g["attrs_encoder.net.0.weight"], 512, 20, B, a_mn=True, b_mn=True, split_k=sp(B),
              accumulate=True)], P)
-        ops.col2im_k4(self.dcols4, self.d_c3h, B, 5, 5, 128, 1, 0)
+        GC = lambda descs: ops.gemm_chain(descs, [-1] * len(descs), self.chain_ws, P)   # noqa: E731
+        if self.subpixel:
+            GC(ops.full_k4s1p0(self.d_c4x, p[f"{e}.8.weight"], self.d_c3h, B, 5, 5, 256, 128, w_is_conv=True))
+        else:
+            ops.col2im_k4(self.dcols4, self.d_c3h, B, 5, 5, 128, 1, 0)
         self._bn_b(self.c3_x, self.d_c3h, self.d_c3x, 1, B * 64, 0, 1, f"{e}.6")
         G([D(self.d_c3x, self.c2_h if imp else self.cols3, g[f"{e}.5.weight"], 128, 1024, B * 64, a_mn=True, b_mn=True,
              split_k=sp(B * 64), accumulate=True, b_view=V(B, 16, 16, 64) if imp else None),
-           D(self.d_c3x, p[f"{e}.5.weight"], self.dcols3, B * 64, 1024, 128, b_mn=True)], P)
-        ops.col2im_k4(self.dcols3, self.d_c2h, B, 8, 8, 64, 2, 1)
+           ] + ([] if self.subpixel else [D(self.d_c3x, p[f"{e}.5.weight"], self.dcols3, B * 64, 1024, 128, b_mn=True)]), P)
+        if self.subpixel:
+            GC(ops.subpixel_k4s2p1(self.d_c3x, p[f"{e}.5.weight"], self.d_c2h, B, 8, 8, 128, 64, w_is_conv=True))
+        else:
+            ops.col2im_k4(self.dcols3, self.d_c2h, B, 8, 8, 64, 2, 1)
         self._bn_b(self.c2_x, self.d_c2h, self.d_c2x, 1, B * 256, 0, 1, f"{e}.3")
         G([D(self.d_c2x, self.c1_h if imp else self.cols2, g[f"{e}.2.weight"], 64, 512, B * 256, a_mn=True, b_mn=True,
              split_k=sp(B * 256), accumulate=True, b_view=V(B, 32, 32, 32) if imp else None),
-           D(self.d_c2x, p[f"{e}.2.weight"], self.dcols2, B * 256, 512, 64, b_mn=True)], P)
-        ops.col2im_k4(self.dcols2, self.d_c1a, B, 16, 16, 32, 2, 1, aux=self.c1_a)
+           ] + ([] if self.subpixel else [D(self.d_c2x, p[f"{e}.2.weight"], self.dcols2, B * 256, 512, 64, b_mn=True)]), P)
+        if self.subpixel:
+            GC(ops.subpixel_k4s2p1(self.d_c2x, p[f"{e}.2.weight"], self.d_c1a, B, 16, 16, 64, 32, w_is_conv=True, aux=self.c1_a,
+                                   epilogue=ops.EPI_MUL_DSWISH))
+        else:
+            ops.col2im_k4(self.dcols2, self.d_c1a, B, 16, 16, 32, 2, 1, aux=self.c1_a)
         G([D(self.d_c1a, self.cols1, g[f"{e}.0.weight"], 32, 48, B * 1024, a_mn=True, b_mn=True, split_k=sp(B * 1024),
              accumulate=True)], P)
 

@@ -119,7 +119,7 @@ class FashionMVAETrainer(MnistMVAETrainer):
         self.implicit_conv = os.environ.get("MVAE_IMPLICIT_CONV", "1") != "0"
         # transposed convolutions (decoder forward, encoder data gradient) as four sub-pixel implicit GEMMs: no cols
         # buffers, no col2im passes (ops.subpixel_k4s2p1); MVAE_SUBPIXEL=0 restores GEMM -> cols -> col2im
-        self.subpixel = self.implicit_conv and os.environ.get("MVAE_SUBPIXEL", "0") != "0"
+        self.subpixel = self.implicit_conv and os.environ.get("MVAE_SUBPIXEL", "1") != "0"
         # image encoder (B rows), NHWC
         self.cols1 = f(B * 196, 16) if not self.direct_c1 else None
         self.c1_a, self.c1_h = f(B * 196, 64), f(B * 196, 64)

@@ -147,6 +147,37 @@ def test_subpixel_conv_data_gradient(ops, prec, B, H, C, Cout):
     wc = w.permute(0, 2, 3, 1).reshape(Cout, 16 * C).contiguous().cuda()                           # [co][(kh,kw,ci)]
     a_rows = a.permute(0, 2, 3, 1).reshape(B * H * H, C).contiguous().cuda()
     dx = torch.full((B * H * H, C), float("nan"), device="cuda")
-    descs = ops.subpixel_k4s2p1(dy.cuda(), wc, dx, B, OH, OH, Cout, C, w_is_conv=True, aux=a_rows, epilogue=ops.EPI_MUL_DSWISH)
+    dyd = dy.cuda()          # (descriptors hold raw pointers: the operand must outlive the launch)
+    descs = ops.subpixel_k4s2p1(dyd, wc, dx, B, OH, OH, Cout, C, w_is_conv=True, aux=a_rows, epilogue=ops.EPI_MUL_DSWISH)
     ops.gemm_chain(descs, [-1] * 4, ops.chain_workspace("cuda"), prec)
+    torch.cuda.synchronize()
     assert _rel(dx, a64.grad.permute(0, 2, 3, 1).reshape(B * H * H, C)) < TOL[prec] * 2
+
+
+@pytest.mark.parametrize("prec", [0, 1])
+@pytest.mark.parametrize("B,IH,Cin,Cout", [(3, 5, 256, 128), (50, 5, 256, 128), (4, 3, 64, 32)])
+def test_full_correlation_conv_transpose_k4s1p0(ops, prec, B, IH, Cin, Cout):
+    """ConvTranspose2d(k4 s1 p0) forward (celeba/model.py:117, 5x5 -> 8x8) and the data gradient of Conv2d(k4 s1 p0)
+    (:85, 8x8 <- 5x5) as ONE implicit GEMM each: 4x4 stride-1 view with lower corner -3 and the filter taps reversed."""
+    rs = np.random.RandomState(B + IH + 3)
+    OH = IH + 3
+    x = torch.from_numpy(rs.standard_normal((B, Cin, IH, IH)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((Cin, Cout, 4, 4)) / (16 * Cin) ** 0.5).astype(np.float32))
+    ref = F.conv_transpose2d(x.double(), w.double(), stride=1, padding=0).permute(0, 2, 3, 1).reshape(B * OH * OH, Cout)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    wt = w.permute(2, 3, 1, 0).reshape(16 * Cout, Cin).contiguous().cuda()                       # [(kh,kw,co)][ci]
+    y = torch.full((B * OH * OH, Cout), float("nan"), device="cuda")
+    ops.gemm_chain(ops.full_k4s1p0(x_nhwc, wt, y, B, IH, IH, Cin, Cout), [-1], ops.chain_workspace("cuda"), prec)
+    assert _rel(y, ref) < TOL[prec] * 2
+    # data gradient of a k4 s1 p0 convolution: d in [B,OH,OH,Cout'] from d out [B,IH,IH,Cin'] with Wc [Cin'][(kh,kw,Cout')]
+    a = torch.from_numpy(rs.standard_normal((B, Cout, OH, OH)).astype(np.float32)).double().requires_grad_(True)
+    wc = torch.from_numpy((rs.standard_normal((Cin, Cout, 4, 4)) / (16 * Cout) ** 0.5).astype(np.float32))   # Conv2d(Cout -> Cin)
+    out = F.conv2d(a, wc.double(), stride=1, padding=0)                                           # [B,Cin,IH,IH]
+    dy = torch.from_numpy(rs.standard_normal((B, IH, IH, Cin)).astype(np.float32))
+    (out.permute(0, 2, 3, 1) * dy.double()).sum().backward()
+    wcm = wc.permute(0, 2, 3, 1).reshape(Cin, 16 * Cout).contiguous().cuda()                      # [co][(kh,kw,ci)]
+    dx = torch.full((B * OH * OH, Cout), float("nan"), device="cuda")
+    dyd = dy.cuda()
+    ops.gemm_chain(ops.full_k4s1p0(dyd, wcm, dx, B, IH, IH, Cin, Cout, w_is_conv=True), [-1], ops.chain_workspace("cuda"), prec)
+    torch.cuda.synchronize()
+    assert _rel(dx, a.grad.permute(0, 2, 3, 1).reshape(B * OH * OH, Cout)) < TOL[prec] * 2

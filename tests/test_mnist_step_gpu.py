@@ -140,6 +140,8 @@ def test_full_size_properties():
         half.set_inputs(image[sl], text[sl], noise[:, sl], 0.5)
         with torch.cuda.stream(half._stream):
             half.grad_bucket.zero_(); half.zero_region.zero_()
+            if half.presplit:
+                T.ops.split_lo(half.flat_params, half.params_lo)
             half._enqueue_forward(True, True)
             half._enqueue_loss_and_backward(True, B)
             T.ops.elbo_finalize(half.acc[0:3], half.acc[3:6], half.acc[6:9], 3, half.lam_i, half.lam_t, 1.0, 1.0 / B,
