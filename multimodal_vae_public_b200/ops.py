@@ -155,7 +155,10 @@ def gemm_chain(descs: Sequence[GemmDesc], deps: Sequence[int], ws: torch.Tensor,
                "mvae_gemm_chain")
 
 
-def chain_workspace(device, ints: int = 16384) -> torch.Tensor:
+def chain_workspace(device, ints: int = 1 << 18) -> torch.Tensor:
+    """Counter workspace of mvae_gemm_chain: one int per 128-row block of every problem of a launch (+ 8 per output tile of a
+    fused split-K problem); 1 MiB covers the largest launches of the conv flavours (4 sub-pixel problems of 3 B x 32 x 32
+    rows at B = 1024: 24.6 K counters)."""
     return torch.zeros(ints, dtype=torch.int32, device=device)
 
 

@@ -237,6 +237,10 @@ class MnistMVAETrainer:
         self.loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self._graphs: Dict[Tuple[bool, bool], object] = {}
         self._stream = torch.cuda.Stream(device=dev)
+        # independent small kernels (the label encoder's class table, the label-side loss) run on a side stream next to
+        # the GEMM chains -- inside the captured graph they become parallel branches; MVAE_OVERLAP=0 serialises them
+        self._side_stream = torch.cuda.Stream(device=dev)
+        self.overlap = os.environ.get("MVAE_OVERLAP", "1") != "0"
         self.launches_per_step = 0
         self.init_parameters(seed)
 
@@ -287,6 +291,20 @@ class MnistMVAETrainer:
         # same launch (the wgrad of the layer above) still reads it
         self.id_dA = [f(2 * B, 512) for _ in range(3)]; self.td_dA = [f(2 * B, 512) for _ in range(3)]
         self.ie_dA = [f(B, 512) for _ in range(2)]; self.te_dA = [f(B, 512) for _ in range(2)]
+
+    # ------------------------------------------------------------------ parallel branches (side stream)
+    def _fork(self):
+        """Context manager: the enclosed launches go to the side stream, ordered after everything enqueued so far on the
+        step stream; ``_join()`` orders the step stream after them.  With MVAE_OVERLAP=0 a no-op (same stream)."""
+        import contextlib
+        if not self.overlap:
+            return contextlib.nullcontext()
+        self._side_stream.wait_stream(torch.cuda.current_stream())
+        return torch.cuda.stream(self._side_stream)
+
+    def _join(self) -> None:
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self._side_stream)
 
     # ------------------------------------------------------------------ GEMM problem helpers
     def _D(self, key: str, A, Bm, Cm, M: int, N: int, K: int, share: int = 1, **kw):
@@ -411,11 +429,13 @@ class MnistMVAETrainer:
         heads_t = S("heads_t", self.te_h2, wt, self.enc_t, B, 2 * L, 512, share=2, bias=bt)
         if self.label_table:
             emb, w2, b2, w3, b3 = self._label_encoder(0)
-            ops.label_table_fwd(emb, w2, b2, w3, b3, self.tt_a2, self.tt_h2, self.enc_tab)
+            with self._fork():      # (the class table needs 10 rows of work: next to the image encoder chain, not before it)
+                ops.label_table_fwd(emb, w2, b2, w3, b3, self.tt_a2, self.tt_h2, self.enc_tab)
             if self.chain:
                 ops.gemm_chain([fc1_i, fc2_i, heads_i], [-1, 0, 1], self.chain_ws, P)
             else:
                 ops.gemm_batch([fc1_i], P); ops.gemm_batch([fc2_i], P); ops.gemm_batch([heads_i], P)
+            self._join()
         else:
             ops.embedding_swish_fwd(p["text_encoder.fc1.weight"], self.text, None, self.te_h1)
         if self.label_table:
@@ -460,13 +480,15 @@ class MnistMVAETrainer:
         B, L, P = self.B, self.L, self.prec
         p, g = self.params, self.grads
         # reconstruction losses + dlogits (in place)
-        ops.bce_logits_fwd_bwd(self.logit_i, self.x, self.logit_i, self.lam_i / b_global, self.acc[0:3], seg_rows=B)
-        ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)
-        # ---- decoders backward, the two decoders batched per layer
         dyi, dyt = self.logit_i, self.logit_t
-        nk = max(1, (2 * B) // 32)  # k-blocks of a decoder wgrad
+        with self._fork():          # label term + its bias gradient next to the image term
+            ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)
+            ops.colsum_accumulate(dyt, g["text_decoder.fc4.bias"])
+        ops.bce_logits_fwd_bwd(self.logit_i, self.x, self.logit_i, self.lam_i / b_global, self.acc[0:3], seg_rows=B)
         ops.colsum_accumulate(dyi, g["image_decoder.fc4.bias"])
-        ops.colsum_accumulate(dyt, g["text_decoder.fc4.bias"])
+        self._join()
+        # ---- decoders backward, the two decoders batched per layer
+        nk = max(1, (2 * B) // 32)  # k-blocks of a decoder wgrad
         D = ops.gemm_desc
         S = (lambda key, *a, **k: self._D(key, *a, **k)) if self.chain else (lambda key, *a, share=1, **k: D(*a, **k))
         split = max(1, min(nk // 16, 32))   # ~16 k-blocks per wgrad tile, like the dgrad tiles of the same launch
@@ -539,14 +561,16 @@ class MnistMVAETrainer:
         wg_1i = D(self.ie_dA[1], self.x, g["image_encoder.fc1.weight"], 512, 784, B, a_mn=True, b_mn=True,
                   split_k=split, accumulate=True)
         if self.label_table:
-            # image encoder backward (one chained launch), then the label encoder's backward on its class table
+            # the label encoder's backward on its class table (side stream) next to the image encoder's chained backward
+            emb, w2, _, w3, _ = self._label_encoder(0)
+            g_emb, g_w2, g_b2, g_w3, g_b3 = self._label_encoder(1)
+            with self._fork():
+                ops.label_table_bwd(emb, w2, w3, self.tt_a2, self.tt_h2, self.d_tab, self.tt_dA2, g_emb, g_w2, g_b2, g_w3, g_b3)
             if self.chain:
                 ops.gemm_chain([dg_hi, wg_hi, dg_2i, wg_2i, wg_1i], [-1, -1, 0, 0, 2], self.chain_ws, P)
             else:
                 ops.gemm_batch([wg_hi, dg_hi], P); ops.gemm_batch([wg_2i, dg_2i], P); ops.gemm_batch([wg_1i], P)
-            emb, w2, _, w3, _ = self._label_encoder(0)
-            g_emb, g_w2, g_b2, g_w3, g_b3 = self._label_encoder(1)
-            ops.label_table_bwd(emb, w2, w3, self.tt_a2, self.tt_h2, self.d_tab, self.tt_dA2, g_emb, g_w2, g_b2, g_w3, g_b3)
+            self._join()
             return
         if self.chain:   # both encoders' backward: one launch
             ops.gemm_chain([dg_hi, dg_ht, wg_hi, wg_ht, dg_2i, dg_2t, wg_2i, wg_2t, wg_1i],

@@ -197,9 +197,10 @@ class FashionMVAETrainer(MnistMVAETrainer):
         if not imp:
             ops.im2col_k4s2p1(self.c1_h, self.cols2, B, 14, 14, 64)
         lt = self.label_table
-        if lt:   # label encoder once per class (csrc/label_table.cu); the PoE kernels gather row text[b]
+        if lt:   # label encoder once per class (csrc/label_table.cu, side stream); the PoE kernels gather row text[b]
             emb, w2, b2, w3, b3 = self._label_encoder(0)
-            ops.label_table_fwd(emb, w2, b2, w3, b3, self.tt_a2, self.tt_h2, self.enc_tab)
+            with self._fork():
+                ops.label_table_fwd(emb, w2, b2, w3, b3, self.tt_a2, self.tt_h2, self.enc_tab)
         else:
             ops.embedding_swish_fwd(p["text_encoder.net.0.weight"], self.text, None, self.te_h1)
         ops.gemm_batch([
@@ -216,6 +217,7 @@ class FashionMVAETrainer(MnistMVAETrainer):
         self._gemm([self._D("cls2", self.fc_h, p["image_encoder.classifier.2.weight"], self.enc_i, B, 2 * L, 512,
                             bias=p["image_encoder.classifier.2.bias"])])
         # ---- PoE + reparametrise + KL (three passes)
+        self._join()
         mu_e, lv_e, _, _, gather = self._label_experts()
         ops.poe_fwd(mu_e, lv_e, _PASS_MASKS, B, L, self.Z, variant=0, training=training,
                     noise=self.noise if (training and use_noise_input) else None,
@@ -263,8 +265,10 @@ class FashionMVAETrainer(MnistMVAETrainer):
         def split_for(rows):   # ~16 k-blocks (512 rows) per wgrad tile, as many tiles as the reduction needs
             return max(1, min(rows // 512, 4096))
 
+        with self._fork():
+            ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)
         ops.bce_logits_fwd_bwd(self.logit_i, self.x, self.logit_i, self.lam_i / b_global, self.acc[0:3], seg_rows=B)
-        ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)
+        self._join()
         # ---- last layers: convT2 (image) and net.6 (text)
         direct = self.direct_c1_bwd
         ops.colsum_accumulate(self.logit_t, g["text_decoder.net.6.bias"])
@@ -350,7 +354,8 @@ class FashionMVAETrainer(MnistMVAETrainer):
         if lt:
             emb, w2, _, w3, _ = self._label_encoder(0)
             g_emb, g_w2, g_b2, g_w3, g_b3 = self._label_encoder(1)
-            ops.label_table_bwd(emb, w2, w3, self.tt_a2, self.tt_h2, self.d_tab, self.tt_dA2, g_emb, g_w2, g_b2, g_w3, g_b3)
+            with self._fork():     # joined at the end of the backward pass
+                ops.label_table_bwd(emb, w2, w3, self.tt_a2, self.tt_h2, self.d_tab, self.tt_dA2, g_emb, g_w2, g_b2, g_w3, g_b3)
         else:
             ops.embedding_swish_bwd(p["text_encoder.net.0.weight"], self.text, self.te_dA[1], g["text_encoder.net.0.weight"])
         # ---- conv2
@@ -372,3 +377,4 @@ class FashionMVAETrainer(MnistMVAETrainer):
         else:
             ops.gemm_batch([ops.gemm_desc(self.d_c1, self.cols1, g["image_encoder.features.0.weight"], 64, 16, B * 196,
                                           a_mn=True, b_mn=True, split_k=split_for(B * 196), accumulate=True)], P)
+        self._join()
