@@ -372,11 +372,18 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         G([D(self.d0_h[: P * B].view(P * B * 25, 256), p[f"{d}.0.weight"], self.colsT1[: P * B * 25], P * B * 25, 2048, 256)], Pp)
         ops.col2im_k4(self.colsT1, self.t1_x, P * B, 5, 5, 128, 1, 0)
         self._bn_f(self.t1_x[: P * B * 64], self.t1_h[: P * B * 64], P, B * 64, f"{d}.1", bo, training)
-        G([D(self.t1_h[: P * B * 64], p[f"{d}.3.weight"], self.colsT2[: P * B * 64], P * B * 64, 1024, 128)], Pp)
-        ops.col2im_k4(self.colsT2, self.t2_x, P * B, 8, 8, 64, 2, 1)
+        GC = lambda descs: ops.gemm_chain(descs, [-1] * len(descs), self.chain_ws, Pp)   # noqa: E731
+        if self.subpixel:   # stride-2 transposed convs as four sub-pixel implicit GEMMs (no cols, no col2im)
+            GC(ops.subpixel_k4s2p1(self.t1_h, p[f"{d}.3.weight"], self.t2_x, P * B, 8, 8, 128, 64))
+        else:
+            G([D(self.t1_h[: P * B * 64], p[f"{d}.3.weight"], self.colsT2[: P * B * 64], P * B * 64, 1024, 128)], Pp)
+            ops.col2im_k4(self.colsT2, self.t2_x, P * B, 8, 8, 64, 2, 1)
         self._bn_f(self.t2_x[: P * B * 256], self.t2_h[: P * B * 256], P, B * 256, f"{d}.4", bo, training)
-        G([D(self.t2_h[: P * B * 256], p[f"{d}.6.weight"], self.colsT3[: P * B * 256], P * B * 256, 512, 64)], Pp)
-        ops.col2im_k4(self.colsT3, self.t3_x, P * B, 16, 16, 32, 2, 1)
+        if self.subpixel:
+            GC(ops.subpixel_k4s2p1(self.t2_h, p[f"{d}.6.weight"], self.t3_x, P * B, 16, 16, 64, 32))
+        else:
+            G([D(self.t2_h[: P * B * 256], p[f"{d}.6.weight"], self.colsT3[: P * B * 256], P * B * 256, 512, 64)], Pp)
+            ops.col2im_k4(self.colsT3, self.t3_x, P * B, 16, 16, 32, 2, 1)
         self._bn_f(self.t3_x[: P * B * 1024], self.t3_h[: P * B * 1024], P, B * 1024, f"{d}.7", bo, training)
         R = NI * B                                     # image logits: only the passes whose loss has an image term
         G([D(self.t3_h[: R * 1024], p[f"{d}.9.weight"], self.colsT4[: R * 1024], R * 1024, 48, 32)], Pp)
@@ -518,13 +525,20 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         self._bn_b(self.c3_x, self.d_c3h, self.d_c3x, 1, B * 64, 0, 1, f"{e}.6")
         G([D(self.d_c3x, self.c2_h if imp else self.cols3, g[f"{e}.5.weight"], 128, 1024, B * 64, a_mn=True, b_mn=True,
              split_k=sp(B * 64), accumulate=True, b_view=V(B, 16, 16, 64) if imp else None),
-           D(self.d_c3x, p[f"{e}.5.weight"], self.dcols3, B * 64, 1024, 128, b_mn=True)], Pp)
-        ops.col2im_k4(self.dcols3, self.d_c2h, B, 8, 8, 64, 2, 1)
+           ] + ([] if self.subpixel else [D(self.d_c3x, p[f"{e}.5.weight"], self.dcols3, B * 64, 1024, 128, b_mn=True)]), Pp)
+        if self.subpixel:
+            GC(ops.subpixel_k4s2p1(self.d_c3x, p[f"{e}.5.weight"], self.d_c2h, B, 8, 8, 128, 64, w_is_conv=True))
+        else:
+            ops.col2im_k4(self.dcols3, self.d_c2h, B, 8, 8, 64, 2, 1)
         self._bn_b(self.c2_x, self.d_c2h, self.d_c2x, 1, B * 256, 0, 1, f"{e}.3")
         G([D(self.d_c2x, self.c1_h if imp else self.cols2, g[f"{e}.2.weight"], 64, 512, B * 256, a_mn=True, b_mn=True,
              split_k=sp(B * 256), accumulate=True, b_view=V(B, 32, 32, 32) if imp else None),
-           D(self.d_c2x, p[f"{e}.2.weight"], self.dcols2, B * 256, 512, 64, b_mn=True)], Pp)
-        ops.col2im_k4(self.dcols2, self.d_c1a, B, 16, 16, 32, 2, 1, aux=self.c1_a)
+           ] + ([] if self.subpixel else [D(self.d_c2x, p[f"{e}.2.weight"], self.dcols2, B * 256, 512, 64, b_mn=True)]), Pp)
+        if self.subpixel:
+            GC(ops.subpixel_k4s2p1(self.d_c2x, p[f"{e}.2.weight"], self.d_c1a, B, 16, 16, 64, 32, w_is_conv=True, aux=self.c1_a,
+                                   epilogue=ops.EPI_MUL_DSWISH))
+        else:
+            ops.col2im_k4(self.dcols2, self.d_c1a, B, 16, 16, 32, 2, 1, aux=self.c1_a)
         G([D(self.d_c1a, self.cols1, g[f"{e}.0.weight"], 32, 48, B * 1024, a_mn=True, b_mn=True, split_k=sp(B * 1024),
              accumulate=True)], Pp)
         # ================================================================ exchange + update
