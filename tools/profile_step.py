@@ -1,7 +1,8 @@
 """Run a few eager (non-graph) training steps / single kernels for ncu captures.
    python tools/profile_step.py step [--steps N] [--batch B] [--prec 0|1]
    python tools/profile_step.py gemm  fwd|dgrad|wgrad  prec  M N K [iters]
-   python tools/profile_step.py bce R D [iters]"""
+   python tools/profile_step.py bce R D [iters]
+   python tools/profile_step.py poe B L [iters]"""
 import os
 import sys
 
@@ -43,6 +44,20 @@ def main():
         acc = torch.zeros(2, dtype=torch.float64, device="cuda")
         for _ in range(iters):
             ops.bce_logits_fwd_bwd(x, t, dx, 1e-3, acc, seg_rows=R // 2)
+        torch.cuda.synchronize()
+    elif mode == "poe":
+        # roofline-size run of the fused PoE + reparametrise + KL kernels (MNIST pass structure): poe B L [iters]
+        B, L = int(sys.argv[2]), int(sys.argv[3]); iters = int(sys.argv[4]) if len(sys.argv) > 4 else 4
+        enc = [torch.randn(B, 2 * L, device="cuda") * 0.5 for _ in range(2)]
+        mu_e = [e[:, :L] for e in enc]; lv_e = [e[:, L:] for e in enc]
+        z = torch.empty(3 * B, L, device="cuda"); nz = torch.empty(3 * B, L, device="cuda"); dz = torch.randn(3 * B, L, device="cuda")
+        d_enc = [torch.empty(B, 2 * L, device="cuda") for _ in range(2)]
+        kl = torch.zeros(3, dtype=torch.float64, device="cuda"); stepc = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for _ in range(iters):
+            ops.poe_fwd(mu_e, lv_e, (1, 3, 2), B, L, z, variant=0, training=True, noise=None, noise_out=nz, seed=1, step_dev=stepc,
+                        kl_acc=kl)
+            ops.poe_bwd(mu_e, lv_e, (1, 3, 2), B, L, dz, [d[:, :L] for d in d_enc], [d[:, L:] for d in d_enc], kl_scale=1.0 / B,
+                        variant=0, training=True, noise=nz)
         torch.cuda.synchronize()
 
 
