@@ -163,9 +163,17 @@ __device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
 // ---- MUFU forms for the bandwidth-bound fast path (ex2 / lg2 / rcp / sqrt: <= 2 ulp each; the outputs are compared
 // against the fp64 oracle at rtol 2e-5, tests/test_kernels_gpu.py).  The IEEE expf / logf / division forms cost ~10-20
 // instructions each and made these kernels instruction-bound: 1.9 TB/s at roofline size (profiles/r02_bench_v0_*).
-__device__ __forceinline__ float fexp(float x) { return __expf(x); }
-__device__ __forceinline__ float flog(float x) { return __logf(x); }
-__device__ __forceinline__ float frcp(float x) { return __fdividef(1.0f, x); }
+// The .ftz PTX forms are used directly: without -ftz the __expf / __logf / sqrtf intrinsics carry a denormal guard (scale,
+// select, sometimes a slow-path call) around every MUFU, which doubled the instruction count of these kernels
+// (profiles/r02_poe_raw_key_metrics.txt: 1120 instructions per 4-latent item, issue slots 66 % busy, DRAM 37 %).
+__device__ __forceinline__ float fex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float flg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float frcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fsqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fsin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fcos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fexp(float x) { return fex2(x * 1.4426950408889634f); }
+__device__ __forceinline__ float flog(float x) { return flg2(x) * 0.6931471805599453f; }
 
 // Four N(0,1) draws from one Philox4x32-10 block, Box-Muller with MUFU log / sin / cos (|error| ~ 1e-6 on the draws:
 // irrelevant for noise; the stream stays a pure function of (seed, counter, step)).
@@ -176,11 +184,10 @@ __device__ __forceinline__ void normal4_fast(uint64_t seed, uint64_t ctr, uint32
   const float u1 = (static_cast<float>(c[1]) + 0.5f) * 2.3283064365386963e-10f;
   const float u2 = (static_cast<float>(c[2]) + 0.5f) * 2.3283064365386963e-10f;
   const float u3 = (static_cast<float>(c[3]) + 0.5f) * 2.3283064365386963e-10f;
-  const float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
-  float s0, c0, s1, c1;
-  __sincosf(6.283185307179586f * u1 - 3.141592653589793f, &s0, &c0);   // argument in [-pi, pi): MUFU range, full circle
-  __sincosf(6.283185307179586f * u3 - 3.141592653589793f, &s1, &c1);
-  n[0] = r0 * c0; n[1] = r0 * s0; n[2] = r1 * c1; n[3] = r1 * s1;
+  const float r0 = fsqrt(-1.3862943611198906f * flg2(u0)), r1 = fsqrt(-1.3862943611198906f * flg2(u2));   // -2 ln u
+  const float t0 = 6.283185307179586f * u1 - 3.141592653589793f;        // argument in [-pi, pi): MUFU range, full circle
+  const float t1 = 6.283185307179586f * u3 - 3.141592653589793f;
+  n[0] = r0 * fcos(t0); n[1] = r0 * fsin(t0); n[2] = r1 * fcos(t1); n[3] = r1 * fsin(t1);
 }
 
 constexpr int kFastPasses = 4;   // passes whose KL partial sums a thread keeps in registers on the fast path
@@ -199,10 +206,14 @@ __global__ void __launch_bounds__(256, 3) poe_fwd_fast_kernel(const __grid_const
   const float T0 = a.no_prior ? 0.0f : 1.0f / ((1.0f + e1) + e2);  // prior expert: mu = 0, logvar = 0
   const uint32_t step = (a.training && a.noise == nullptr && a.step_dev) ? static_cast<uint32_t>(__ldg(a.step_dev)) : 0u;
   float klacc[kFastPasses] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total;
-       gid += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(gid / l4n);
-    const int l = static_cast<int>(gid - static_cast<int64_t>(b) * l4n) * 4;
+  // (b, l4) walk the grid-stride sequence incrementally: one 64-bit division per thread, none per item
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int db = static_cast<int>(stride / l4n), dl = static_cast<int>(stride - static_cast<int64_t>(db) * l4n);
+  int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int b = static_cast<int>(gid / l4n), l4 = static_cast<int>(gid - static_cast<int64_t>(b) * l4n);
+  for (; gid < total; gid += stride, b += db, l4 += dl) {
+    if (l4 >= l4n) { l4 -= l4n; ++b; }
+    const int l = l4 * 4;
     float T[EMAX][4], M[EMAX][4];
 #pragma unroll
     for (int e = 0; e < EMAX; ++e) {
@@ -253,7 +264,7 @@ __global__ void __launch_bounds__(256, 3) poe_fwd_fast_kernel(const __grid_const
           mu[q] = N[q] * pv;
           const float ev = pv + e2;                 // = exp(logvar) of the fused posterior
           lv[q] = flog(ev);
-          z[q] = a.training ? nz[q] * sqrtf(ev) + mu[q] : mu[q];        // exp(0.5 logvar) = sqrt(exp(logvar))
+          z[q] = a.training ? nz[q] * fsqrt(ev) + mu[q] : mu[q];        // exp(0.5 logvar) = sqrt(exp(logvar))
           klf += 1.0f + lv[q] - mu[q] * mu[q] - ev;
         }
         klacc[p] += -0.5f * klf;
@@ -278,10 +289,14 @@ __global__ void __launch_bounds__(256, 3) poe_bwd_fast_kernel(const __grid_const
   const float e2 = a.variant == 0 ? 1e-8f : 0.0f;
   const float kls = a.kl_scale * (a.kl_scale_dev ? __ldg(a.kl_scale_dev) : 1.0f);
   const float T0 = a.no_prior ? 0.0f : 1.0f / ((1.0f + e1) + e2);
-  for (int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total;
-       gid += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int b = static_cast<int>(gid / l4n);
-    const int l = static_cast<int>(gid - static_cast<int64_t>(b) * l4n) * 4;
+  // (b, l4) walk the grid-stride sequence incrementally: one 64-bit division per thread, none per item
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int db = static_cast<int>(stride / l4n), dl = static_cast<int>(stride - static_cast<int64_t>(db) * l4n);
+  int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int b = static_cast<int>(gid / l4n), l4 = static_cast<int>(gid - static_cast<int64_t>(b) * l4n);
+  for (; gid < total; gid += stride, b += db, l4 += dl) {
+    if (l4 >= l4n) { l4 -= l4n; ++b; }
+    const int l = l4 * 4;
     float T[EMAX][4], MU[EMAX][4], EX[EMAX][4], dMU[EMAX][4], dLV[EMAX][4];
     int64_t erow[EMAX];
 #pragma unroll
@@ -330,7 +345,7 @@ __global__ void __launch_bounds__(256, 3) poe_bwd_fast_kernel(const __grid_const
           const float ev = pv + e2;                                 // exp(logvar)
           g_mu[q] = dz[q] + gmu_up[q] + kls * mu[q];
           float g_lv = glv_up[q] + kls * 0.5f * (ev - 1.0f);
-          if (a.training) g_lv += dz[q] * nz[q] * 0.5f * sqrtf(ev);
+          if (a.training) g_lv += dz[q] * nz[q] * 0.5f * fsqrt(ev);
           g_lvS[q] = g_lv * (-(pv * pv) * frcp(ev));                // d logvar / d S
         }
 #pragma unroll
