@@ -42,11 +42,14 @@ def conv_view(N, H, W, Cch, taps=4, stride=2, pad=1, lower=None, upper=None) -> 
 
 # Pre-split weights (3xTF32): arenas registered here hold parameters whose low halves (x - trunc_tf32(x)) live at the same
 # offset in a twin buffer, refreshed once per step by split_lo(); gemm_desc() then hands the GEMM the twin of any B operand
-# that points into a registered arena (weights are the B operand of every forward / dgrad problem).
-_LO_ARENAS = []      # (base_ptr, end_ptr, lo_base_ptr)
+# that points into a registered arena (weights are the B operand of every forward / dgrad problem).  ``max_n`` restricts
+# this to problems with N <= max_n: narrow tiles (N <= 64) are paced by the operand-splitter warps, whose B pass costs as
+# much as for a 128-wide tile while the TMA moves only half the bytes, so fetching B_lo pays there -- and only there
+# (profiles/r02_notes.md section 6).
+_LO_ARENAS = []      # (base_ptr, end_ptr, lo_base_ptr, max_n)
 
 
-def register_lo_arena(params: torch.Tensor, lo: torch.Tensor) -> None:
+def register_lo_arena(params: torch.Tensor, lo: torch.Tensor, max_n: int = 0) -> None:
     if params.numel() != lo.numel() or params.dtype != torch.float32 or lo.dtype != torch.float32:
         raise _lib.MvaeError("register_lo_arena: params / lo must be fp32 buffers of the same size")
     b0, e0 = params.data_ptr(), params.data_ptr() + params.numel() * 4
@@ -56,7 +59,7 @@ def register_lo_arena(params: torch.Tensor, lo: torch.Tensor) -> None:
     _LO_ARENAS[:] = [a for a in _LO_ARENAS
                      if not (a[0] < e0 and b0 < a[1]) and not (a[2] < l1 and l0 < a[2] + (a[1] - a[0]))
                      and not (a[0] < l1 and l0 < a[1]) and not (a[2] < e0 and b0 < a[2] + (a[1] - a[0]))]
-    _LO_ARENAS.append((b0, e0, l0))
+    _LO_ARENAS.append((b0, e0, l0, int(max_n)))
 
 
 def unregister_lo_arena(params: torch.Tensor) -> None:
@@ -82,8 +85,8 @@ def gemm_desc(A, B, Cmat, M, N, K, a_mn=False, b_mn=False, bias=None, aux=None, 
     if rowmap is not None:
         d.rowmap_IH, d.rowmap_IW, d.rowmap_s, d.rowmap_py, d.rowmap_px = rowmap
     bp = B.data_ptr()
-    for base, end, lo_base in _LO_ARENAS:
-        if base <= bp < end and b_view is None:
+    for base, end, lo_base, max_n in _LO_ARENAS:
+        if base <= bp < end and b_view is None and (max_n == 0 or N <= max_n):
             d.B_lo = lo_base + (bp - base)
             break
     d.A, d.lda, d.a_mn_major = A.data_ptr(), (A.stride(0) if a_view is None else 0), int(a_mn)

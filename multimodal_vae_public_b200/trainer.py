@@ -186,15 +186,18 @@ class MnistMVAETrainer:
         self.grads = {k: self.arena.view(1, k) for k, _ in self.layout}
         n = self.arena.numel
         self.flat_params, self.adam_m, self.adam_v = (self.arena.buffers[i][:n] for i in (0, 2, 3))
-        # pre-split weights (3xTF32), OPT-IN (MVAE_PRESPLIT=1): low halves of the parameters in a twin buffer, refreshed once
-        # per step and fetched by TMA as the GEMMs' B_lo operand (ops.register_lo_arena) instead of being computed by the
-        # splitter warps per tile and k-block.  Bit-identical results, but measured SLOWER on the same box (MNIST 0.727 vs
-        # 0.713 ms/step, FashionMNIST 6.70 vs 6.49): the extra 16 KiB of L2 -> shared-memory traffic per k-block costs more
-        # than the 300 splitter cycles it removes (profiles/r02_ab_mnist_fashion.txt) -- the loop is L2-feed / smem bound.
-        self.presplit = precision == PREC_3XTF32 and os.environ.get("MVAE_PRESPLIT", "0") != "0"
+        # pre-split weights (3xTF32): low halves of the parameters in a twin buffer, refreshed once per step and fetched by
+        # TMA as the GEMMs' B_lo operand (ops.register_lo_arena) instead of being computed by the splitter warps per tile and
+        # k-block.  Bit-identical results.  For 128-wide tiles it measured SLOWER on the same box (MNIST 0.727 vs 0.713
+        # ms/step, FashionMNIST 6.70 vs 6.49: the extra 16 KiB of L2 -> shared-memory traffic per k-block costs more than
+        # the ~300 splitter cycles it removes, profiles/r02_ab_mnist_fashion.txt); for narrow tiles (N <= 64: the sub-pixel
+        # transposed convolutions of the conv flavours) the splitters pace the loop and B_lo is only 8 KiB.
+        # MVAE_PRESPLIT = 0 (off) | 1 (every weight operand) | narrow (problems with N <= 64 only); flavour default below.
+        mode = os.environ.get("MVAE_PRESPLIT", self._presplit_default)
+        self.presplit = precision == PREC_3XTF32 and mode != "0"
         if self.presplit:
             self.params_lo = torch.zeros(n, dtype=torch.float32, device=self.dev)
-            ops.register_lo_arena(self.flat_params, self.params_lo)
+            ops.register_lo_arena(self.flat_params, self.params_lo, max_n=64 if mode == "narrow" else 0)
         self.grad_bucket = self.arena.buffers[1]          # gradients + 4 loss floats: the all-reduce payload
         self.flat_grads = self.grad_bucket[:n]
         B, L, dev = batch_size, n_latents, self.dev
@@ -243,6 +246,8 @@ class MnistMVAETrainer:
         self.overlap = os.environ.get("MVAE_OVERLAP", "1") != "0"
         self.launches_per_step = 0
         self.init_parameters(seed)
+
+    _presplit_default = "0"
 
     def __del__(self):
         try:
