@@ -33,10 +33,13 @@ POOL = 16                      # rotating pool of distinct input batches (> L2: 
 LAMBDA_IMAGE, LAMBDA_TEXT = 1.0, 10.0
 ANNEAL_EPOCHS, N_MINI = 200, 15  # KL annealing schedule of mnist/train.py:180-186 with 60000/4096 ~ 15 batches/epoch
 
-# DRAM traffic per launch from the committed ncu captures (profiles/): the four chained GEMM launches of one MNIST B=4096
-# step moved 31.1 + 197.6 + 501.3 + 92.9 MB; the roofline-size BCE launch 308.3 MB read + 157.3 MB written
-GEMM_CHAIN_DRAM_BYTES_PER_LAUNCH = (31.07e6 + 197.58e6 + 501.33e6 + 92.89e6) / 4
-BCE_DRAM_BYTES_PER_LAUNCH = 308.29e6 + 157.27e6
+# DRAM traffic per launch from the committed round-2 ncu captures (profiles/r02_*_raw_key_metrics.txt): the four chained GEMM
+# launches of one MNIST B=4096 step moved 16.1 + 202.6 + 492.9 + 54.9 MB; the roofline-size BCE launch 308.3 MB read +
+# 152.3 MB written; the roofline-size PoE launches 268.5 + 352.8 MB (forward) and 671.1 + 247.7 MB (backward)
+GEMM_CHAIN_DRAM_BYTES_PER_LAUNCH = (16.14e6 + 202.64e6 + 492.93e6 + 54.89e6) / 4
+BCE_DRAM_BYTES_PER_LAUNCH = 308.29e6 + 152.33e6
+POE_FWD_DRAM_BYTES_PER_LAUNCH = 268.48e6 + 352.78e6
+POE_BWD_DRAM_BYTES_PER_LAUNCH = 671.12e6 + 247.67e6
 
 # algorithmic work per sample per step
 FLOP_PER_SAMPLE_REFERENCE = 32.4e6     # everything the reference executes (incl. dead decoder passes, duplicate encoders)
@@ -467,7 +470,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "traffic": GEMM_CHAIN_DRAM_BYTES_PER_LAUNCH if (wl == "mnist" and main["chain"] and
                                                                          b_local == BATCH) else None,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum averaged over the "
-                                           "4 chained GEMM launches of one B=4096 step (profiles/r01_gemm_chain_v5_raw_key_metrics.txt)",
+                                           "4 chained GEMM launches of one B=4096 step (profiles/r02_gemm_chain_raw_key_metrics.txt)",
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained/2 (tf32 rate = half bf16) [{peaks['source']}]",
                          "algorithmic_flops_per_launch_avg": gemm["algorithmic_flops_per_step"] / max(gemm["launches"], 1),
                          "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms_per_step"] / max(gemm["launches"], 1),
@@ -615,7 +618,7 @@ def measure_rooflines(tr, dev, prec, wl, world, micro=True):
                                             f"one target), roofline-size run R={R} D={D}",
                   "achieved": alg / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
                   "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": BCE_DRAM_BYTES_PER_LAUNCH,
-                  "traffic_source": "ncu --set full of this launch (profiles/r01_bce_stacked_v5_raw_key_metrics.txt): below the "
+                  "traffic_source": "ncu --set full of this launch (profiles/r02_bce_raw_key_metrics.txt): below the "
                                     "algorithmic bytes because part of the gradient write-back is still in L2 when the kernel ends",
                   "algorithmic_bytes_per_launch": alg, "avg_launch_ms": ms, "peak_source": peaks["source"]}
     del x, t, dx
@@ -636,8 +639,9 @@ def measure_rooflines(tr, dev, prec, wl, world, micro=True):
     # passes; bwd reads the experts, dz and the noise, writes 2 experts x (dmu, dlogvar).  SURVEY 8d's algorithmic
     # figure counts every pass separately (4,352 / 7,168 B per sample) -- both fractions are reported.
     moved_f, moved_b = (4 * L + 6 * L) * 4, (4 * L + 6 * L + 4 * L) * 4
-    for key, ms_k, moved, alg_b, name in (("hbm_poe_fwd", ms_f, moved_f, POE_FWD_BYTES_PER_SAMPLE, "poe_fwd_kernel"),
-                                          ("hbm_poe_bwd", ms_b, moved_b, POE_BWD_BYTES_PER_SAMPLE, "poe_bwd_kernel")):
+    for key, ms_k, moved, alg_b, name, dram in (
+            ("hbm_poe_fwd", ms_f, moved_f, POE_FWD_BYTES_PER_SAMPLE, "poe_fwd_fast_kernel", POE_FWD_DRAM_BYTES_PER_LAUNCH),
+            ("hbm_poe_bwd", ms_b, moved_b, POE_BWD_BYTES_PER_SAMPLE, "poe_bwd_fast_kernel", POE_BWD_DRAM_BYTES_PER_LAUNCH)):
         out[key] = {"bound": "hbm", "kernel": f"{name} (PoE + reparametrise + KL, 3 passes in one launch), roofline-size run "
                                               f"B={Bp} L={L}",
                     "achieved": moved * Bp / (ms_k * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -645,7 +649,9 @@ def measure_rooflines(tr, dev, prec, wl, world, micro=True):
                     "achieved_algorithmic": alg_b * Bp / (ms_k * 1e-3) / 1e9,
                     "frac_algorithmic": alg_b * Bp / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "bytes_moved_per_launch": moved * Bp, "algorithmic_bytes_per_launch": alg_b * Bp,
-                    "avg_launch_ms": ms_k, "traffic": None, "peak_source": peaks["source"]}
+                    "avg_launch_ms": ms_k, "traffic": dram,
+                    "traffic_source": "ncu --set full of this launch (profiles/r02_poe_raw_key_metrics.txt)",
+                    "peak_source": peaks["source"]}
     del enc, z, nz, dz, d_enc
     return out
 
