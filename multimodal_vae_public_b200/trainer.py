@@ -311,6 +311,20 @@ class MnistMVAETrainer:
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self._side_stream)
 
+    def _side_mark(self):
+        """Inside a ``_fork()`` block: an event after the side-stream work enqueued so far, for ``_wait_mark`` -- the step
+        stream can then wait for THAT work only while later side-stream launches (bias-gradient column sums, which nothing
+        but the optimizer reads) keep running beside the next GEMM chain until the final ``_join()``."""
+        if not self.overlap:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self._side_stream)
+        return ev
+
+    def _wait_mark(self, ev) -> None:
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
     # ------------------------------------------------------------------ GEMM problem helpers
     def _D(self, key: str, A, Bm, Cm, M: int, N: int, K: int, share: int = 1, **kw):
         """``ops.gemm_desc`` for a forward / dgrad problem, with FUSED SPLIT-K chosen automatically when the problem has
@@ -486,12 +500,14 @@ class MnistMVAETrainer:
         p, g = self.params, self.grads
         # reconstruction losses + dlogits (in place)
         dyi, dyt = self.logit_i, self.logit_t
-        with self._fork():          # label term + its bias gradient next to the image term
+        with self._fork():          # label term next to the image term
             ops.ce_fwd_bwd(self.logit_t, self.text, self.logit_t, 10, self.lam_t / b_global, self.acc[4:6], seg_rows=B)
+            ce_done = self._side_mark()
             ops.colsum_accumulate(dyt, g["text_decoder.fc4.bias"])
         ops.bce_logits_fwd_bwd(self.logit_i, self.x, self.logit_i, self.lam_i / b_global, self.acc[0:3], seg_rows=B)
-        ops.colsum_accumulate(dyi, g["image_decoder.fc4.bias"])
-        self._join()
+        with self._fork():          # the last layers' bias gradients: beside the decoder backward chain, joined at the end
+            ops.colsum_accumulate(dyi, g["image_decoder.fc4.bias"])
+        self._wait_mark(ce_done)
         # ---- decoders backward, the two decoders batched per layer
         nk = max(1, (2 * B) // 32)  # k-blocks of a decoder wgrad
         D = ops.gemm_desc
@@ -547,9 +563,10 @@ class MnistMVAETrainer:
         gbt = arena.span(1, "text_encoder.fc31.bias", "text_encoder.fc32.bias")
         wi = arena.span(0, "image_encoder.fc31.weight", "image_encoder.fc32.weight").view(2 * L, 512)
         wt = arena.span(0, "text_encoder.fc31.weight", "text_encoder.fc32.weight").view(2 * L, 512)
-        ops.colsum_accumulate(self.d_enc_i, gbi)
-        if not self.label_table:
-            ops.colsum_accumulate(self.d_enc_t, gbt)
+        with self._fork():          # bias gradients of the encoder heads: beside the encoder backward chain
+            ops.colsum_accumulate(self.d_enc_i, gbi)
+            if not self.label_table:
+                ops.colsum_accumulate(self.d_enc_t, gbt)
         wg_hi = D(self.d_enc_i, self.ie_h2, gwi, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True)
         wg_ht = D(self.d_enc_t, self.te_h2, gwt, 2 * L, 512, B, a_mn=True, b_mn=True, split_k=split, accumulate=True)
         dg_hi = D(self.d_enc_i, wi, self.ie_dA[0], B, 512, 2 * L, b_mn=True, aux=self.ie_a2,
@@ -594,6 +611,7 @@ class MnistMVAETrainer:
             ops.split_lo(self.flat_params, self.params_lo)
         self._enqueue_forward(training, use_noise_input)
         self._enqueue_loss_and_backward(training, b_global)
+        self._join()                # side-stream bias-gradient sums / label-table backward
         ops.elbo_finalize(self.acc[0:3], self.acc[3:6], self.acc[6:9], 3, self.lam_i, self.lam_t, 1.0, 1.0 / b_global,
                           self.loss_tail, beta_dev=self.beta_dev)
 

@@ -271,7 +271,8 @@ class FashionMVAETrainer(MnistMVAETrainer):
         self._join()
         # ---- last layers: convT2 (image) and net.6 (text)
         direct = self.direct_c1_bwd
-        ops.colsum_accumulate(self.logit_t, g["text_decoder.net.6.bias"])
+        with self._fork():          # bias gradients are read by the optimizer only: beside the GEMMs, joined at the end
+            ops.colsum_accumulate(self.logit_t, g["text_decoder.net.6.bias"])
         txt_last = [
             ops.gemm_desc(self.logit_t, self.td_h[2], g["text_decoder.net.6.weight"], 10, 512, 2 * B, a_mn=True, b_mn=True,
                           split_k=split_for(2 * B), accumulate=True),
@@ -304,7 +305,8 @@ class FashionMVAETrainer(MnistMVAETrainer):
             ops.gemm_desc(self.td_dA[0], p["text_decoder.net.4.weight"], self.td_dA[1], 2 * B, 512, 512, b_mn=True,
                           aux=self.td_a[1], epilogue=ops.EPI_MUL_DSWISH, colsum=g["text_decoder.net.2.bias"])], P)
         # ---- upsampler.2 (image) and net.2 (text)
-        ops.colsum_accumulate(self.d_u2, g["image_decoder.upsampler.2.bias"])
+        with self._fork():
+            ops.colsum_accumulate(self.d_u2, g["image_decoder.upsampler.2.bias"])
         self._gemm([
             ops.gemm_desc(self.d_u2, self.u1_h, g["image_decoder.upsampler.2.weight"], 6272, 512, 2 * B, a_mn=True, b_mn=True,
                           split_k=split_for(2 * B), accumulate=True),
@@ -330,9 +332,10 @@ class FashionMVAETrainer(MnistMVAETrainer):
                     training=training, noise=self.noise if training else None, kl_scale_dev=self.beta_dev, gather=gather)
         lt = self.label_table
         # ---- encoders backward: heads
-        ops.colsum_accumulate(self.d_enc_i, g["image_encoder.classifier.2.bias"])
-        if not lt:
-            ops.colsum_accumulate(self.d_enc_t, g["text_encoder.net.4.bias"])
+        with self._fork():
+            ops.colsum_accumulate(self.d_enc_i, g["image_encoder.classifier.2.bias"])
+            if not lt:
+                ops.colsum_accumulate(self.d_enc_t, g["text_encoder.net.4.bias"])
         ops.gemm_batch([
             ops.gemm_desc(self.d_enc_i, self.fc_h, g["image_encoder.classifier.2.weight"], 2 * L, 512, B, a_mn=True, b_mn=True,
                           split_k=split_for(B), accumulate=True),
