@@ -349,9 +349,6 @@ def bench_workload(args, wl: str, steps: int, dev, prec, rank: int, local_rank: 
         # public host-fed API: pinned host batch -> (copy stream) -> device, step, loss read back on the host every
         # call (one step lagged, as in any asynchronous training loop); flush() at the end of the timed region
         im, ot = host[i % npool]
-        if c19:      # the 19-expert flavour re-plans its passes on the host every step: synchronous public API
-            e2e_losses.append(tr.step(im, ot, annealing_factor=annealing(i), sync=True))
-            return
         v = tr.step_pipelined(im, ot, annealing_factor=annealing(i))
         if v is not None:
             e2e_losses.append(v)
@@ -458,11 +455,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        **({"gemm_chain": main["chain"]} if wl == "mnist" else {})},
             "clocks": main["clocks"],
             "e2e": {"value": main["e2e_value"], "unit": "samples/s", "ms_per_step": main["e2e_ms_per_step"],
-                    "h2d_bytes_per_step": main["h2d_bytes_per_step"], "d2h_bytes_per_step": 16,
+                    "h2d_bytes_per_step": main["h2d_bytes_per_step"], "d2h_bytes_per_step": 4 if wl == "celeba19" else 16,
                     "losses_read": main["losses_read"],
-                    "note": ("trainer.step(pinned host image NCHW, pinned host attrs): H2D + NCHW->NHWC staging + step + loss "
-                             "read back synchronously every step" if wl == "celeba19" else
-                             "trainer.step_pipelined(pinned host image, pinned host labels/attrs): H2D of batch i+1 on a copy "
+                    "note": ("trainer.step_pipelined(pinned host image, pinned host labels/attrs): H2D of batch i+1 on a copy "
                              "stream overlaps step i; the loss is copied D2H and read on the host every step (one step lagged)")},
             "gpu_launches": main["launches"],
             "roofline": {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 kind::tf32; all GEMM launches of a step)",

@@ -240,6 +240,20 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
         """noise: optional [P,B,L] in the REFERENCE's pass order; drop_masks: optional [n_img,B,512] in the reference's
         call order of the image-containing passes (joint, image-only, sampled...)."""
         B, L = self.B, self.L
+        plan = self._sample_plan(combos)
+        with torch.cuda.stream(self._stream):
+            self.x_nchw.copy_(image.reshape(B, 3 * 4096), non_blocking=True)
+            a = attrs.reshape(B, N_ATTRS).to(self.dev, non_blocking=True)
+            self._stage_and_enqueue(plan, self.x_nchw, a, annealing_factor, noise, drop_masks, training, update)
+        if sync:
+            self._stream.synchronize()
+            self.check_device_errors()
+            return float(self.loss19.item())
+        return None
+
+    def _sample_plan(self, combos):
+        """The step's pass structure: the sampled attribute subsets (celeba19/train.py:240-309; one draw per GLOBAL batch --
+        rank 0's wins) and the plan of stacked passes built from them."""
         if combos is None:
             combos = sample_combinations(19, self.approx_m) if self.approx_m > 0 else np.zeros((0, 19), dtype=bool)
             if self.world > 1 and self.approx_m > 0:     # one global batch = one set of subsets: rank 0's draw wins
@@ -252,34 +266,84 @@ class CelebA19MVAETrainer(CelebAMVAETrainer):
             raise _lib.MvaeError(f"expected {self.approx_m} sampled combinations, got {len(combos)}")
         plan = self._plan(combos)
         self._last_plan = plan
+        return plan
+
+    def _stage_and_enqueue(self, plan, img_nchw, a, annealing_factor, noise, drop_masks, training, update,
+                           staged: Optional[torch.cuda.Event] = None) -> None:
+        """(on the step stream) device-side staging of one batch -- NCHW -> NHWC, the attribute columns -- and the step's
+        launches.  ``img_nchw`` [B, 3*4096] and ``a`` [B, 18] are device tensors; ``staged`` is recorded once they have
+        been read (the pipelined path re-uses them for the upload after next)."""
+        B, L = self.B, self.L
+        ops.nchw_to_nhwc(img_nchw, self.x, B, 3, 4096)
+        self.attrs_t.copy_(a.t().to(torch.float32)); self.attrs_idx.copy_(a.t().to(torch.int64))
+        if staged is not None:
+            staged.record(self._stream)
+        if noise is not None:
+            nz = self.noise.view(self.P, B, L)
+            for ip, r in enumerate(plan["order"]):
+                nz[ip].copy_(noise[r], non_blocking=True)
+        if drop_masks is not None:
+            for call_i, ip in enumerate(plan["img_call_order"]):
+                self.drop_mask[ip * B:(ip + 1) * B].copy_(drop_masks[call_i], non_blocking=True)
+        for k in ("rowidx", "term_idx", "term_w"):
+            plan[k + "_dev"] = torch.as_tensor(plan[k], device=self.dev)
+        n0 = _lib.launch_count()
+        self._enqueue(plan, training, noise is not None, drop_masks is not None, float(annealing_factor), update)
+        self.launches_per_step = _lib.launch_count() - n0
+        if training and update:
+            for p in _IMG_BN:
+                self.num_batches_tracked[p] += plan["n_img"] if p.startswith("image_encoder") else plan["P"]
+
+    def step_pipelined(self, image, attrs, annealing_factor: float = 1.0, training: bool = True, update: bool = True):
+        """``step`` for HOST batches with the upload on a copy stream (it overlaps the previous step's kernels) and the loss
+        read back one call late, like the other flavours' ``step_pipelined``; the pass structure is still re-planned on the
+        host every call (the sampled subsets change the launches), which the asynchronous launches hide behind the
+        previous step.  Returns the PREVIOUS call's loss (None on the first call); ``flush()`` returns the last one."""
+        B = self.B
+        if not hasattr(self, "_pipe"):
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._pipe = [{"img": torch.empty(B, 3 * 4096, dtype=torch.float32, device=self.dev),
+                           "oth": torch.empty(B, N_ATTRS, dtype=torch.float32, device=self.dev),
+                           "loss": torch.zeros(1, dtype=torch.float32).pin_memory(),
+                           "up": torch.cuda.Event(), "free": torch.cuda.Event(), "done": torch.cuda.Event(), "busy": False}
+                          for _ in range(2)]
+            for slot in self._pipe:
+                slot["free"].record(self._stream)
+            self._pipe_idx = 0
+        k = self._pipe_idx
+        self._pipe_idx ^= 1
+        cur, prev = self._pipe[k], self._pipe[k ^ 1]
+        plan = self._sample_plan(None)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(cur["free"])            # the step stream finished reading this staging slot
+            cur["img"].copy_(image.reshape(B, 3 * 4096), non_blocking=True)
+            cur["oth"].copy_(attrs.reshape(B, N_ATTRS), non_blocking=True)
+            cur["up"].record(self._copy_stream)
         with torch.cuda.stream(self._stream):
-            self.x_nchw.copy_(image.reshape(B, 3 * 4096), non_blocking=True)
-            ops.nchw_to_nhwc(self.x_nchw, self.x, B, 3, 4096)
-            a = attrs.reshape(B, N_ATTRS).to(self.dev, non_blocking=True)
-            self.attrs_t.copy_(a.t().to(torch.float32)); self.attrs_idx.copy_(a.t().to(torch.int64))
-            if noise is not None:
-                nz = self.noise.view(self.P, B, L)
-                for ip, r in enumerate(plan["order"]):
-                    nz[ip].copy_(noise[r], non_blocking=True)
-            if drop_masks is not None:
-                for call_i, ip in enumerate(plan["img_call_order"]):
-                    self.drop_mask[ip * B:(ip + 1) * B].copy_(drop_masks[call_i], non_blocking=True)
-            for k in ("rowidx", "term_idx", "term_w"):
-                plan[k + "_dev"] = torch.as_tensor(plan[k], device=self.dev)
-            n0 = _lib.launch_count()
-            self._enqueue(plan, training, noise is not None, drop_masks is not None, float(annealing_factor), update)
-            self.launches_per_step = _lib.launch_count() - n0
-            if training and update:
-                for p in _IMG_BN:
-                    self.num_batches_tracked[p] += plan["n_img"] if p.startswith("image_encoder") else plan["P"]
-        if sync:
-            self._stream.synchronize()
-            self.check_device_errors()
-            return float(self.loss19.item())
+            self._stream.wait_event(cur["up"])
+            self._stage_and_enqueue(plan, cur["img"], cur["oth"], annealing_factor, None, None, training, update,
+                                    staged=cur["free"])
+            cur["loss"].copy_(self.loss19.reshape(1), non_blocking=True)
+            cur["done"].record(self._stream)
+        cur["busy"] = True
+        if prev["busy"]:
+            prev["done"].synchronize()
+            prev["busy"] = False
+            return float(prev["loss"][0])
         return None
 
-    def step_pipelined(self, *a, **k):  # pragma: no cover
-        raise _lib.MvaeError("step_pipelined: the 19-expert flavour re-plans its passes on the host every step; use step()")
+    def flush(self):
+        """Wait for the in-flight pipelined step and return its loss."""
+        out = None
+        if hasattr(self, "_pipe"):
+            for slot in (self._pipe[self._pipe_idx], self._pipe[self._pipe_idx ^ 1]):
+                if slot["busy"]:
+                    slot["done"].synchronize()
+                    slot["busy"] = False
+                    out = float(slot["loss"][0])
+        self._stream.synchronize()
+        self.check_device_errors()
+        return out
 
     def losses(self):
         """Per-pass ELBO terms in the reference's order (after a synchronised step)."""

@@ -143,3 +143,29 @@ def test_celeba19_eval_mode_matches_oracle_fp64():
     sd = tr.state_dict()
     for k, v in bufs.items():
         assert torch.equal(sd[k].cpu(), st[k]), k
+
+
+def test_pipelined_host_fed_steps_equal_synchronous_steps():
+    """step_pipelined (upload of batch i+1 on a copy stream, loss read one call late) == step on the same batches and the
+    same sampled subsets (numpy's global stream, re-seeded), eval mode (no noise / masks)."""
+    B = 8
+    rs = np.random.RandomState(12)
+    batches = [(torch.from_numpy(rs.uniform(0, 1, (B, 3, 64, 64)).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rs.randint(0, 2, (B, 18)).astype(np.float32)).pin_memory()) for _ in range(4)]
+    a = _trainer(B, 2)
+    b = _trainer(B, 2)
+    b.load_state_dict(a.state_dict())
+    np.random.seed(5)
+    ref = [a.step(im, at, annealing_factor=0.5, training=False) for im, at in batches]
+    np.random.seed(5)
+    got = []
+    for im, at in batches:
+        v = b.step_pipelined(im, at, annealing_factor=0.5, training=False)
+        if v is not None:
+            got.append(v)
+    got.append(b.flush())
+    assert len(got) == len(ref)
+    for x, y in zip(ref, got):
+        assert abs(x - y) <= 2e-6 * abs(x), (ref, got)
+    for k in a.params:   # (several Adam steps on atomically-summed gradients: equal up to a small fraction of lr per step)
+        assert (a.params[k] - b.params[k]).abs().max().item() <= 1e-4, k
