@@ -305,11 +305,14 @@ class MnistMVAETrainer:
         if not self.overlap:
             return contextlib.nullcontext()
         self._side_stream.wait_stream(torch.cuda.current_stream())
+        self._forked = True
         return torch.cuda.stream(self._side_stream)
 
     def _join(self) -> None:
-        if self.overlap:
+        # (only after a fork: waiting on a side stream that holds no work of THIS capture is a capture-isolation error)
+        if self.overlap and getattr(self, "_forked", False):
             torch.cuda.current_stream().wait_stream(self._side_stream)
+            self._forked = False
 
     def _side_mark(self):
         """Inside a ``_fork()`` block: an event after the side-stream work enqueued so far, for ``_wait_mark`` -- the step

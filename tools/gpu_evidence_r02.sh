@@ -3,7 +3,7 @@
 # reference arm, the ncu launch list of a bench step, `ncu --set full` captures of the dominant GEMM launches and of the fused
 # PoE / BCE kernels at roofline size.  Summaries are copied to profiles/ by hand afterwards (gpurun_out/ is scratch).
 mkdir -p gpurun_out
-O=gpurun_out/ev3
+O=gpurun_out/ev4
 ( time timeout 1500 python -m pytest tests -m gpu -q --timeout 900 ) > ${O}_pytest.log 2>&1
 echo "pytest rc=$?" >> ${O}_pytest.log; tail -4 ${O}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > ${O}_smoke.log 2>&1; tail -2 ${O}_smoke.log
@@ -14,10 +14,10 @@ timeout 400 python bench.py --workload celeba --steps 20 > ${O}_bench_celeba.jso
 timeout 400 python bench.py --workload celeba19 --steps 10 > ${O}_bench_celeba19.json 2> ${O}_bench_celeba19.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${O}_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-extras > ${O}_ncu_bench.log 2>&1
 # (GEMM chain capture: profiles/r02_gemm_chain_raw_key_metrics.txt, unchanged kernels)
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"poe_(fwd|bwd)_fast" -s 4 -c 2 -o ${O}_poe -f python tools/profile_step.py poe 262144 64 4 > ${O}_ncu_poe.log 2>&1
+# (PoE capture: profiles/r02_poe_v2_raw_key_metrics.txt)
 # (BCE capture: profiles/r02_bce_raw_key_metrics.txt, unchanged kernel)
-for r in poe; do ncu -i ${O}_${r}.ncu-rep --page details --csv > ${O}_${r}_details.csv 2>/dev/null; ncu -i ${O}_${r}.ncu-rep --page raw --csv > ${O}_${r}_raw.csv 2>/dev/null; done
-ls -la gpurun_out/ev3_*.ncu-rep; tail -3 ${O}_bench_celeba19.err
+
+tail -3 ${O}_bench_celeba19.err
 for f in ${O}_bench_*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
