@@ -3,6 +3,8 @@
 #include <atomic>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/mvae_b200.h"
 
@@ -20,6 +22,10 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+bool pdl_enabled() {   // read at every launch (a getenv, no caching): tests and A/B runs flip it inside one process
+  const char* v = getenv("MVAE_PDL");
+  return v == nullptr || strcmp(v, "0") != 0;
+}
 }  // namespace mvae
 
 extern "C" int mvae_version(void) { return 100; }

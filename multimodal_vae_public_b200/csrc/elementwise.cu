@@ -198,6 +198,7 @@ constexpr int kFastPasses = 4;   // passes whose KL partial sums a thread keeps 
 // atomics serialised in L2 at roofline size (16 K blocks x 3 passes on 3 addresses).
 template <int EMAX>
 __global__ void __launch_bounds__(256, 3) poe_fwd_fast_kernel(const __grid_constant__ PoeArgs a) {
+  pdl_prologue();
   __shared__ double scratch[32];
   const int l4n = a.L >> 2;
   const int64_t total = static_cast<int64_t>(a.B) * l4n;
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(256, 3) poe_fwd_fast_kernel(const __grid_const
 
 template <int EMAX>
 __global__ void __launch_bounds__(256, 3) poe_bwd_fast_kernel(const __grid_constant__ PoeArgs a) {
+  pdl_prologue();
   const int l4n = a.L >> 2;
   const int64_t total = static_cast<int64_t>(a.B) * l4n;
   const float e1 = 1e-8f;
@@ -384,6 +386,7 @@ __global__ void __launch_bounds__(256, 3) poe_bwd_fast_kernel(const __grid_const
 // reused by every pass.
 template <int VEC, int EMAX>
 __global__ void __launch_bounds__(256) poe_fwd_kernel(const __grid_constant__ PoeArgs a) {
+  pdl_prologue();
   __shared__ double scratch[32];
   const int lv_per_row = a.L / VEC;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -461,6 +464,7 @@ __global__ void __launch_bounds__(256) poe_fwd_kernel(const __grid_constant__ Po
 
 template <int VEC, int EMAX>
 __global__ void __launch_bounds__(256) poe_bwd_kernel(const __grid_constant__ PoeArgs a) {
+  pdl_prologue();
   const int lv_per_row = a.L / VEC;
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= static_cast<int64_t>(a.B) * lv_per_row) return;
@@ -598,6 +602,7 @@ __global__ void __launch_bounds__(256, kBceUnroll == 4 ? 4 : 2) bce_kernel(const
                                                      int ldt, int t_rows, float* dx, int lddx, int R, int D4,
                                                      float scale, double* loss_acc, int seg_rows, float* loss_elem,
                                                      int ldl, int slabs) {
+  pdl_prologue();
   __shared__ double scratch[32];
   __shared__ int seg_smem;
   const unsigned n4 = static_cast<unsigned>(R) * static_cast<unsigned>(D4);
@@ -660,6 +665,7 @@ template <int COPIES>
 __global__ void __launch_bounds__(256, 4) bce_stacked_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ t,
                                                              int ldt, int t_rows, float* dx, int lddx, int D4, float scale,
                                                              double* loss_acc) {
+  pdl_prologue();
   __shared__ double scratch[32];
   const unsigned n4 = static_cast<unsigned>(t_rows) * static_cast<unsigned>(D4);
   double acc[COPIES];
@@ -727,6 +733,7 @@ __global__ void __launch_bounds__(256) bce_rows_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ x, int64_t ldx, const int64_t* __restrict__ target,
                                                  int t_rows, float* dx, int64_t lddx, int R, int K, float scale,
                                                  double* loss_acc, int seg_rows, float* loss_rows, int64_t ldl) {
+  pdl_prologue();
   __shared__ double scratch[32];
   __shared__ int seg_smem;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -760,6 +767,7 @@ __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ x, in
 // block = 32 columns x 8 row lanes; grid.x = column blocks, grid.y = row chunks of kColsumRows.
 constexpr int kColsumRows = 256;
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int64_t ld, float* db, int M, int N) {
+  pdl_prologue();
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
@@ -856,6 +864,7 @@ __global__ void __launch_bounds__(128) emb_swish_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* __restrict__ g, float* m, float* v, int64_t n,
                                                    float lr, const float* lr_mult_dev, float beta1, float beta2,
                                                    float eps, float grad_scale, const int32_t* step_count) {
+  pdl_prologue();
   // bias corrections: one double-precision pow per BLOCK (thread 0), broadcast through shared memory
   __shared__ float s_step_size, s_inv_sqrt_bc2;
   if (threadIdx.x == 0) {
@@ -901,11 +910,15 @@ __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* __rest
     }
   }
 }
-__global__ void step_inc_kernel(int32_t* step_count) { *step_count += 1; }
+__global__ void step_inc_kernel(int32_t* step_count) {
+  pdl_prologue();
+  *step_count += 1;
+}
 
 __global__ void elbo_finalize_kernel(const double* recon_img, const double* recon_txt, const double* kl, int P,
                                      float lambda_image, float lambda_text, float beta, const float* beta_dev,
                                      float inv_batch, float* out) {
+  pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double b = static_cast<double>(beta) * (beta_dev ? static_cast<double>(*beta_dev) : 1.0);
   double tot = 0.0;
@@ -993,14 +1006,14 @@ extern "C" int mvae_poe_fwd_g(const float* const* mu_e, const float* const* lv_e
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (vec4_ok(a, false) && P <= kFastPasses && !getenv("MVAE_POE_SLOW")) {
     const int64_t n = static_cast<int64_t>(B) * (L / 4);
-    if (E <= 2) poe_fwd_fast_kernel<2><<<fast_grid(n), 256, 0, st>>>(a);
-    else poe_fwd_fast_kernel<4><<<fast_grid(n), 256, 0, st>>>(a);
+    if (E <= 2) launch_pdl(poe_fwd_fast_kernel<2>, dim3(fast_grid(n)), dim3(256), 0, st, a);
+    else launch_pdl(poe_fwd_fast_kernel<4>, dim3(fast_grid(n)), dim3(256), 0, st, a);
   } else if (vec4_ok(a, false)) {
     const int64_t n = static_cast<int64_t>(B) * (L / 4);
-    poe_fwd_kernel<4, 4><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a);
+    launch_pdl(poe_fwd_kernel<4, 4>, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, a);
   } else {
     const int64_t n = static_cast<int64_t>(B) * L;
-    poe_fwd_kernel<1, kMaxExperts><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a);
+    launch_pdl(poe_fwd_kernel<1, kMaxExperts>, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, a);
   }
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
@@ -1035,14 +1048,14 @@ extern "C" int mvae_poe_bwd_g(const float* const* mu_e, const float* const* lv_e
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (vec4_ok(a, true) && P <= kFastPasses && !getenv("MVAE_POE_SLOW")) {
     const int64_t n = static_cast<int64_t>(B) * (L / 4);
-    if (E <= 2) poe_bwd_fast_kernel<2><<<fast_grid(n), 256, 0, st>>>(a);
-    else poe_bwd_fast_kernel<4><<<fast_grid(n), 256, 0, st>>>(a);
+    if (E <= 2) launch_pdl(poe_bwd_fast_kernel<2>, dim3(fast_grid(n)), dim3(256), 0, st, a);
+    else launch_pdl(poe_bwd_fast_kernel<4>, dim3(fast_grid(n)), dim3(256), 0, st, a);
   } else if (vec4_ok(a, true)) {
     const int64_t n = static_cast<int64_t>(B) * (L / 4);
-    poe_bwd_kernel<4, 4><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a);
+    launch_pdl(poe_bwd_kernel<4, 4>, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, a);
   } else {
     const int64_t n = static_cast<int64_t>(B) * L;
-    poe_bwd_kernel<1, kMaxExperts><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(a);
+    launch_pdl(poe_bwd_kernel<1, kMaxExperts>, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, a);
   }
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
@@ -1105,11 +1118,11 @@ extern "C" int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float*
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const unsigned gb = static_cast<unsigned>(blocks);
     if (copies == 2)
-      bce_stacked_kernel<2><<<gb, 256, 0, st>>>(x, (int)ldx, t, (int)ldt, t_rows, dx, (int)lddx, D / 4, scale, loss_acc);
+      launch_pdl(bce_stacked_kernel<2>, dim3(gb), dim3(256), 0, st, x, (int)ldx, t, (int)ldt, t_rows, dx, (int)lddx, D / 4, scale, loss_acc);
     else if (copies == 3)
-      bce_stacked_kernel<3><<<gb, 256, 0, st>>>(x, (int)ldx, t, (int)ldt, t_rows, dx, (int)lddx, D / 4, scale, loss_acc);
+      launch_pdl(bce_stacked_kernel<3>, dim3(gb), dim3(256), 0, st, x, (int)ldx, t, (int)ldt, t_rows, dx, (int)lddx, D / 4, scale, loss_acc);
     else
-      bce_stacked_kernel<4><<<gb, 256, 0, st>>>(x, (int)ldx, t, (int)ldt, t_rows, dx, (int)lddx, D / 4, scale, loss_acc);
+      launch_pdl(bce_stacked_kernel<4>, dim3(gb), dim3(256), 0, st, x, (int)ldx, t, (int)ldt, t_rows, dx, (int)lddx, D / 4, scale, loss_acc);
     count_launch();
     MVAE_CUDA_CHECK(cudaGetLastError());
     return MVAE_OK;
@@ -1126,11 +1139,11 @@ extern "C" int mvae_bce_logits_fwd_bwd(const float* x, int64_t ldx, const float*
   slabs = slabs < 1 ? 1 : (slabs > 16 ? 16 : slabs);
   const int64_t blocks = (nslabs + slabs - 1) / slabs;
   if (unroll == 8)
-    bce_kernel<8><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(bce_kernel<8>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
         x, static_cast<int>(ldx), t, static_cast<int>(ldt), t_rows, dx, static_cast<int>(lddx), R, D / 4, scale, loss_acc,
         seg_rows, loss_elem, static_cast<int>(ldl), slabs);
   else
-    bce_kernel<4><<<static_cast<unsigned>(blocks), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    launch_pdl(bce_kernel<4>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
         x, static_cast<int>(ldx), t, static_cast<int>(ldt), t_rows, dx, static_cast<int>(lddx), R, D / 4, scale, loss_acc,
         seg_rows, loss_elem, static_cast<int>(ldl), slabs);
   count_launch();
@@ -1143,7 +1156,7 @@ extern "C" int mvae_ce_fwd_bwd(const float* x, int64_t ldx, const int64_t* targe
                                float* loss_rows, int64_t ldl, void* stream) {
   if (!x || !target || R < 1 || K < 1 || t_rows < 1) return set_error(MVAE_ERR_BAD_ARG, "ce: bad pointers/shape");
   if (seg_rows < 1) seg_rows = R;
-  ce_kernel<<<(R + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, ldx, target, t_rows, dx, lddx, R,
+  launch_pdl(ce_kernel, dim3((R + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), x, ldx, target, t_rows, dx, lddx, R,
                                                                                   K, scale, loss_acc, seg_rows, loss_rows, ldl);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
@@ -1153,7 +1166,7 @@ extern "C" int mvae_ce_fwd_bwd(const float* x, int64_t ldx, const int64_t* targe
 extern "C" int mvae_colsum_accumulate(const float* dy, int64_t lddy, float* db, int M, int N, void* stream) {
   if (!dy || !db || M < 1 || N < 1) return set_error(MVAE_ERR_BAD_ARG, "colsum: bad pointers/shape");
   dim3 grid((N + 31) / 32, (M + kColsumRows - 1) / kColsumRows);
-  colsum_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, lddy, db, M, N);
+  launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), dy, lddy, db, M, N);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
@@ -1212,9 +1225,9 @@ extern "C" int mvae_adam_flat(float* p, const float* g, float* m, float* v, int6
     return set_error(MVAE_ERR_UNSUPPORTED, "adam: buffers must be 16B aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int64_t n4 = (n + 3) / 4;
-  adam_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(p, g, m, v, n, lr, lr_mult_dev, beta1, beta2, eps,
+  launch_pdl(adam_kernel, dim3(static_cast<unsigned>((n4 + 255) / 256)), dim3(256), 0, st, p, g, m, v, n, lr, lr_mult_dev, beta1, beta2, eps,
                                                                         grad_scale, step_count);
-  step_inc_kernel<<<1, 1, 0, st>>>(step_count);
+  launch_pdl(step_inc_kernel, dim3(1), dim3(1), 0, st, step_count);
   count_launch(2);
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
@@ -1251,7 +1264,7 @@ extern "C" int mvae_elbo_finalize(const double* recon_img, const double* recon_t
                                   float lambda_image, float lambda_text, float beta, const float* beta_dev,
                                   float inv_batch, float* out, void* stream) {
   if (!out || P < 1 || P > kMaxPasses) return set_error(MVAE_ERR_BAD_ARG, "elbo_finalize: bad args");
-  elbo_finalize_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(recon_img, recon_txt, kl, P, lambda_image,
+  launch_pdl(elbo_finalize_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream), recon_img, recon_txt, kl, P, lambda_image,
                                                                               lambda_text, beta, beta_dev, inv_batch, out);
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());

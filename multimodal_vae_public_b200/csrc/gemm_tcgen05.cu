@@ -600,6 +600,7 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
+  pdl_trigger();   // the next kernel of the stream may be scheduled as soon as every CTA of this one is resident (common.h)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -638,6 +639,7 @@ __device__ __forceinline__ void gemm_body(const GemmBatch& batch) {
   if (kPair) ptx::cluster_sync_all();   // also: the peer's barriers are initialised before anyone arrives on them
   else __syncthreads();
   ptx::tc_fence_after();
+  pdl_wait();      // everything above ran beside the predecessor's tail; from here on its results are complete and visible
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
@@ -1552,7 +1554,10 @@ int launch_problems(const char* who, const mvae_gemm_desc* descs, const int32_t*
       MVAE_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr_done[split3 ? 1 : 0][extra] = true;
     }
-    kern<<<grid, threads, smem, st>>>(batch);
+    // programmatic dependent launch: this kernel's prologue (barrier init, TMEM allocation, tensor-map prefetch) and its
+    // launch latency overlap the tail of the preceding kernel; gemm_body waits (griddepcontrol.wait) before it touches
+    // global memory (common.h)
+    launch_pdl(kern, dim3(grid), dim3(threads), static_cast<size_t>(smem), st, batch);
   }
   count_launch();
   MVAE_CUDA_CHECK(cudaGetLastError());

@@ -78,6 +78,7 @@ template <bool kSwishIn>
 __global__ void __launch_bounds__(256) rows_linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
                                                           const float* __restrict__ bias, float* __restrict__ out,
                                                           float* __restrict__ out2, int V, int D, int N) {
+  pdl_prologue();
   extern __shared__ __align__(16) float s_in[];   // [V][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256) rows_linear_bwd_kernel(const float* __res
                                                               const float* __restrict__ pre, const float* __restrict__ W,
                                                               float* __restrict__ dW, float* __restrict__ db,
                                                               float* __restrict__ dx, int V, int D, int N, int gw) {
+  pdl_prologue();
   extern __shared__ __align__(16) float smem[];
   float* s_dy = smem;             // [V][N]
   float* s_x = smem + V * N;      // [V][D]   (dW blocks only)
@@ -245,8 +247,8 @@ extern "C" int mvae_label_table_fwd(const float* emb, const float* w2, const flo
   const size_t smem = static_cast<size_t>(V) * D * sizeof(float);
   if (smem > 48 * 1024 || V * D > 8 * 256 * 4)
     return set_error(MVAE_ERR_UNSUPPORTED, "label_table_fwd: V*D too large (<= 8192 floats)");
-  rows_linear_kernel<true><<<(D + 7) / 8, 256, smem, st>>>(emb, w2, b2, a2, h2, V, D, D);
-  rows_linear_kernel<false><<<(N3 + 7) / 8, 256, smem, st>>>(h2, w3, b3, tab, nullptr, V, D, N3);
+  launch_pdl(rows_linear_kernel<true>, dim3((D + 7) / 8), dim3(256), smem, st, emb, w2, b2, a2, h2, V, D, D);
+  launch_pdl(rows_linear_kernel<false>, dim3((N3 + 7) / 8), dim3(256), smem, st, h2, w3, b3, tab, static_cast<float*>(nullptr), V, D, N3);
   count_launch(2);
   MVAE_CUDA_CHECK(cudaGetLastError());
   return MVAE_OK;
@@ -267,7 +269,7 @@ extern "C" int mvae_label_table_bwd(const float* emb, const float* w2, const flo
     const int gw = (N3 + kWRows - 1) / kWRows, gx = ((N3 + kNChunk - 1) / kNChunk) * kblocks;
     const size_t smem = (static_cast<size_t>(V) * N3 + static_cast<size_t>(V) * D) * sizeof(float);
     if (smem > 48 * 1024) return set_error(MVAE_ERR_UNSUPPORTED, "label_table_bwd: V*(D+N3) too large for shared memory");
-    rows_linear_bwd_kernel<false><<<gw + gx, 256, smem, st>>>(dtab, h2, a2, w3, dw3, db3, d_a2, V, D, N3, gw);
+    launch_pdl(rows_linear_bwd_kernel<false>, dim3(gw + gx), dim3(256), smem, st, dtab, h2, a2, w3, dw3, db3, d_a2, V, D, N3, gw);
   }
   // stage 2: the hidden layer; its input is swish(embedding), the embedding gradient accumulates into d_emb (the caller's
   // gradient buffer, zeroed with the rest of the bucket)
@@ -275,7 +277,7 @@ extern "C" int mvae_label_table_bwd(const float* emb, const float* w2, const flo
     const int gw = (D + kWRows - 1) / kWRows, gx = ((D + kNChunk - 1) / kNChunk) * kblocks;
     const size_t smem = 2 * static_cast<size_t>(V) * D * sizeof(float);
     if (smem > 48 * 1024) return set_error(MVAE_ERR_UNSUPPORTED, "label_table_bwd: V*D too large for shared memory");
-    rows_linear_bwd_kernel<true><<<gw + gx, 256, smem, st>>>(d_a2, nullptr, emb, w2, dw2, db2, d_emb, V, D, D, gw);
+    launch_pdl(rows_linear_bwd_kernel<true>, dim3(gw + gx), dim3(256), smem, st, d_a2, static_cast<const float*>(nullptr), emb, w2, dw2, db2, d_emb, V, D, D, gw);
   }
   count_launch(2);
   MVAE_CUDA_CHECK(cudaGetLastError());
