@@ -18,7 +18,7 @@ void count_launch(int n = 1);
 // kernel's CTAs become resident early, `griddepcontrol.wait` blocks until every prerequisite grid has completed and its
 // memory is visible, so nothing is read or written early.  Both instructions are no-ops in a normally launched kernel,
 // and a normally launched kernel after a PDL kernel keeps the full stream-order dependency, so the two kinds mix freely.
-// MVAE_PDL=0 turns the launch attribute off (plain stream order everywhere).
+// The attribute is OPT-IN (MVAE_PDL=1): measured neutral to slightly negative at the BASELINE batch sizes (common.cu).
 bool pdl_enabled();
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

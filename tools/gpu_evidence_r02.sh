@@ -3,7 +3,7 @@
 # reference arm, the ncu launch list of a bench step, `ncu --set full` captures of the dominant GEMM launches and of the fused
 # PoE / BCE kernels at roofline size.  Summaries are copied to profiles/ by hand afterwards (gpurun_out/ is scratch).
 mkdir -p gpurun_out
-O=gpurun_out/ev4
+O=gpurun_out/ev5
 ( time timeout 1500 python -m pytest tests -m gpu -q --timeout 900 ) > ${O}_pytest.log 2>&1
 echo "pytest rc=$?" >> ${O}_pytest.log; tail -4 ${O}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > ${O}_smoke.log 2>&1; tail -2 ${O}_smoke.log
