@@ -283,6 +283,15 @@ def run_reference(args, rank: int, world: int):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def exchange_entry(m: dict) -> dict:
+    """Cost of the data-parallel exchange at this N: step time minus the time of the same per-GPU batch on one GPU."""
+    return {"mode": m["dp_mode"], "step_ms": m["ms_per_step"], "compute_only_ms": m["compute_only_ms"],
+            "exchange_ms": m["ms_per_step"] - m["compute_only_ms"], "per_gpu_batch": m["b_local"],
+            "how": "compute_only_ms = the same per-GPU batch stepped by a world-size-1 trainer (no exchange, plain fused Adam) "
+                   "on rank 0's GPU, CUDA events; exchange_ms = step_ms - compute_only_ms (includes the rank skew the "
+                   "exchange has to absorb)"}
+
+
 def make_trainer(wl: str, b_local: int, dev, prec, world: int, rank: int, no_graph: bool):
     w = WORKLOADS[wl]
     kw = dict(device=dev, lr=w["lr"], lambda_image=LAMBDA_IMAGE, precision=prec, world_size=world, rank=rank, seed=0)
@@ -389,6 +398,26 @@ def bench_workload(args, wl: str, steps: int, dev, prec, rank: int, local_rank: 
            "losses_read": len(e2e_losses), "clocks": clocks, "npool": npool, "trainer": tr, "steps": steps,
            "dp_mode": tr.dp_mode, "cuda_graph": bool(tr.use_graph), "chain": bool(getattr(tr, "chain", False)),
            "h2d_bytes_per_step": (b_local * (12288 + 18) * 4 + 4) if celeba else (b_local * (784 * 4 + 8) + 4)}
+    if world > 1 and not c19:
+        # What the exchange costs: the same per-GPU batch stepped by a world-size-1 trainer on this GPU (no exchange, plain
+        # fused Adam), timed locally -- no collective in this block, every rank does the same, any failure only drops
+        # the entry.  exchange_ms = step time at N GPUs - this.
+        try:
+            tr1 = make_trainer(wl, b_local, dev, prec, 1, 0, args.no_graph)
+            for i in range(max(args.warmup, 3) + 5):
+                tr1.step(pool[i % npool][0], pool[i % npool][1], annealing_factor=annealing(i), sync=False)
+            tr1.synchronize()
+            n1 = max(10, min(steps, 100))
+            s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s1.record(tr1._stream)
+            for i in range(n1):
+                tr1.step(pool[i % npool][0], pool[i % npool][1], annealing_factor=annealing(i), sync=False)
+            e1.record(tr1._stream)
+            tr1.synchronize()
+            out["compute_only_ms"] = s1.elapsed_time(e1) / n1
+            del tr1
+        except Exception as ex:  # noqa: BLE001  (informative entry only)
+            log(f"compute-only comparison skipped: {ex!r}")
     if with_rooflines:
         log("per-kernel roofline pass")
         out["roof"] = measure_rooflines(tr, dev, prec, wl, world, micro=micro)
@@ -477,6 +506,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "roofline_hbm": roof["hbm"],
             "kernel_breakdown_ms": roof["breakdown"],
         }
+        if "compute_only_ms" in main:
+            line["exchange"] = exchange_entry(main)
         for k in ("hbm_poe_fwd", "hbm_poe_bwd"):
             if k in roof:
                 line["roofline_" + k] = roof[k]
@@ -494,6 +525,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     "roofline": {"bound": "tensor", "achieved": a2, "peak": tf32_peak, "unit": "TFLOP/s", "frac": a2 / tf32_peak,
                                  "share_of_step": g2["ms_per_step"] / ex["ms_per_step"], "launches_per_step": g2["launches"]},
                     "kernel_breakdown_ms": ex["roof"]["breakdown"]}
+                if "compute_only_ms" in ex:
+                    line["extra"][name]["exchange"] = exchange_entry(ex)
         if world == 1 and not args.no_cpu_baseline:
             w = WORKLOADS[wl]
             cpu = cpu_baseline(wl, w["cpu_batch"], budget_s=12.0)
