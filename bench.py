@@ -192,6 +192,19 @@ def _reference_stepper(wl: str, device: str = "cpu"):
 _THREADS = {}
 
 
+def cpu_model() -> str:
+    """CPU model name of the box (the CPU baseline states core count and CPU model)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    import platform
+    return platform.processor() or "unknown CPU"
+
+
 def pick_threads(wl: str, step, data) -> tuple:
     """"All the host threads it can use": the box may expose 128 logical CPUs behind a much smaller cgroup quota, where
     128 intra-op threads are 100x SLOWER than 8.  Time the REAL step at the REAL sample batch (1 warm-up + 2 timed steps
@@ -234,7 +247,7 @@ def cpu_baseline(wl: str, batch: int, budget_s: float, steps: int | None = None)
     dt = time.perf_counter() - t0
     return {"value": batch * n / dt, "unit": "samples/s", "cores": cores, "kind": kind,
             "sample": f"{n} steps of B={batch} of the same workload in {dt:.1f}s, torch {torch.__version__} CPU fp32, "
-                      f"{cores} intra-op threads (fastest of {cands} on the real step; affinity mask {avail} CPUs)",
+                      f"{cores} intra-op threads (fastest of {cands} on the real step; affinity mask {avail} CPUs; {cpu_model()})",
             "ms_per_step": 1e3 * dt / n, "batch": batch}
 
 
