@@ -37,3 +37,15 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_other_ranks_stay_silent():
     r = _run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_exchange_entry_shape():
+    """bench.py's per-N exchange cost entry (N > 1): step time minus the same per-GPU batch on a world-size-1 trainer."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    e = bench.exchange_entry({"dp_mode": "p2p", "ms_per_step": 0.42, "compute_only_ms": 0.32, "b_local": 512})
+    assert e["mode"] == "p2p" and e["per_gpu_batch"] == 512
+    assert abs(e["exchange_ms"] - 0.10) < 1e-9 and e["step_ms"] == 0.42 and e["compute_only_ms"] == 0.32
+    assert "Intel" in bench.cpu_model() or len(bench.cpu_model()) > 0
